@@ -1,0 +1,342 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (TEST INFRASTRUCTURE).
+
+Run in the build container only (needs /root/reference):
+
+    python oracle/make_golden.py
+
+The reference's viabel/*.py files are imported as they lie under /root/reference;
+`autograd`, `paragami` and `pystan` (absent from the image) are replaced by the
+stand-ins in oracle/refshim (torch float64 provides the reverse-mode AD that autograd
+would).  viabel/_psis.py and viabel/diagnostics.py need numpy only and run untouched.
+
+Every RandomState draw the reference makes is recorded, so the goldens carry the
+base draws (eps / t / (chi2, z)) next to the outputs: parity is by draw injection.
+"""
+import math
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'refshim'))
+sys.path.insert(1, '/root/reference')
+
+import numpy as np  # noqa: E402
+
+import autograd.numpy as anp  # noqa: E402
+import autograd.numpy.random as shim_random  # noqa: E402
+from autograd.scipy.stats import norm as anorm  # noqa: E402
+from autograd.scipy.stats import t as at_dist  # noqa: E402
+from autograd.scipy.special import gammaln as agammaln  # noqa: E402,F401
+
+import viabel  # noqa: E402
+from viabel import _psis as ref_psis  # noqa: E402
+from viabel import diagnostics as ref_diag  # noqa: E402
+from viabel.approximations import MFGaussian, MFStudentT, MultivariateT  # noqa: E402
+from viabel.objectives import AlphaDivergence, ExclusiveKL  # noqa: E402
+from viabel.optimization import Adam, RMSProp  # noqa: E402
+
+OUT = os.path.join(HERE, '..', 'tests', 'golden')
+os.makedirs(OUT, exist_ok=True)
+
+
+# ---------------------------------------------------------------------------
+# synthetic problems (shared with tests/_problems.py, which rebuilds them by seed)
+# ---------------------------------------------------------------------------
+sys.path.insert(0, os.path.join(HERE, '..', 'tests'))
+from _problems import (  # noqa: E402
+    diag_problem, hier_problem, logistic_problem, psis_case, PSIS_CASES, target_params)
+
+
+def logistic_log_p(X, y, prior_sd):
+    def f(theta):
+        z = anp.dot(theta, X.T) * y
+        d = X.shape[1]
+        return (-anp.sum(anp.logaddexp(0.0, -z), axis=1)
+                - 0.5 * anp.sum(theta ** 2, axis=1) / prior_sd ** 2
+                - d * math.log(prior_sd * math.sqrt(2 * math.pi)))
+    return f
+
+
+def probit_log_p(X, y, prior_sd):
+    def f(theta):
+        z = anp.dot(theta, X.T) * y
+        d = X.shape[1]
+        return (anp.sum(anorm.logcdf(z), axis=1)
+                - 0.5 * anp.sum(theta ** 2, axis=1) / prior_sd ** 2
+                - d * math.log(prior_sd * math.sqrt(2 * math.pi)))
+    return f
+
+
+def gauss_log_p(mean, sd):
+    return lambda x: anp.sum(anorm.logpdf(x, loc=mean, scale=sd), axis=1)
+
+
+def student_log_p(loc, scale, df):
+    return lambda x: anp.sum(at_dist.logpdf(x, df, loc, scale), axis=1)
+
+
+def hier_log_p(X, y, group, G, p):
+    N = X.shape[0]
+    onehot = np.zeros((N, G))
+    onehot[np.arange(N), group] = 1.0
+
+    def f(theta):
+        S = theta.shape[0]
+        beta = theta[:, :G * p].reshape((S, G, p))
+        m = theta[:, G * p:G * p + p]
+        ltau, lsig = theta[:, -2], theta[:, -1]
+        lp = 0.0
+        for g in range(G):
+            sel = group == g
+            pred = anp.dot(beta[:, g, :], X[sel].T)                 # [S, n_g]
+            lp = lp + anp.sum(anorm.logpdf(y[sel], pred, anp.exp(lsig)[:, None]), axis=1)
+            lp = lp + anp.sum(anorm.logpdf(beta[:, g, :], m, anp.exp(ltau)[:, None]), axis=1)
+        lp = lp + anp.sum(anorm.logpdf(m, 0.0, 10.0), axis=1)
+        lp = lp + anorm.logpdf(ltau, 0.0, 1.0) + anorm.logpdf(lsig, 0.0, 1.0)
+        return lp
+    return f
+
+
+class Recorder(object):
+    def __enter__(self):
+        shim_random.RECORD = []
+        return shim_random.RECORD
+
+    def __exit__(self, *a):
+        shim_random.RECORD = None
+
+
+def first_draws(rec, family):
+    """Base draws of the FIRST sample() call in a recording."""
+    if family == 'mvt':
+        assert rec[0][0] == 'chisquare' and rec[1][0] == 'randn'
+        return dict(chi2=rec[0][2], z=rec[1][2])
+    assert rec[0][0] in ('randn', 'standard_t')
+    return dict(base=rec[0][2])
+
+
+def make_family(kind, d, df, seed):
+    if kind == 'mfg':
+        return MFGaussian(d, seed=seed)
+    if kind == 'mft':
+        return MFStudentT(d, df, seed=seed)
+    return MultivariateT(d, df, seed=seed)
+
+
+def random_var_param(fam, kind, d, rs):
+    if kind == 'mvt':
+        B = rs.randn(d, d) * 0.4 + np.eye(d)
+        Sigma = B @ B.T + 0.3 * np.eye(d)
+        return fam._pattern.flatten(dict(mu=rs.randn(d), Sigma=Sigma))
+    return np.concatenate([rs.randn(d), 0.5 * rs.randn(d) - 0.5])
+
+
+# ---------------------------------------------------------------------------
+def gen_families():
+    out = {}
+    rs = np.random.RandomState(341)
+    for kind, df in (('mfg', None), ('mft', 20), ('mft', 5.5), ('mvt', 100), ('mvt', 7)):
+        for d in (1, 3, 8):
+            tag = '%s_df%s_d%d' % (kind, df, d)
+            fam = make_family(kind, d, df, seed=226)
+            vp = random_var_param(fam, kind, d, rs)
+            vp1 = random_var_param(fam, kind, d, rs)
+            with Recorder() as rec:
+                x = fam.sample(vp, 64)
+            for k, v in first_draws(rec, kind).items():
+                out[tag + '/' + k] = v
+            out[tag + '/var_param'] = vp
+            out[tag + '/var_param1'] = vp1
+            out[tag + '/init_param'] = fam.init_param()
+            out[tag + '/sample'] = x
+            out[tag + '/log_density'] = np.asarray(fam.log_density(vp, x))
+            out[tag + '/log_density_1d'] = np.asarray(fam.log_density(vp, x[0]))
+            out[tag + '/entropy'] = fam.entropy(vp)
+            if fam.supports_kl:
+                out[tag + '/kl'] = fam.kl(vp, vp1)
+            mean, cov = fam.mean_and_cov(vp)
+            out[tag + '/mean'] = mean
+            out[tag + '/cov'] = cov
+            for p in (2, 4):
+                if fam.supports_pth_moment(p):
+                    out[tag + '/moment%d' % p] = fam.pth_moment(vp, p)
+    np.savez_compressed(os.path.join(OUT, 'families.npz'), **out)
+    print('families: %d arrays' % len(out))
+
+
+def gen_objectives():
+    out = {}
+    rs = np.random.RandomState(851)
+    models = {}
+    X, y, _ = logistic_problem(60, 4, seed=11)
+    models['logistic_d4'] = (4, logistic_log_p(X, y, 10.0))
+    X, y, _ = logistic_problem(1000, 10, seed=12)
+    models['logistic_d10'] = (10, logistic_log_p(X, y, 10.0))
+    X, y, _ = logistic_problem(200, 6, seed=13)
+    models['probit_d6'] = (6, probit_log_p(X, y, 10.0))
+    mean, sd = target_params(5, seed=14)
+    models['gauss_d5'] = (5, gauss_log_p(mean, sd))
+    models['student_d5'] = (5, student_log_p(mean, sd, 10.0))
+    hp = hier_problem(G=3, p=2, n_per=7, seed=15)
+    models['hier_G3p2'] = (3 * 2 + 2 + 2, hier_log_p(hp['X'], hp['y'], hp['group'], 3, 2))
+
+    for mname, (d, logp) in models.items():
+        for kind, df in (('mfg', None), ('mft', 8), ('mvt', 9)):
+            fam = make_family(kind, d, df, seed=1214)
+            for point in ('init', 'rand'):
+                if point == 'init' and kind == 'mvt':
+                    continue        # Sigma = 10 I is degenerate for eigh's VJP
+                vp = fam.init_param() if point == 'init' else random_var_param(fam, kind, d, rs)
+                if mname.startswith('hier') and point == 'init':
+                    continue        # exp(log_sigma=2) draws overflow the likelihood scale
+                for S in (7,):
+                    objs = {'ekl': lambda: ExclusiveKL(fam, logp, S),
+                            'alpha2': lambda: AlphaDivergence(fam, logp, S, 2.0),
+                            'alpha1.5': lambda: AlphaDivergence(fam, logp, S, 1.5)}
+                    if kind != 'mvt':
+                        objs['ekl_path'] = lambda: ExclusiveKL(fam, logp, S, use_path_deriv=True)
+                    for oname, mk in objs.items():
+                        tag = '%s/%s_df%s/%s/%s' % (mname, kind, df, point, oname)
+                        obj = mk()
+                        np.random.seed(5039)
+                        with Recorder() as rec:
+                            value, grad = obj(vp)
+                        for k, v in first_draws(rec, kind).items():
+                            out[tag + '/' + k] = v
+                        out[tag + '/var_param'] = vp
+                        out[tag + '/value'] = float(value)
+                        out[tag + '/grad'] = grad
+    np.savez_compressed(os.path.join(OUT, 'objectives.npz'), **out)
+    print('objectives: %d arrays' % len(out))
+
+
+def gen_optimizers():
+    out = {}
+    rs = np.random.RandomState(153)
+    grads = rs.randn(6, 5) * np.array([1.0, 10.0, 0.1, 3.0, 1e-3])
+    out['grads'] = grads
+    for name, opt in (('rmsprop', RMSProp(0.01)), ('adam', Adam(0.01)),
+                      ('rmsprop_b', RMSProp(0.01, beta=0.5, jitter=1e-6)),
+                      ('adam_b', Adam(0.01, beta1=0.7, beta2=0.9, jitter=1e-6))):
+        dirs = []
+        for g in grads:
+            dirs.append(np.array(opt.descent_direction(g.copy()), copy=True))
+        out[name + '/dirs'] = np.array(dirs)
+
+    # a short full optimize() run on a deterministic quadratic objective
+    class Quad(object):
+        def __call__(self, vp):
+            return 0.5 * np.sum(vp ** 2), vp.copy()
+
+        def update(self, vp, direction):
+            return vp - direction
+    for name, mk in (('rmsprop', lambda: RMSProp(0.1)), ('adam', lambda: Adam(0.1))):
+        res = mk().optimize(25, Quad(), np.array([1.0, -2.0, 0.5]))
+        out[name + '/opt_param'] = res['opt_param']
+        out[name + '/value_history'] = res['value_history']
+        out[name + '/param_history'] = res['variational_param_history']
+    np.savez_compressed(os.path.join(OUT, 'optimizers.npz'), **out)
+    print('optimizers: %d arrays' % len(out))
+
+
+def gen_psis():
+    out = {}
+    for name in PSIS_CASES:
+        lw = psis_case(name)
+        res, k = ref_psis.psislw(lw.copy())
+        n = lw.shape[0]
+        out[name + '/khat'] = np.asarray(k)
+        if lw.ndim == 1:
+            # tail = entries above the cutoff, recomputed exactly as _psis.py:163-175 does
+            x = lw - np.max(lw)
+            M = int(np.ceil(min(0.2 * n, 3 * np.sqrt(n))))
+            cut = max(np.sort(x)[-M - 1], np.log(np.finfo(float).tiny))
+            out[name + '/tail_idx'] = np.flatnonzero(x > cut).astype(np.int64)
+        stride = max(1, n // 4096)
+        out[name + '/out_stride'] = np.asarray(stride)
+        out[name + '/out_sub'] = res[::stride]
+        out[name + '/out_sorted_sub'] = np.sort(res, axis=0)[::stride]
+        out[name + '/out_max'] = np.max(res, axis=0)
+        out[name + '/out_min'] = np.min(res, axis=0)
+        out[name + '/out_mean'] = np.mean(res, axis=0)
+        if lw.ndim == 1 and np.isfinite(k):
+            d2, lnb = ref_diag.divergence_bound(res, return_log_norm_bound=True)
+            out[name + '/d2'] = np.asarray(d2)
+            out[name + '/elbo'] = np.asarray(lnb)
+            for alpha in (1.5, 3.0):
+                out[name + '/dalpha%.1f' % alpha] = np.asarray(
+                    ref_diag.divergence_bound(res, alpha=alpha))
+    # gpdfitnew / gpinv / sumlogs on their own
+    rs = np.random.RandomState(1639)
+    for n in (5, 37, 1000):
+        x = np.sort(rs.pareto(2.5, size=n))
+        k, sigma = ref_psis.gpdfitnew(x, sort=False)
+        out['gpd_n%d/x' % n] = x
+        out['gpd_n%d/k' % n] = np.asarray(k)
+        out['gpd_n%d/sigma' % n] = np.asarray(sigma)
+    p = (np.arange(0.5, 50) / 50)
+    for k in (0.5, -0.3, 0.0):
+        out['gpinv_k%.1f' % k] = ref_psis.gpinv(p, k, 1.7)
+    v = rs.randn(1000) * 30
+    out['sumlogs/x'] = v
+    out['sumlogs/out'] = np.asarray(ref_psis.sumlogs(v))
+    np.savez_compressed(os.path.join(OUT, 'psis.npz'), **out)
+    print('psis: %d arrays' % len(out))
+
+
+def gen_diagnostics():
+    out = {}
+    samples, lw = diag_problem()
+    for alpha in (1.5, 2.0, 3.0):
+        out['dalpha%.1f' % alpha] = np.asarray(ref_diag.divergence_bound(lw, alpha=alpha))
+        out['dalpha%.1f_lnb0' % alpha] = np.asarray(
+            ref_diag.divergence_bound(lw, alpha=alpha, log_norm_bound=0.0))
+    wb = ref_diag.wasserstein_bounds(0.7, samples=samples)
+    out['wb_samples'] = np.array([wb['W1'], wb['W2']])
+    wb = ref_diag.wasserstein_bounds(0.7, samples=samples[:, 0])
+    out['wb_samples_1d'] = np.array([wb['W1'], wb['W2']])
+    wb = ref_diag.wasserstein_bounds(0.7, moment_bound_fn=lambda p: 3.0 * p)
+    out['wb_fn'] = np.array([wb['W1'], wb['W2']])
+    keys = ['W1', 'W2', 'mean_error', 'std_error', 'cov_error', 'd2', 'log_norm_bound']
+    res = ref_diag.all_diagnostics(lw, samples=samples)
+    out['all_samples'] = np.array([res[k] for k in keys])
+    res = ref_diag.all_diagnostics(lw, moment_bound_fn=lambda p: 2.5 * p, q_var=1.7)
+    out['all_fn_scalar'] = np.array([res[k] for k in keys])
+    res = ref_diag.all_diagnostics(lw, samples=samples, q_var=np.cov(samples.T) * 1.1,
+                                   p_var=0.9, log_norm_bound=-1.5)
+    out['all_full'] = np.array([res[k] for k in keys])
+    eb = ref_diag.error_bounds(W1=0.3, W2=0.5, q_var=2.0)
+    out['error_bounds'] = np.array([eb['mean_error'], eb['std_error'], eb['cov_error']])
+
+    # vi_diagnostics end to end (convenience.py:97-179) on MFGaussian vs Gaussian targets
+    import contextlib
+    import io
+    from viabel import convenience
+    from viabel.models import Model
+    mean, sd = target_params(4, seed=21)
+    for name, scale in (('matched', 1.05), ('narrow', 0.5), ('wide', 3.0)):
+        fam = MFGaussian(4, seed=56)        # same seed each time -> identical eps
+        vp = np.concatenate([mean, np.log(sd)])
+        model = Model(gauss_log_p(mean + 0.02, sd * scale))
+        with Recorder() as rec, contextlib.redirect_stdout(io.StringIO()):
+            res = convenience.vi_diagnostics(vp, model=model, approx=fam, n_samples=20000)
+        out['vi_eps'] = rec[0][2]
+        out['vi_%s/var_param' % name] = vp
+        out['vi_%s/target_mean' % name] = mean + 0.02
+        out['vi_%s/target_sd' % name] = sd * scale
+        out['vi_%s/khat' % name] = np.asarray(res['khat'])
+        out['vi_%s/slw_sub' % name] = res['smoothed_log_weights'][::20]
+        for k in keys:
+            if k in res:
+                out['vi_%s/%s' % (name, k)] = np.asarray(res[k])
+    np.savez_compressed(os.path.join(OUT, 'diagnostics.npz'), **out)
+    print('diagnostics: %d arrays' % len(out))
+
+
+if __name__ == '__main__':
+    print('reference:', os.path.dirname(viabel.__file__))
+    gen_families()
+    gen_objectives()
+    gen_optimizers()
+    gen_psis()
+    gen_diagnostics()
