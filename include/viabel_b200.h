@@ -1,0 +1,135 @@
+/* libviabel_b200 -- C ABI of the B200-native hot path for jhuggins/viabel.
+ *
+ * The reference (pure Python, /root/reference/viabel) has no FFI of its own; its seams
+ * are Python call signatures.  Each entry point below names the reference call it sits
+ * under (file:line relative to the reference tree).  INTEGRATION.md shows the ctypes
+ * binding a viabel maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative VB_ERR_* code; vb_last_error()
+ *    returns a thread-local message for the last failure;
+ *  - all array arguments are DEVICE pointers unless the name ends in `_host`;
+ *  - matrices are row-major; `ld*` is the row pitch in elements;
+ *  - no hidden allocation: scratch memory comes from the caller, sized by the matching
+ *    *_workspace_bytes() query (256-byte aligned);
+ *  - work is enqueued on `stream` and is asynchronous with respect to the host.
+ */
+#ifndef VIABEL_B200_H_
+#define VIABEL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define VB_OK 0
+#define VB_ERR_INVALID_ARG (-1)   /* -> ValueError   */
+#define VB_ERR_UNSUPPORTED (-2)   /* -> NotImplementedError */
+#define VB_ERR_CUDA (-3)          /* -> RuntimeError */
+#define VB_ERR_WORKSPACE (-4)     /* -> RuntimeError (workspace too small) */
+#define VB_ERR_NUMERIC (-5)       /* -> ValueError (e.g. all weights zero) */
+
+/* variational families (viabel/approximations.py) */
+#define VB_FAMILY_MF_GAUSSIAN 0   /* MFGaussian :192-251 */
+#define VB_FAMILY_MF_STUDENT 1    /* MFStudentT :254-312 */
+
+/* link functions of the built-in GLM model plugins (the reference evaluates user Python
+ * code at models.py:27-39; these are the GPU-resident replacements) */
+#define VB_LINK_LOGISTIC 0        /* log sigmoid(y * x.theta),  y in {-1,+1} */
+#define VB_LINK_PROBIT 1          /* log Phi(y * x.theta),      y in {-1,+1} */
+#define VB_LINK_GAUSSIAN 2        /* -0.5*((y - x.theta)*aux_s)^2 + log(aux_s), aux_s = 1/sigma_s */
+
+/* objectives (viabel/objectives.py) */
+#define VB_OBJ_EXCLUSIVE_KL 0       /* ExclusiveKL :154-168, entropy branch */
+#define VB_OBJ_EXCLUSIVE_KL_PATH 1  /* ExclusiveKL use_path_deriv=True :156-159 */
+#define VB_OBJ_ALPHA 2              /* AlphaDivergence :440-463 */
+
+const char* vb_last_error(void);
+int vb_version(void);
+int vb_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Base draws.  Replaces numpy RandomState.randn / standard_t / chisquare at
+ * approximations.py:216, :274, :345-347.  Philox4x32-10, counter = element index + offset,
+ * so any sub-range can be regenerated and every rank draws identical values.
+ * quantize: 0 = full precision; 1 = round each draw to bfloat16 (8-bit mantissa), which
+ * makes the draws exact operands of the tensor-core fast path.
+ * ------------------------------------------------------------------------------------- */
+int vb_philox_normal_f64(double* out, int64_t n, uint64_t seed, uint64_t offset, int quantize,
+                         cudaStream_t stream);
+int vb_philox_normal_f32(float* out, int64_t n, uint64_t seed, uint64_t offset, int quantize,
+                         cudaStream_t stream);
+int vb_philox_chisquare_f64(double* out, int64_t n, double df, uint64_t seed, uint64_t offset,
+                            cudaStream_t stream);
+int vb_philox_student_t_f64(double* out, int64_t n, double df, uint64_t seed, uint64_t offset,
+                            int quantize, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Mean-field families: var_param = [mu(d), log_sigma(d)] (approximations.py:185-189).
+ * ------------------------------------------------------------------------------------- */
+/* theta[s,:] = mu + exp(log_sigma) * base[s,:]        (MFGaussian.sample :212-216,
+ *                                                      MFStudentT.sample :270-274) */
+int vb_mf_sample_f64(const double* var_param, const double* base, double* theta, int64_t S, int d,
+                     cudaStream_t stream);
+/* out[i] = log q(x[i,:]; var_param)                   (log_density :231-236, :281-286) */
+int vb_mf_log_density_f64(const double* var_param, const double* x, int64_t n, int d, int family,
+                          double df, double* out, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * GLM model plugin, float64 exact path.  One sweep over this rank's N observations:
+ *   z[n,s]   = sum_j X[n,j] theta[s,j]
+ *   out_ll[s]  = sum_n loglik(y_n, z[n,s])                             (always)
+ *   out_gmu[j] = sum_n X[n,j] sum_s w[s] dloglik/dz[n,s]               (want_grad)
+ *   out_ge[j]  = sum_n X[n,j] sum_s w[s] dloglik/dz[n,s] base[s,j]     (want_grad)
+ * i.e. the S x N contraction X.Theta^T of the user's log_density (models.py:27-39) fused
+ * with the link function and the back-projection that autograd's reverse sweep performs
+ * (objectives.py:167, :448).  w == NULL means all ones; aux == NULL unless the link needs it.
+ * Outputs are per-rank partial sums (the caller all-reduces them when N is sharded).
+ * ------------------------------------------------------------------------------------- */
+size_t vb_glm_sweep_workspace_bytes(int64_t N, int d, int64_t S);
+int vb_glm_sweep_f64(const double* X, int64_t ldx, const double* y, int64_t N, int d, int link,
+                     const double* theta, const double* base, const double* w, const double* aux,
+                     int64_t S, int want_grad, double* out_ll, double* out_gmu, double* out_ge,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Objective assembly for mean-field families on "GLM likelihood + iid Gaussian prior"
+ * models (objectives.py:154-168 and :440-463; gradients per SURVEY.md App. A.1).
+ *
+ * vb_mf_alpha_weights_f64: lw[s] = ll[s] + logprior(theta_s) - log q(theta_s); m = max lw;
+ *   w[s] = exp(alpha*(lw[s]-m)); value = log(mean w)/alpha + m          (:456-459)
+ * vb_mf_objective_finish_f64: value[0] and grad[2d] from the (all-reduced) sweep sums.
+ *   For VB_OBJ_ALPHA pass the weights used in the sweep; otherwise w = NULL.
+ * ------------------------------------------------------------------------------------- */
+int vb_mf_alpha_weights_f64(const double* var_param, const double* theta, const double* base,
+                            const double* ll, int64_t S, int d, int family, double df,
+                            double prior_sd, double alpha, double* lw, double* w, double* value,
+                            cudaStream_t stream);
+int vb_mf_objective_finish_f64(const double* var_param, const double* theta, const double* base,
+                               const double* ll, const double* gmu, const double* ge,
+                               const double* w, int64_t S, int d, int family, double df,
+                               double prior_sd, int objective, double alpha, double* value,
+                               double* grad, double* logp, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Optimiser steps fused with the parameter update (optimization.py:188-197 RMSProp,
+ * :308-326 Adam incl. the first-step aliasing quirk, objectives.py:57-59 update).
+ * `first` != 0 on the first call after reset_state().  direction may be NULL.
+ * ------------------------------------------------------------------------------------- */
+int vb_rmsprop_step_f64(double* var_param, const double* grad, double* nu, double* direction,
+                        int64_t P, double lr, double beta, double jitter, int first,
+                        cudaStream_t stream);
+int vb_adam_step_f64(double* var_param, const double* grad, double* m, double* nu,
+                     double* direction, int64_t P, double lr, double beta1, double beta2,
+                     double jitter, int first, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIABEL_B200_H_ */

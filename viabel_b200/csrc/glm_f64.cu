@@ -1,0 +1,462 @@
+// Float64 "exact path" of the GLM model plugin: one fused sweep over the observations.
+//
+//   z[n,s] = sum_j X[n,j] theta[s,j]          (DMMA m8n8k4, X tile resident in shared memory)
+//   ll[s]  = sum_n loglik(y_n, z[n,s])        (link epilogue on the accumulators, in registers)
+//   gmu[j] = sum_n X[n,j] sum_s w_s r[n,s]    r = dloglik/dz
+//   ge[j]  = sum_n X[n,j] (r.w E)[n,j]        second DMMA whose A operand IS the epilogue's
+//                                             register fragment (no N x S intermediate anywhere)
+//
+// Replaces the user's numpy log_density + autograd reverse sweep (reference models.py:27-39,
+// objectives.py:161-167): X.Theta^T, logaddexp, sum, and the transposed GEMM of the VJP.
+//
+// Data layout: X row-major [N,ldx] fp64 in HBM, read once per sweep.  theta / base draws are
+// re-packed once per sweep into mma-fragment order (glm_pack_f64_kernel) so every operand load
+// in the hot loop is a fully coalesced 512-byte LDG.128 that hits L2.
+#include "common.cuh"
+
+namespace vb {
+
+constexpr int kSweepThreads = 256;
+constexpr int kSweepWarps = 8;
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Packing: thetaP[((sb*KG + kg)*32 + lane)] = (theta[8sb+g][8kg+2t], theta[8sb+g][8kg+2t+1])
+//          baseP [((sb*KG + jb)*32 + lane)] = (w? no: base[8sb+2t][8jb+g], base[8sb+2t+1][8jb+g])
+// with g = lane>>2, t = lane&3; out-of-range entries are zero.  wP/auxP are padded copies.
+// ---------------------------------------------------------------------------------------------
+__global__ void glm_pack_f64_kernel(const double* __restrict__ theta, const double* __restrict__ base,
+                                    const double* __restrict__ w, const double* __restrict__ aux,
+                                    int64_t S, int d, int KG, int SB, double2* __restrict__ thetaP,
+                                    double2* __restrict__ baseP, double* __restrict__ wP,
+                                    double* __restrict__ auxP) {
+  const int64_t total = (int64_t)SB * KG * 32;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int lane = (int)(i & 31);
+    const int64_t blk = i >> 5;
+    const int kg = (int)(blk % KG);
+    const int64_t sb = blk / KG;
+    const int g = lane >> 2, t = lane & 3;
+    {
+      const int64_t s = sb * 8 + g;
+      const int j = kg * 8 + 2 * t;
+      double2 v = make_double2(0.0, 0.0);
+      if (s < S) {
+        if (j < d) v.x = theta[s * d + j];
+        if (j + 1 < d) v.y = theta[s * d + j + 1];
+      }
+      thetaP[i] = v;
+    }
+    if (base != nullptr) {
+      const int64_t s = sb * 8 + 2 * t;
+      const int j = kg * 8 + g;
+      double2 v = make_double2(0.0, 0.0);
+      if (j < d) {
+        if (s < S) v.x = base[s * d + j];
+        if (s + 1 < S) v.y = base[(s + 1) * d + j];
+      }
+      baseP[i] = v;
+    }
+  }
+  const int64_t Sp = (int64_t)SB * 8;
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < Sp;
+       s += (int64_t)gridDim.x * blockDim.x) {
+    wP[s] = (s < S) ? (w ? w[s] : 1.0) : 0.0;
+    auxP[s] = (s < S && aux) ? aux[s] : 1.0;
+  }
+}
+
+struct SweepArgs {
+  const double* X;
+  int64_t ldx;
+  const double* y;
+  int64_t N;
+  int d;
+  const double2* thetaP;
+  const double2* baseP;
+  const double* wP;
+  const double* auxP;
+  int WC;   // number of 32-sample warp-chunks (S padded to 32)
+  int KG;   // ceil(d/8)
+  int P;    // shared-memory row pitch of the X tile, in doubles
+  int want_grad;
+  int64_t numTiles;
+  double* ll_part;   // [grid][WC*32]
+  double* gmu_part;  // [grid][KG*8]
+  double* ge_part;   // [grid][KG*8]
+};
+
+template <int LINK>
+__device__ __forceinline__ void link_eval(double z, double yv, double auxv, double& ll, double& r) {
+  if (LINK == VB_LINK_LOGISTIC) {
+    double dl;
+    link_logistic(yv * z, ll, dl);
+    r = yv * dl;
+  } else if (LINK == VB_LINK_PROBIT) {
+    double dl;
+    link_probit(yv * z, ll, dl);
+    r = yv * dl;
+  } else {  // gaussian, aux = 1/sigma_s
+    double e = (yv - z) * auxv;
+    ll = -0.5 * e * e + log(auxv) - 0.5 * kLog2Pi;
+    r = e * auxv;
+  }
+}
+
+template <int BM, int LINK>
+__global__ void __launch_bounds__(kSweepThreads, 1) glm_sweep_f64_kernel(SweepArgs a) {
+  constexpr int MT = BM / 8;
+  extern __shared__ __align__(16) double smem[];
+  const int Dp = a.KG * 8;
+  double* Xs = smem;                        // [BM][P]
+  double* ys = Xs + (size_t)BM * a.P;       // [BM]
+  double* rbar = ys + BM;                   // [BM]
+  double* gmu_s = rbar + BM;                // [Dp]
+  double* ge_s = gmu_s + Dp;                // [Dp]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+
+  for (int j = tid; j < 2 * Dp; j += kSweepThreads) gmu_s[j] = 0.0;   // gmu_s and ge_s are adjacent
+
+  const int numSuper = (a.WC + kSweepWarps - 1) / kSweepWarps;
+  const bool vec_ok = ((a.ldx & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.X) & 15) == 0);
+
+  for (int sc = 0; sc < numSuper; ++sc) {
+    const int wc = sc * kSweepWarps + warp;
+    const bool active = wc < a.WC;
+    double llacc[4][2];
+    double wv[4][2], av[4][2];
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        llacc[jn][c] = 0.0;
+        const int s = wc * 32 + jn * 8 + 2 * t + c;
+        wv[jn][c] = active ? a.wP[s] : 0.0;
+        av[jn][c] = active ? a.auxP[s] : 1.0;
+      }
+
+    for (int64_t tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+      const int64_t n0 = tile * BM;
+      __syncthreads();   // previous tile's readers of Xs / rbar are done
+      // ---- stage the X tile (zero padded) ----------------------------------------------
+      if (vec_ok) {
+        const int half = a.P >> 1;
+        for (int idx = tid; idx < BM * half; idx += kSweepThreads) {
+          const int r = idx / half, c2 = idx - r * half;
+          const int64_t n = n0 + r;
+          double2 v = make_double2(0.0, 0.0);
+          if (n < a.N) {
+            const int j = 2 * c2;
+            if (j + 1 < a.d)
+              v = *reinterpret_cast<const double2*>(a.X + n * a.ldx + j);
+            else if (j < a.d)
+              v.x = a.X[n * a.ldx + j];
+          }
+          *reinterpret_cast<double2*>(Xs + (size_t)r * a.P + 2 * c2) = v;
+        }
+      } else {
+        for (int idx = tid; idx < BM * a.P; idx += kSweepThreads) {
+          const int r = idx / a.P, c = idx - r * a.P;
+          const int64_t n = n0 + r;
+          Xs[(size_t)r * a.P + c] = (n < a.N && c < a.d) ? a.X[n * a.ldx + c] : 0.0;
+        }
+      }
+      if (tid < BM) {
+        ys[tid] = (n0 + tid < a.N) ? a.y[n0 + tid] : 0.0;
+        rbar[tid] = 0.0;
+      }
+      __syncthreads();
+
+      double acc[MT][4][2];
+      if (active) {
+        // ---- phase A: z = X_tile . theta^T for this warp's 32 samples ------------------
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+          for (int jn = 0; jn < 4; ++jn) acc[i][jn][0] = acc[i][jn][1] = 0.0;
+
+        const double2* tp = a.thetaP + ((size_t)wc * 4 * a.KG) * 32 + lane;
+        const size_t sbStride = (size_t)a.KG * 32;
+        double2 bcur[4], bnxt[4];
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) bcur[jn] = tp[jn * sbStride];
+        for (int kg = 0; kg < a.KG; ++kg) {
+          if (kg + 1 < a.KG) {
+#pragma unroll
+            for (int jn = 0; jn < 4; ++jn) bnxt[jn] = tp[jn * sbStride + (size_t)(kg + 1) * 32];
+          }
+          double2 af[MT];
+#pragma unroll
+          for (int i = 0; i < MT; ++i)
+            af[i] = *reinterpret_cast<const double2*>(Xs + (size_t)(8 * i + g) * a.P + 8 * kg + 2 * t);
+#pragma unroll
+          for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int jn = 0; jn < 4; ++jn) {
+              dmma884(acc[i][jn][0], acc[i][jn][1], af[i].x, bcur[jn].x);
+              dmma884(acc[i][jn][0], acc[i][jn][1], af[i].y, bcur[jn].y);
+            }
+#pragma unroll
+          for (int jn = 0; jn < 4; ++jn) bcur[jn] = bnxt[jn];
+        }
+
+        // ---- phase B: link epilogue in registers -----------------------------------------
+        double rsum[MT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          const int r = 8 * i + g;
+          const double yv = ys[r];
+          const double rv = (n0 + r < a.N) ? 1.0 : 0.0;
+          double rs = 0.0;
+#pragma unroll
+          for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              double ll, rr;
+              link_eval<LINK>(acc[i][jn][c], yv, av[jn][c], ll, rr);
+              llacc[jn][c] += ll * rv;
+              rr *= wv[jn][c] * rv;
+              acc[i][jn][c] = rr;
+              rs += rr;
+            }
+          rsum[i] = rs;
+        }
+        if (a.want_grad) {
+#pragma unroll
+          for (int i = 0; i < MT; ++i) {
+            double rs = rsum[i];
+            rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+            rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+            if (t == 0) atomicAdd(&rbar[8 * i + g], rs);
+          }
+        }
+      }
+      if (a.want_grad) {
+        __syncthreads();   // rbar complete
+        // ---- gmu[j] += sum_n X[n,j] rbar[n] -------------------------------------------------
+        for (int j = tid; j < Dp; j += kSweepThreads) {
+          double s = 0.0;
+#pragma unroll 8
+          for (int r = 0; r < BM; ++r) s += Xs[(size_t)r * a.P + j] * rbar[r];
+          gmu_s[j] += s;
+        }
+        if (active) {
+          // ---- phase C: T = (r.w) E for this warp's samples; ge += colsum(X .* T) -------
+          const double2* bp = a.baseP + ((size_t)wc * 4 * a.KG) * 32 + lane;
+          const size_t sbStride = (size_t)a.KG * 32;
+          double2 ecur[4], enxt[4];
+#pragma unroll
+          for (int jn = 0; jn < 4; ++jn) ecur[jn] = bp[jn * sbStride];
+          for (int jb = 0; jb < a.KG; ++jb) {
+            if (jb + 1 < a.KG) {
+#pragma unroll
+              for (int jn = 0; jn < 4; ++jn) enxt[jn] = bp[jn * sbStride + (size_t)(jb + 1) * 32];
+            }
+            double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+              double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+              for (int jn = 0; jn < 4; ++jn) {
+                dmma884(t0, t1, acc[i][jn][0], ecur[jn].x);
+                dmma884(t0, t1, acc[i][jn][1], ecur[jn].y);
+              }
+              const double2 xv =
+                  *reinterpret_cast<const double2*>(Xs + (size_t)(8 * i + g) * a.P + 8 * jb + 2 * t);
+              p0 += xv.x * t0;
+              p1 += xv.y * t1;
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+              p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+              p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+            }
+            if (g == 0) {
+              atomicAdd(&ge_s[8 * jb + 2 * t], p0);
+              atomicAdd(&ge_s[8 * jb + 2 * t + 1], p1);
+            }
+#pragma unroll
+            for (int jn = 0; jn < 4; ++jn) ecur[jn] = enxt[jn];
+          }
+        }
+      }
+    }  // tiles
+
+    // ---- per-CTA log-likelihood partials for this super-chunk ------------------------------
+    if (active) {
+#pragma unroll
+      for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          double v = llacc[jn][c];
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (g == 0) a.ll_part[(size_t)blockIdx.x * a.WC * 32 + wc * 32 + jn * 8 + 2 * t + c] = v;
+        }
+    }
+  }  // super-chunks
+  __syncthreads();
+  if (a.want_grad) {
+    for (int j = tid; j < Dp; j += kSweepThreads) {
+      a.gmu_part[(size_t)blockIdx.x * Dp + j] = gmu_s[j];
+      a.ge_part[(size_t)blockIdx.x * Dp + j] = ge_s[j];
+    }
+  }
+}
+
+// out[i] = sum_b part[b][i]  (fixed order -> deterministic)
+__global__ void reduce_partials_f64_kernel(const double* __restrict__ part, int nblk, int64_t stride,
+                                           int64_t n, double* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += part[(size_t)b * stride + i];
+    out[i] = s;
+  }
+}
+
+struct SweepPlan {
+  int BM, KG, P, WC, SB, grid;
+  int64_t numTiles;
+  size_t smem;
+  size_t off_thetaP, off_baseP, off_wP, off_auxP, off_ll, off_gmu, off_ge, total;
+};
+
+static bool make_plan(int64_t N, int d, int64_t S, SweepPlan& p) {
+  p.KG = (int)ceil_div(d, 8);
+  const int Dp = p.KG * 8;
+  p.P = (Dp % 16 == 0) ? Dp + 8 : Dp + 16;
+  p.WC = (int)ceil_div(S, 32);
+  p.SB = p.WC * 4;
+  p.BM = 0;
+  for (int bm : {32, 16, 8}) {
+    size_t bytes = sizeof(double) * ((size_t)bm * p.P + 2 * bm + 2 * (size_t)Dp);
+    if (bytes <= 227 * 1024) {
+      p.BM = bm;
+      p.smem = bytes;
+      break;
+    }
+  }
+  if (p.BM == 0) return false;
+  p.numTiles = ceil_div(N, p.BM);
+  int sms = sm_count();
+  p.grid = (int)((p.numTiles < sms) ? (p.numTiles > 0 ? p.numTiles : 1) : sms);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  const size_t packed = (size_t)p.SB * p.KG * 32 * sizeof(double2);
+  p.off_thetaP = take(packed);
+  p.off_baseP = take(packed);
+  p.off_wP = take((size_t)p.SB * 8 * sizeof(double));
+  p.off_auxP = take((size_t)p.SB * 8 * sizeof(double));
+  p.off_ll = take((size_t)p.grid * p.WC * 32 * sizeof(double));
+  p.off_gmu = take((size_t)p.grid * Dp * sizeof(double));
+  p.off_ge = take((size_t)p.grid * Dp * sizeof(double));
+  p.total = off;
+  return true;
+}
+
+template <int BM, int LINK>
+static int launch_sweep(const SweepArgs& a, const SweepPlan& p, cudaStream_t stream) {
+  auto kern = glm_sweep_f64_kernel<BM, LINK>;
+  VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  kern<<<p.grid, kSweepThreads, p.smem, stream>>>(a);
+  VB_CHECK_LAUNCH();
+  return VB_OK;
+}
+
+template <int LINK>
+static int launch_sweep_bm(const SweepArgs& a, const SweepPlan& p, cudaStream_t stream) {
+  switch (p.BM) {
+    case 32: return launch_sweep<32, LINK>(a, p, stream);
+    case 16: return launch_sweep<16, LINK>(a, p, stream);
+    default: return launch_sweep<8, LINK>(a, p, stream);
+  }
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" size_t vb_glm_sweep_workspace_bytes(int64_t N, int d, int64_t S) {
+  SweepPlan p;
+  if (N < 0 || d <= 0 || S <= 0 || !make_plan(N, d, S, p)) return 0;
+  return p.total;
+}
+
+extern "C" int vb_glm_sweep_f64(const double* X, int64_t ldx, const double* y, int64_t N, int d,
+                                int link, const double* theta, const double* base, const double* w,
+                                const double* aux, int64_t S, int want_grad, double* out_ll,
+                                double* out_gmu, double* out_ge, void* workspace,
+                                size_t workspace_bytes, cudaStream_t stream) {
+  if (N < 0 || d <= 0 || S <= 0 || ldx < d) return set_error(VB_ERR_INVALID_ARG, "glm_sweep: bad shape");
+  if (!X || !y || !theta || !out_ll) return set_error(VB_ERR_INVALID_ARG, "glm_sweep: null pointer");
+  if (want_grad && (!base || !out_gmu || !out_ge))
+    return set_error(VB_ERR_INVALID_ARG, "glm_sweep: want_grad needs base, out_gmu, out_ge");
+  if (link == VB_LINK_GAUSSIAN && !aux)
+    return set_error(VB_ERR_INVALID_ARG, "glm_sweep: gaussian link needs aux = 1/sigma_s");
+  if (link < 0 || link > VB_LINK_GAUSSIAN) return set_error(VB_ERR_INVALID_ARG, "glm_sweep: unknown link");
+  SweepPlan p;
+  if (!make_plan(N, d, S, p)) return set_error(VB_ERR_UNSUPPORTED, "glm_sweep: d too large for one tile");
+  if (!workspace || workspace_bytes < p.total) return set_error(VB_ERR_WORKSPACE, "glm_sweep: workspace too small");
+  char* ws = static_cast<char*>(workspace);
+  const int Dp = p.KG * 8;
+
+  SweepArgs a;
+  a.X = X; a.ldx = ldx; a.y = y; a.N = N; a.d = d;
+  a.thetaP = reinterpret_cast<double2*>(ws + p.off_thetaP);
+  a.baseP = reinterpret_cast<double2*>(ws + p.off_baseP);
+  a.wP = reinterpret_cast<double*>(ws + p.off_wP);
+  a.auxP = reinterpret_cast<double*>(ws + p.off_auxP);
+  a.WC = p.WC; a.KG = p.KG; a.P = p.P; a.want_grad = want_grad; a.numTiles = p.numTiles;
+  a.ll_part = reinterpret_cast<double*>(ws + p.off_ll);
+  a.gmu_part = reinterpret_cast<double*>(ws + p.off_gmu);
+  a.ge_part = reinterpret_cast<double*>(ws + p.off_ge);
+
+  {
+    const int64_t total = (int64_t)p.SB * p.KG * 32;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+    glm_pack_f64_kernel<<<blocks, 256, 0, stream>>>(theta, want_grad ? base : nullptr, w, aux, S, d, p.KG,
+                                                    p.SB, const_cast<double2*>(a.thetaP),
+                                                    const_cast<double2*>(a.baseP),
+                                                    const_cast<double*>(a.wP), const_cast<double*>(a.auxP));
+    VB_CHECK_LAUNCH();
+  }
+  if (N == 0) {
+    VB_CUDA(cudaMemsetAsync(out_ll, 0, sizeof(double) * S, stream));
+    if (want_grad) {
+      VB_CUDA(cudaMemsetAsync(out_gmu, 0, sizeof(double) * d, stream));
+      VB_CUDA(cudaMemsetAsync(out_ge, 0, sizeof(double) * d, stream));
+    }
+    return VB_OK;
+  }
+  int rc;
+  switch (link) {
+    case VB_LINK_LOGISTIC: rc = launch_sweep_bm<VB_LINK_LOGISTIC>(a, p, stream); break;
+    case VB_LINK_PROBIT: rc = launch_sweep_bm<VB_LINK_PROBIT>(a, p, stream); break;
+    default: rc = launch_sweep_bm<VB_LINK_GAUSSIAN>(a, p, stream); break;
+  }
+  if (rc != VB_OK) return rc;
+  reduce_partials_f64_kernel<<<(int)ceil_div(S, 256), 256, 0, stream>>>(a.ll_part, p.grid, (int64_t)p.WC * 32, S, out_ll);
+  VB_CHECK_LAUNCH();
+  if (want_grad) {
+    reduce_partials_f64_kernel<<<(int)ceil_div(d, 256), 256, 0, stream>>>(a.gmu_part, p.grid, Dp, d, out_gmu);
+    VB_CHECK_LAUNCH();
+    reduce_partials_f64_kernel<<<(int)ceil_div(d, 256), 256, 0, stream>>>(a.ge_part, p.grid, Dp, d, out_ge);
+    VB_CHECK_LAUNCH();
+  }
+  return VB_OK;
+}

@@ -1,0 +1,143 @@
+// Counter-based base draws (Philox4x32-10): normal, chi-square, Student-t.
+// Replaces numpy RandomState.randn / chisquare / standard_t (reference approximations.py:216,
+// :274, :345-347).  The numpy MT19937 streams are NOT reproduced; parity is by draw injection.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace vb {
+
+__device__ __forceinline__ double quantize_bf16(double x) {
+  return (double)__bfloat162float(__float2bfloat16_rn((float)x));
+}
+
+// two independent N(0,1) from one Philox block (Box-Muller, 53-bit uniforms)
+__device__ __forceinline__ void normal_pair(const Philox& ph, uint64_t ctr, uint64_t stream_id, double& z0,
+                                            double& z1) {
+  uint32_t r[4];
+  ph(ctr, stream_id, r);
+  const double u1 = u01_53(r[0], r[1]), u2 = u01_53(r[2], r[3]);
+  const double rad = sqrt(-2.0 * log(u1));
+  double sn, cs;
+  sincospi(2.0 * u2, &sn, &cs);
+  z0 = rad * cs;
+  z1 = rad * sn;
+}
+
+template <typename T>
+__global__ void philox_normal_kernel(T* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset,
+                                     int quantize) {
+  const Philox ph(seed);
+  const int64_t pairs = (n + 1) / 2;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pairs;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    // element i uses counter (offset + i) / 2: a run that starts at an even offset is a
+    // contiguous slice of the same infinite stream
+    const uint64_t e0 = offset + 2 * (uint64_t)p;
+    double z0, z1;
+    normal_pair(ph, e0 >> 1, 0, z0, z1);
+    if (e0 & 1) {  // odd offset: element e0 is the second of its pair, e0+1 the first of the next
+      double a0, a1;
+      normal_pair(ph, (e0 >> 1) + 1, 0, a0, a1);
+      z0 = z1;
+      z1 = a0;
+    }
+    if (quantize) {
+      z0 = quantize_bf16(z0);
+      z1 = quantize_bf16(z1);
+    }
+    out[2 * p] = (T)z0;
+    if (2 * p + 1 < n) out[2 * p + 1] = (T)z1;
+  }
+}
+
+// Marsaglia-Tsang gamma(shape a >= 1/3 boosted), counter = element, attempts on the high word
+__device__ double gamma_draw(const Philox& ph, uint64_t elem, uint64_t stream_id, double a) {
+  double boost = 1.0;
+  if (a < 1.0) {
+    uint32_t r[4];
+    ph(elem, stream_id | (1ull << 62), r);
+    boost = pow(u01_53(r[0], r[1]), 1.0 / a);
+    a += 1.0;
+  }
+  const double dd = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * dd);
+  for (uint64_t attempt = 0; attempt < 64; ++attempt) {
+    double x, unused;
+    normal_pair(ph, elem, stream_id | ((2 * attempt + 1) << 40), x, unused);
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    uint32_t r[4];
+    ph(elem, stream_id | ((2 * attempt + 2) << 40), r);
+    const double u = u01_53(r[0], r[1]);
+    if (log(u) < 0.5 * x * x + dd - dd * v + dd * log(v)) return boost * dd * v;
+  }
+  return boost * dd;  // unreachable in practice (acceptance > 95% per attempt)
+}
+
+__global__ void philox_chisquare_kernel(double* __restrict__ out, int64_t n, double df, uint64_t seed,
+                                        uint64_t offset) {
+  const Philox ph(seed);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = 2.0 * gamma_draw(ph, offset + (uint64_t)i, 1, 0.5 * df);
+}
+
+__global__ void philox_student_t_kernel(double* __restrict__ out, int64_t n, double df, uint64_t seed,
+                                        uint64_t offset, int quantize) {
+  const Philox ph(seed);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t e = offset + (uint64_t)i;
+    double z, unused;
+    normal_pair(ph, e, 2, z, unused);
+    const double chi2 = 2.0 * gamma_draw(ph, e, 3, 0.5 * df);
+    double tv = z / sqrt(chi2 / df);
+    out[i] = quantize ? quantize_bf16(tv) : tv;
+  }
+}
+
+static inline int grid_for(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace vb
+using namespace vb;
+
+extern "C" int vb_philox_normal_f64(double* out, int64_t n, uint64_t seed, uint64_t offset, int quantize,
+                                    cudaStream_t stream) {
+  if (n < 0 || (n > 0 && !out)) return set_error(VB_ERR_INVALID_ARG, "philox_normal: bad arguments");
+  if (n == 0) return VB_OK;
+  philox_normal_kernel<double><<<grid_for((n + 1) / 2, 256), 256, 0, stream>>>(out, n, seed, offset, quantize);
+  VB_CHECK_LAUNCH();
+  return VB_OK;
+}
+
+extern "C" int vb_philox_normal_f32(float* out, int64_t n, uint64_t seed, uint64_t offset, int quantize,
+                                    cudaStream_t stream) {
+  if (n < 0 || (n > 0 && !out)) return set_error(VB_ERR_INVALID_ARG, "philox_normal: bad arguments");
+  if (n == 0) return VB_OK;
+  philox_normal_kernel<float><<<grid_for((n + 1) / 2, 256), 256, 0, stream>>>(out, n, seed, offset, quantize);
+  VB_CHECK_LAUNCH();
+  return VB_OK;
+}
+
+extern "C" int vb_philox_chisquare_f64(double* out, int64_t n, double df, uint64_t seed, uint64_t offset,
+                                       cudaStream_t stream) {
+  if (n < 0 || (n > 0 && !out) || !(df > 0)) return set_error(VB_ERR_INVALID_ARG, "philox_chisquare: bad arguments");
+  if (n == 0) return VB_OK;
+  philox_chisquare_kernel<<<grid_for(n, 256), 256, 0, stream>>>(out, n, df, seed, offset);
+  VB_CHECK_LAUNCH();
+  return VB_OK;
+}
+
+extern "C" int vb_philox_student_t_f64(double* out, int64_t n, double df, uint64_t seed, uint64_t offset,
+                                       int quantize, cudaStream_t stream) {
+  if (n < 0 || (n > 0 && !out) || !(df > 0)) return set_error(VB_ERR_INVALID_ARG, "philox_student_t: bad arguments");
+  if (n == 0) return VB_OK;
+  philox_student_t_kernel<<<grid_for(n, 256), 256, 0, stream>>>(out, n, df, seed, offset, quantize);
+  VB_CHECK_LAUNCH();
+  return VB_OK;
+}

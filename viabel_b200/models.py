@@ -1,0 +1,134 @@
+"""Model plugin boundary -- mirror of viabel/models.py (Model :11-76) plus the GPU-resident
+built-in models named by the north star (logistic / probit regression).
+
+The reference calls user Python under autograd (models.py:27-39).  Here a model either is a
+built-in plugin whose S x N likelihood contraction runs as one fused CUDA sweep, or wraps a
+user callable on CUDA tensors with an explicit gradient (`Model(log_density, grad)`).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._tensor import F64, device, is_host, like_input, to_dev
+
+__all__ = ['Model', 'GLMModel', 'LogisticRegression', 'ProbitRegression']
+
+
+class Model(object):
+    """Base class for representing a model (models.py:11-76).
+
+    `log_density(theta[S,d]) -> [S]` operates on CUDA float64 tensors.  `grad(theta) -> [S,d]`
+    is its gradient; when omitted, torch autograd differentiates `log_density`.
+    """
+
+    def __init__(self, log_density, grad=None):
+        self._log_density = log_density
+        self._grad = grad
+
+    def __call__(self, model_param):
+        host = is_host(model_param)
+        x = to_dev(model_param)
+        squeeze = x.dim() == 1
+        if squeeze:
+            x = x[None, :]
+        out = self._log_density(x)
+        if squeeze:
+            out = out.reshape(())
+        return like_input(out, host)
+
+    def logp_and_grad(self, theta):
+        """(log density [S], gradient [S,d]) at CUDA tensor theta[S,d]."""
+        if self._grad is not None:
+            return self._log_density(theta), self._grad(theta)
+        with torch.enable_grad():
+            t = theta.detach().requires_grad_(True)
+            lp = self._log_density(t)
+            (g,) = torch.autograd.grad(lp.sum(), t)
+        return lp.detach(), g
+
+    def constrain(self, model_param):
+        raise NotImplementedError()
+
+    @property
+    def supports_tempering(self):
+        return False
+
+    def set_inverse_temperature(self, inverse_temp):
+        raise NotImplementedError()
+
+
+class GLMModel(Model):
+    """GPU-resident generalised linear model with an iid N(0, prior_scale^2) prior:
+
+        log p(theta) = sum_n loglik(y_n, x_n . theta) - |theta|^2 / (2 prior_scale^2) + const
+
+    X[N,d] (row-major float64) and y[N] (+1/-1) live in HBM for the lifetime of the object.
+    When torch.distributed is initialised and `sharded=True`, X holds this rank's N/world rows
+    and the per-sample log-likelihoods and gradient sums are all-reduced.
+    """
+    link = None
+
+    def __init__(self, X, y, prior_scale=10.0, sharded=False, process_group=None):
+        self.X = to_dev(X)
+        self.y = to_dev(y).reshape(-1)
+        if self.X.dim() != 2 or self.X.shape[0] != self.y.shape[0]:
+            raise ValueError('X must be [N, d] and y must be [N]')
+        self.N, self.dim = int(self.X.shape[0]), int(self.X.shape[1])
+        self.prior_scale = float(prior_scale)
+        self.sharded = bool(sharded)
+        self.process_group = process_group
+        self._ws = None
+        self._ws_S = -1
+        super().__init__(self._logp)
+
+    # -- fused sweep -----------------------------------------------------------------------------
+    def _workspace(self, S):
+        if self._ws_S != S:
+            nbytes = _lib.lib.vb_glm_sweep_workspace_bytes(self.N, self.dim, S)
+            if nbytes == 0:
+                raise NotImplementedError('model dimension too large for the fused sweep')
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=device())
+            self._ws_S = S
+        return self._ws
+
+    def _allreduce(self, buf):
+        if self.sharded and torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(buf, group=self.process_group)
+
+    def sweep(self, theta, base=None, w=None, want_grad=True, aux=None):
+        """One pass over the observations.  Returns (ll[S], gmu[d], ge[d]); the last two are None
+        when want_grad is False.  Sums are all-reduced across ranks when sharded."""
+        S = int(theta.shape[0])
+        d = self.dim
+        ws = self._workspace(S)
+        out = torch.empty(S + 2 * d, dtype=F64, device=device())
+        ll, gmu, ge = out[:S], out[S:S + d], out[S + d:]
+        _lib.check(_lib.lib.vb_glm_sweep_f64(
+            _lib.ptr(self.X), self.X.stride(0), _lib.ptr(self.y), self.N, d, self.link,
+            _lib.ptr(theta), _lib.ptr(base) if want_grad else None, _lib.ptr(w), _lib.ptr(aux), S,
+            int(bool(want_grad)), _lib.ptr(ll), _lib.ptr(gmu) if want_grad else None,
+            _lib.ptr(ge) if want_grad else None, _lib.ptr(ws), ws.numel(), _lib.stream()))
+        if want_grad:
+            self._allreduce(out)
+            return ll, gmu, ge
+        self._allreduce(ll)
+        return ll, None, None
+
+    def log_prior(self, theta):
+        d = self.dim
+        return (-0.5 * (theta * theta).sum(dim=1) / self.prior_scale ** 2
+                - d * np.log(self.prior_scale * np.sqrt(2 * np.pi)))
+
+    def _logp(self, theta):
+        ll, _, _ = self.sweep(theta.contiguous(), want_grad=False)
+        return ll + self.log_prior(theta)
+
+
+class LogisticRegression(GLMModel):
+    """Bayesian logistic regression, y in {-1,+1} (BASELINE.json configs 1-3)."""
+    link = _lib.LINK_LOGISTIC
+
+
+class ProbitRegression(GLMModel):
+    """Bayesian probit regression, y in {-1,+1}."""
+    link = _lib.LINK_PROBIT

@@ -1,0 +1,192 @@
+"""Variational objectives -- drop-in mirror of viabel/objectives.py for the hot path:
+ExclusiveKL (:108-168, entropy and path-derivative forms) and AlphaDivergence (:419-463).
+
+The reference differentiates a Python closure with autograd; here `objective(var_param)`
+launches the fused CUDA sweep (sample -> model log density + gradient -> reduction) and
+assembles the analytic gradient of SURVEY.md App. A on the device.
+"""
+from abc import ABC, abstractmethod
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._tensor import F64, device, is_host, like_input, to_dev
+from .approximations import _MeanField
+from .models import GLMModel, Model
+
+__all__ = ['VariationalObjective', 'StochasticVariationalObjective', 'ExclusiveKL', 'AlphaDivergence']
+
+
+class VariationalObjective(ABC):
+    """A variational objective to minimise (objectives.py:17-79)."""
+
+    def __init__(self, approx, model):
+        self._approx = approx
+        self._model = model if isinstance(model, Model) or model is None else Model(model)
+        self._objective_and_grad = None
+        self._update_objective_and_grad()
+
+    def __call__(self, var_param):
+        if self._objective_and_grad is None:
+            raise RuntimeError("no objective and gradient available")
+        return self._objective_and_grad(var_param)
+
+    @abstractmethod
+    def _update_objective_and_grad(self):
+        """Rebuild the objective when approx / model / num_mc_samples change."""
+
+    def update(self, var_param, direction):
+        """objectives.py:57-59"""
+        return var_param - direction
+
+    @property
+    def approx(self):
+        return self._approx
+
+    @approx.setter
+    def approx(self, value):
+        self._approx = value
+        self._update_objective_and_grad()
+
+    @property
+    def model(self):
+        return self._model
+
+    @model.setter
+    def model(self, value):
+        self._model = value if isinstance(value, Model) else Model(value)
+        self._update_objective_and_grad()
+
+
+class StochasticVariationalObjective(VariationalObjective):
+    """objectives.py:82-105"""
+
+    def __init__(self, approx, model, num_mc_samples):
+        self._num_mc_samples = num_mc_samples
+        super().__init__(approx, model)
+
+    @property
+    def num_mc_samples(self):
+        return self._num_mc_samples
+
+    @num_mc_samples.setter
+    def num_mc_samples(self, value):
+        self._num_mc_samples = value
+        self._update_objective_and_grad()
+
+
+def _mf_objective(approx, model, S, objective, alpha, var_param, base=None, seed=None, want_logp=False):
+    """One fused evaluation for a mean-field family.  Returns (value, grad[, logp]) as 0-d / 1-d
+    CUDA tensors (no host sync)."""
+    if not isinstance(approx, _MeanField):
+        raise NotImplementedError('only mean-field families are supported by this objective path')
+    d = approx.dim
+    vp = to_dev(var_param)
+    if vp.numel() != 2 * d:
+        raise ValueError('var_param has the wrong length')
+    e = approx.base_draws(S, seed) if base is None else to_dev(base)
+    approx.last_base = e
+    S = int(e.shape[0])
+    dev = device()
+    theta = torch.empty_like(e)
+    lib, ptr, st = _lib.lib, _lib.ptr, _lib.stream()
+    _lib.check(lib.vb_mf_sample_f64(ptr(vp), ptr(e), ptr(theta), S, d, st))
+    family, df = approx._family, float(approx.df) if approx._family else 0.0
+    out = torch.empty(1 + 2 * d, dtype=F64, device=dev)
+    value, grad = out[:1], out[1:]
+    logp = torch.empty(S, dtype=F64, device=dev) if want_logp else None
+    glm = isinstance(model, GLMModel)
+    prior_sd = model.prior_scale if glm else float('inf')
+
+    def sweep(w):
+        if glm:
+            return model.sweep(theta, e, w, True)
+        f, G = model.logp_and_grad(theta)
+        Gw = G if w is None else G * w[:, None]
+        return f.contiguous(), Gw.sum(dim=0).contiguous(), (Gw * e).sum(dim=0).contiguous()
+
+    w = None
+    if objective == _lib.OBJ_ALPHA:
+        if glm:
+            ll, _, _ = model.sweep(theta, None, None, False)
+        else:
+            ll = model.logp_and_grad(theta)[0].contiguous()
+        lw = torch.empty(S, dtype=F64, device=dev)
+        w = torch.empty(S, dtype=F64, device=dev)
+        _lib.check(lib.vb_mf_alpha_weights_f64(ptr(vp), ptr(theta), ptr(e), ptr(ll), S, d, family, df,
+                                               prior_sd, float(alpha), ptr(lw), ptr(w), ptr(value), st))
+    ll, gmu, ge = sweep(w)
+    _lib.check(lib.vb_mf_objective_finish_f64(
+        ptr(vp), ptr(theta), ptr(e), ptr(ll), ptr(gmu), ptr(ge), ptr(w), S, d, family, df, prior_sd,
+        objective, float(alpha), ptr(value), ptr(grad), ptr(logp), st))
+    if want_logp:
+        return value[0], grad, logp
+    return value[0], grad
+
+
+class ExclusiveKL(StochasticVariationalObjective):
+    """Exclusive KL / negative ELBO with the reparameterised gradient (objectives.py:108-168)."""
+
+    def __init__(self, approx, model, num_mc_samples, use_path_deriv=False, hessian_approx_method=None):
+        self._use_path_deriv = use_path_deriv
+        if hessian_approx_method in [None, 'full', 'mean_only', 'loo_diag_approx', 'loo_direct_approx']:
+            self.hessian_approx_method = hessian_approx_method
+        else:
+            raise ValueError("Name of approximation must be one of 'full', 'mean_only', 'loo_diag_approx', 'loo_direct_approx' or None object.")
+        super().__init__(approx, model, num_mc_samples)
+
+    def _update_objective_and_grad(self):
+        if self.hessian_approx_method is not None:
+            def unsupported(var_param):
+                raise NotImplementedError('control-variate estimators are not on the B200 hot path yet')
+            self._objective_and_grad = unsupported
+            return
+        obj = _lib.OBJ_EXCLUSIVE_KL_PATH if self._use_path_deriv else _lib.OBJ_EXCLUSIVE_KL
+
+        def objective_and_grad(var_param, base=None):
+            host = is_host(var_param)
+            value, grad = _mf_objective(self.approx, self.model, self.num_mc_samples, obj, 0.0,
+                                        var_param, base=base)
+            if host:
+                return float(value), grad.cpu().numpy()
+            return value, grad
+
+        self._objective_and_grad = objective_and_grad
+
+    def __call__(self, var_param, base=None):
+        if self._objective_and_grad is None:
+            raise RuntimeError("no objective and gradient available")
+        if base is None:
+            return self._objective_and_grad(var_param)
+        return self._objective_and_grad(var_param, base=base)
+
+
+class AlphaDivergence(StochasticVariationalObjective):
+    """Log of the alpha-divergence (objectives.py:419-463)."""
+
+    def __init__(self, approx, model, num_mc_samples, alpha):
+        self._alpha = alpha
+        super().__init__(approx, model, num_mc_samples)
+
+    @property
+    def alpha(self):
+        return self._alpha
+
+    def _update_objective_and_grad(self):
+        def objective_grad_and_log_norm(var_param, base=None):
+            host = is_host(var_param)
+            # objectives.py:455: a fresh seed from the GLOBAL numpy RNG, shared by both passes
+            seed = np.random.randint(2 ** 32, dtype=np.uint64) if base is None else None
+            value, grad = _mf_objective(self.approx, self.model, self.num_mc_samples, _lib.OBJ_ALPHA,
+                                        self.alpha, var_param, base=base, seed=seed)
+            if host:
+                return float(value), grad.cpu().numpy()
+            return value, grad
+
+        self._objective_and_grad = objective_grad_and_log_norm
+
+    def __call__(self, var_param, base=None):
+        if base is None:
+            return self._objective_and_grad(var_param)
+        return self._objective_and_grad(var_param, base=base)
