@@ -129,6 +129,30 @@ int vb_adam_step_f64(double* var_param, const double* grad, double* m, double* n
                      double* direction, int64_t P, double lr, double beta1, double beta2,
                      double jitter, int first, cudaStream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Pareto-smoothed importance sampling and divergence-bound moments
+ * (viabel/_psis.py:113-209 psislw, :212-332 gpdfitnew, :335-377 gpinv, :380-396 sumlogs;
+ *  viabel/diagnostics.py:148-186 divergence_bound).
+ *
+ * vb_psislw_f64: one column of log-weights lw[n] -> smoothed, normalised log-weights out[n]
+ * (out may alias lw = the reference's overwrite_lw; out == NULL computes k-hat only).
+ * result[16] (device doubles): [0] k-hat (inf when the tail has <= 4 entries), [1] GPD sigma,
+ * [2] n2 = tail length, [3] shifted cutoff, [4] log-sum-exp, [5] max(lw), [6] status
+ * (0 ok; 1 = the sampled threshold missed, call again with exact=1; 2 = internal overflow),
+ * [7] sum(out+lse), [8] sum exp(2(out+lse)) (moments for the CUBO/ELBO bounds), [9] M,
+ * [10] candidates examined, [11] 1 if the tail was smoothed (k-hat >= 1/3).
+ * tail_idx (optional, [tail capacity]) receives the tail indices in ascending index order
+ * and tail_rank their rank (0 = smallest) among the tail values -- ties ranked by index.
+ * ------------------------------------------------------------------------------------- */
+size_t vb_psis_workspace_bytes(int64_t n, double reff);
+int64_t vb_psis_tail_capacity(int64_t n, double reff);
+int vb_psislw_f64(const double* lw, double* out, int64_t n, double reff, int exact, double* result,
+                  int64_t* tail_idx, int32_t* tail_rank, void* workspace, size_t workspace_bytes,
+                  cudaStream_t stream);
+/* out4[0] = max(lw), out4[1] = sum exp(lw - max)^alpha, out4[2] = sum lw  (out4[3] is scratch) */
+int vb_divergence_moments_f64(const double* lw, int64_t n, double alpha, double* out4,
+                              cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ from numpy import (  # noqa: F401  (non-differentiable helpers pass straight thr
     isnan, isinf, isfinite, logical_not, logical_and, logical_or, any, all, delete,
     nanmean, apply_along_axis, where, ceil, floor, full, empty, cov, round,
     conjugate, real, imag, cumsum, unique, sort, copy, allclose, negative, divide,
-    subtract, add)
+    subtract, add, log10, log2, power, diff, mod, clip, isscalar)
 from numpy import fft  # noqa: F401
 
 from .._box import Box, _t, is_box, unbox

@@ -1,7 +1,7 @@
 """ctypes binding of libviabel_b200.so (the C ABI declared in include/viabel_b200.h).
 
 The product path has no CPU fallback: importing this module fails loudly when the
-shared library has not been built (`python -m viabel_b200.build`), and every compute
+shared library has not been built (`python viabel_b200/csrc/build.py`), and every compute
 entry point needs CUDA device pointers.
 """
 import ctypes
@@ -19,7 +19,7 @@ OBJ_EXCLUSIVE_KL, OBJ_EXCLUSIVE_KL_PATH, OBJ_ALPHA = 0, 1, 2
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
-        'viabel_b200: %s is missing. Build it with `python -m viabel_b200.build` '
+        'viabel_b200: %s is missing. Build it with `python viabel_b200/csrc/build.py` '
         '(nvcc, sm_100a). There is no CPU fallback.' % LIB_PATH)
 
 lib = ctypes.CDLL(LIB_PATH)
@@ -44,6 +44,10 @@ _PROTOS = {
                                            c_int, c_double, P, P, P, P]),
     'vb_rmsprop_step_f64': (c_int, [P, P, P, P, c_int64, c_double, c_double, c_double, c_int, P]),
     'vb_adam_step_f64': (c_int, [P, P, P, P, P, c_int64, c_double, c_double, c_double, c_double, c_int, P]),
+    'vb_psis_workspace_bytes': (c_size_t, [c_int64, c_double]),
+    'vb_psis_tail_capacity': (c_int64, [c_int64, c_double]),
+    'vb_psislw_f64': (c_int, [P, P, c_int64, c_double, c_int, P, P, P, P, c_size_t, P]),
+    'vb_divergence_moments_f64': (c_int, [P, c_int64, c_double, P, P]),
 }
 
 #: symbols declared in include/viabel_b200.h that this build exports

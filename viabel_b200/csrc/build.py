@@ -1,14 +1,17 @@
 """Build libviabel_b200.so in-tree with nvcc for sm_100a (no JIT cache, no pip).
 
-    python -m viabel_b200.build            # incremental
-    python -m viabel_b200.build --force
+    python viabel_b200/csrc/build.py            # incremental
+    python viabel_b200/csrc/build.py --force
+
+Run as a script (or through __graft_entry__.build()); it must not import the package,
+whose __init__ loads the library being built.
 """
 import os
 import subprocess
 import sys
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-CSRC = os.path.join(HERE, 'csrc')
+CSRC = os.path.dirname(os.path.abspath(__file__))
+HERE = os.path.dirname(CSRC)
 LIB = os.path.join(HERE, 'libviabel_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

@@ -1,0 +1,98 @@
+"""VI diagnostics -- drop-in mirror of viabel/diagnostics.py (all_diagnostics :13-64,
+error_bounds :73-103, wasserstein_bounds :106-145, divergence_bound :148-186).
+
+The O(n) reductions over the log weights (and over samples, when given) run on the device;
+the scalar algebra on top of them is host Python.
+"""
+from warnings import warn
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._tensor import F64, device, is_host, to_dev
+
+__all__ = ['all_diagnostics', 'error_bounds', 'wasserstein_bounds', 'divergence_bound']
+
+
+def _moments(log_weights, alpha):
+    lw = to_dev(log_weights).reshape(-1)
+    out = torch.empty(4, dtype=F64, device=lw.device)
+    _lib.check(_lib.lib.vb_divergence_moments_f64(_lib.ptr(lw), lw.numel(), float(alpha), _lib.ptr(out),
+                                                  _lib.stream()))
+    mx, sexp, sx, _ = out.cpu().numpy()
+    return lw, float(mx), float(sexp), float(sx)
+
+
+def _mc_warn(mean, sumsq_centered, n, name, atol=0.01):
+    s = np.sqrt(max(sumsq_centered, 0.0) / n) / np.sqrt(n)
+    if s > atol:  # pragma: no cover
+        warn('significant Monte Carlo error when computing {} (mean = {}, standard deviation = {})'
+             .format(name, mean, s))
+
+
+def divergence_bound(log_weights, *, alpha=2., log_norm_bound=None, return_log_norm_bound=False):
+    """Bound on the alpha-divergence (diagnostics.py:148-186)."""
+    if alpha <= 1:
+        raise ValueError('alpha must be greater than 1')
+    lw, mx, sexp, sx = _moments(log_weights, alpha)
+    n = lw.numel()
+    cubo = np.log(sexp / n) / alpha + mx
+    if log_norm_bound is None:
+        log_norm_bound = sx / n
+        _mc_warn(log_norm_bound, float(((lw - log_norm_bound) ** 2).sum()), n, 'ELBO')
+    dalpha = alpha / (alpha - 1) * (cubo - log_norm_bound)
+    if return_log_norm_bound:
+        return dalpha, log_norm_bound
+    return dalpha
+
+
+def wasserstein_bounds(d2, *, samples=None, moment_bound_fn=None):
+    """1- and 2-Wasserstein bounds from a 2-divergence bound (diagnostics.py:106-145)."""
+    results = dict()
+    if moment_bound_fn is None:
+        if samples is None:
+            raise ValueError('must provides samples if moment_bound_fn not given')
+        x = to_dev(samples)
+        if x.dim() == 1:
+            x = x[:, None]
+        centered = x - x.mean(dim=0, keepdim=True)
+
+        def moment_bound_fn(p):
+            # per-coordinate central power sums, as the reference (diagnostics.py:140-141)
+            return float((centered ** p).sum(dim=1).mean())
+    for p in [1, 2]:
+        Cp = moment_bound_fn(2 * p)
+        results['W{}'.format(p)] = 2 * Cp ** (.5 / p) * np.expm1(d2) ** (.5 / p)
+    return results
+
+
+def _compute_norm_if_needed(var):
+    if isinstance(var, torch.Tensor):
+        var = var.detach().cpu().numpy()
+    if np.asarray(var).ndim == 2:
+        return np.linalg.norm(var, ord=2)
+    return var
+
+
+def error_bounds(*, W1=np.inf, W2=np.inf, q_var=np.inf, p_var=np.inf):
+    """Mean / std / covariance error bounds (diagnostics.py:73-103, :201-219)."""
+    qv, pv = _compute_norm_if_needed(q_var), _compute_norm_if_needed(p_var)
+    min_var = qv if pv is None else np.min([qv, pv], axis=0)
+    return dict(mean_error=min(W1, W2), std_error=W2,
+                cov_error=2 * (np.sqrt(min_var) * W2 + W2 ** 2))
+
+
+def all_diagnostics(log_weights, *, samples=None, moment_bound_fn=None, q_var=None, p_var=None,
+                    log_norm_bound=None):
+    """All VI diagnostics (diagnostics.py:13-64)."""
+    d2, log_norm_bound = divergence_bound(log_weights, log_norm_bound=log_norm_bound,
+                                          return_log_norm_bound=True)
+    results = wasserstein_bounds(d2, samples=samples, moment_bound_fn=moment_bound_fn)
+    if q_var is None and samples is not None:
+        x = to_dev(samples)
+        q_var = torch.cov(x if x.dim() == 1 else x.t()).cpu().numpy()     # np.cov(samples.T)
+    results.update(error_bounds(q_var=q_var, p_var=p_var, **results))
+    results['d2'] = d2
+    results['log_norm_bound'] = log_norm_bound
+    return results

@@ -282,3 +282,323 @@ class WindowedAdagrad(StochasticGradientOptimizer):
             self._history.pop(0)
         mean_sq = sum(self._history) / len(self._history)
         return grad / _sqrt(self._jitter + mean_sq)
+
+
+# ---------------------------------------------------------------------------------------------
+# FASO / RAABBVI: host control loops (optimization.py:479-931).  Per iteration they make exactly
+# the three hot-path calls objective(vp) -> descent_direction -> update; the iterate history
+# stays on the device and only the windows inspected by the convergence checks are copied back.
+# ---------------------------------------------------------------------------------------------
+import time as _time
+
+from ._mc_diagnostics import MCSE, R_hat_convergence_check
+
+__all__ += ['FASO', 'RAABBVI']
+
+
+def _window(hist, W):
+    """Last W iterates as a host [W, P] array."""
+    return torch.stack(hist[-int(W):]).cpu().numpy()
+
+
+class FASO(Optimizer):
+    """Fixed-learning-rate stochastic optimisation with R-hat / MCSE stopping (:479-633)."""
+
+    def __init__(self, sgo, *, mcse_threshold=0.1, W_min=200, ESS_min=None, k_check=None):
+        if not isinstance(sgo, StochasticGradientOptimizer):
+            raise ValueError('sgo must be a subclass of StochasticGradientOptimizer')
+        self._sgo = sgo
+        self._mcse_threshold = mcse_threshold
+        self._W_min = W_min
+        self._ESS_min = W_min // 8 if ESS_min is None else ESS_min
+        self._k_check = W_min if k_check is None else k_check
+        if mcse_threshold <= 0:
+            raise ValueError('"mcse_threshold" must be greater than zero')
+        if W_min <= 0:
+            raise ValueError('"W_min" must be greater than zero')
+        if self._k_check <= 0:
+            raise ValueError('"k_check" must be greater than zero')
+        if self._ESS_min <= 0:
+            raise ValueError('"ESS_min" must be greater than zero')
+
+    def _mcse_of_window(self, iterates, objective, dim_param):
+        from .approximations import MFGaussian
+        W = iterates.shape[0]
+        if isinstance(objective.approx, MFGaussian):
+            # MCSE(mu / sigma, log sigma), constant coordinates dropped (:575-590)
+            dim = int(dim_param / 2)
+            still = (iterates[W - 2, :] - iterates[W - 1, :]) == 0
+            if np.any(still):
+                iterates = np.delete(iterates, np.argwhere(still), 1)
+            mean_log_sd = np.mean(iterates[:, -dim:], axis=0)
+            ess, mcse = MCSE(iterates)
+            mcse = np.concatenate((mcse[:dim] / np.exp(mean_log_sd), mcse[-dim:]))
+            return ess, mcse
+        return MCSE(iterates)
+
+    def optimize(self, n_iters, objective, init_param):
+        from .objectives import VariationalObjective
+        sgo = self._sgo
+        diagnostics = sgo._diagnostics
+        k_conv = k_stopped = k_Rhat = None
+        lr = sgo._learning_rate
+        host_init = np.array(init_param.detach().cpu().numpy() if isinstance(init_param, torch.Tensor)
+                             else init_param, dtype=np.float64)
+        vp = to_dev(host_init).clone()
+        plain_update = isinstance(objective, VariationalObjective) and \
+            type(objective).update is VariationalObjective.update
+        hist = defaultdict(list)
+        iterate_average = host_init.copy()
+        if diagnostics:
+            hist['iterate_average_k_history'].append(0)
+            hist['iterate_average_history'].append(iterate_average)
+        opt_time = 0.0
+        mcse = ess = None
+        W_check = None
+        progress = getattr(sgo, 'progress', True)
+        bar = tqdm.trange(n_iters, disable=not progress)
+        try:
+            for k in bar:
+                t0 = _time.perf_counter()
+                value, grad = objective(vp)
+                if not isinstance(grad, torch.Tensor):
+                    grad = to_dev(grad)
+                    value = torch.as_tensor(float(value), dtype=F64, device=grad.device)
+                hist['value_history'].append(value.detach().reshape(()))
+                hist['grad_history'].append(grad)
+                if plain_update:
+                    direction = sgo._fused_step(vp, grad, diagnostics)
+                else:
+                    direction = sgo.descent_direction(grad)
+                    vp = to_dev(objective.update(vp, lr * direction))
+                hist['variational_param_history'].append(vp.clone())
+                if diagnostics:
+                    hist['descent_dir_history'].append(direction.clone())
+                opt_time += _time.perf_counter() - t0
+
+                if k_conv is None and k % self._k_check == 0:
+                    W_upper = int(0.95 * k)
+                    if W_upper > self._W_min:
+                        windows = np.linspace(self._W_min, W_upper, num=5, dtype=int)
+                        recent = _window(hist['variational_param_history'], W_upper)
+                        ok, best_W = R_hat_convergence_check(recent, windows)
+                        iterate_average = np.mean(recent[-best_W:], axis=0)
+                        if diagnostics:
+                            hist['iterate_average_k_history'].append(k)
+                            hist['iterate_average_history'].append(iterate_average)
+                        if ok:
+                            k_Rhat, k_conv, W_check = k, k - best_W, best_W
+
+                if k_conv is not None and k - k_conv == W_check:
+                    W = W_check
+                    iterates = _window(hist['variational_param_history'], W)
+                    iterate_average = np.mean(iterates, axis=0)
+                    if diagnostics and k not in hist['iterate_average_k_history']:
+                        hist['iterate_average_k_history'].append(k)
+                        hist['iterate_average_history'].append(iterate_average)
+                    t1 = _time.perf_counter()
+                    ess, mcse = self._mcse_of_window(iterates, objective, host_init.size)
+                    mcse_time = _time.perf_counter() - t1
+                    if diagnostics:
+                        hist['ess_and_mcse_k_history'].append(k)
+                        hist['ess_history'].append(ess)
+                        hist['mcse_history'].append(mcse)
+                    if np.max(mcse) < self._mcse_threshold and np.min(ess) > self._ESS_min:
+                        k_stopped = k
+                        break
+                    ratio = (opt_time / k) / (mcse_time / W)
+                    W_check = int(max(1.05, 1 + 1 / np.sqrt(1 + ratio)) * W_check + 1)
+                if progress and k % self._k_check == 0:
+                    recent = torch.stack(hist['value_history'][max(0, k - 1000):k + 1])
+                    bar.set_description('average loss = {:,.5g} | R hat {}|'.format(
+                        float(recent.mean()), 'converged' if k_conv is not None else 'not converged'))
+        except (KeyboardInterrupt, StopIteration):  # pragma: no cover
+            pass
+        finally:
+            bar.close()
+        if k_stopped is None:
+            if k_conv is None:
+                print('WARNING: stationarity not reached after maximum number of iterations')
+                print('WARNING: try incresing the learning rate or the maximum number of iterations')
+            else:
+                print('WARNING: stationarity reached but MCSE too large and/or ESS too small')
+                print('WARNING: maximum MCSE = {:.3g}'.format(np.max(mcse)))
+                print('WARNING: minimum ESS = {:.1f}'.format(np.min(ess)))
+        else:
+            print('Convergence reached at iteration', k_stopped)
+        results = _to_numpy_results(hist)
+        results['k_conv'] = k_conv
+        results['k_Rhat'] = k_Rhat
+        results['k_stopped'] = k_stopped
+        results['opt_param'] = iterate_average
+        return results
+
+
+def _posterior_mean_regression(y, x, w, rho, fixed_kappa=None):
+    """Deterministic replacement for RAABBVI's Stan/NUTS fit of
+        y_n ~ N(log_c + 2 log(rho^-kappa - 1) + 2 kappa x_n, sigma) ^ w_n,
+        kappa ~ U(0,1), log_c ~ Cauchy(0,10), sigma ~ half-Cauchy(0,10)
+    (stan_models/weighted_lin_regression*.stan, optimization.py:677-725): posterior means of
+    kappa and log_c by quadrature on a (kappa, log_c, sigma) grid."""
+    y, x, w = (np.asarray(v, dtype=np.float64) for v in (y, x, w))
+    kap = np.array([fixed_kappa]) if fixed_kappa is not None else (np.arange(200) + 0.5) / 200
+    off = 2 * np.log(rho ** (-kap) - 1)[:, None] + 2 * kap[:, None] * x[None, :]     # [K, N]
+    resid0 = y[None, :] - off                                                          # = log_c + noise
+    centre = np.sum(w * resid0, axis=1) / np.sum(w)
+    spread = max(np.sqrt(np.max(np.sum(w * (resid0 - centre[:, None]) ** 2, axis=1) / np.sum(w))), 1e-3)
+    lc = np.linspace(centre.min() - 12 * spread - 1, centre.max() + 12 * spread + 1, 400)
+    sig = np.exp(np.linspace(np.log(spread * 1e-2), np.log(spread * 1e2 + 10), 160))
+    # sum_n w_n (r_n - lc)^2 = A - 2 lc B + lc^2 C
+    A = np.sum(w * resid0 ** 2, axis=1)[:, None]
+    B = np.sum(w * resid0, axis=1)[:, None]
+    C = np.sum(w)
+    sse = A - 2 * lc[None, :] * B + lc[None, :] ** 2 * C                               # [K, L]
+    logpost = (-0.5 * sse[:, :, None] / sig[None, None, :] ** 2 - C * np.log(sig)[None, None, :]
+               - np.log1p((lc[None, :, None] / 10) ** 2) - np.log1p((sig[None, None, :] / 10) ** 2)
+               + np.log(sig)[None, None, :])            # + log sigma: grid is uniform in log sigma
+    p = np.exp(logpost - logpost.max())
+    p /= p.sum()
+    kappa = float(np.sum(p.sum(axis=(1, 2)) * kap))
+    log_c = float(np.sum(p.sum(axis=(0, 2)) * lc))
+    return kappa, np.exp(log_c)
+
+
+class RAABBVI(FASO):
+    """Robust, automated, accurate BBVI: FASO runs at a decreasing learning rate with the
+    inefficiency-index termination rule (optimization.py:635-931).  The NUTS regression for
+    (kappa, c) is replaced by deterministic quadrature over the same posterior."""
+
+    def __init__(self, sgo, *, rho=0.5, iters0=1000, accuracy_threshold=0.1, inefficiency_threshold=1.0,
+                 init_rmsprop=False, **kwargs):
+        super().__init__(sgo, **kwargs)
+        self._iters0 = iters0
+        self._rho = rho
+        self._accuracy_threshold = accuracy_threshold
+        self._inefficiency_threshold = inefficiency_threshold
+        self._init_rmsprop = init_rmsprop
+        if rho < 0 or rho > 1:
+            raise ValueError('"rho" must be between zero and one')
+
+    def _averaged(self):
+        return isinstance(self._sgo, (AveragedRMSProp, AveragedAdam))
+
+    def weighted_linear_regression(self, model, y, x, s=9, a=0.25, n_chains=4):
+        N = len(y)
+        w = np.array(1 / (1 + np.arange(N)[::-1] ** 2 / s) ** a)
+        kappa, c = _posterior_mean_regression(y, x, w, self._rho, 1.0 if self._averaged() else None)
+        return None, kappa, c
+
+    def wls(self, x, y, s=9, a=0.25):
+        n = y.size
+        Xd = np.column_stack((np.ones(n), x))
+        w = 1 / (1 + np.arange(n)[::-1] ** 2 / s ** 2) ** a
+        # least squares on the sqrt(w)-scaled system; with a single point (which the reference
+        # hands to np.linalg.inv of a singular 2x2, :754) this is the minimum-norm fit
+        sw = np.sqrt(w)
+        beta = np.linalg.lstsq(sw[:, None] * Xd, sw * np.asarray(y, dtype=float), rcond=None)[0]
+        return beta[0], beta[1]
+
+    def convg_iteration_trend_detection(self, slope):
+        return bool(slope < 0)
+
+    def optimize(self, K_max, objective, init_param):
+        if not objective.approx.supports_kl:
+            print('WARNING: approximation family does not support KL. Using FASO.', flush=True)
+            return super().optimize(K_max, objective, init_param)
+        sgo = self._sgo
+        diagnostics = sgo._diagnostics
+        rho = self._rho
+        k_new, k, k_total, k_add = -1, 0, 0, 0
+        k_stopped_final = None
+        current = np.array(init_param, dtype=np.float64, copy=True)
+        h = defaultdict(list)
+        h['iterate_average_curr_hist'].append(current)
+        h['k_mcse'].append(0)
+        stopped = False
+        index = None
+        try:
+            while not stopped:
+                K_max -= (k_new + 1)
+                previous = current
+                if k == 0 and self._init_rmsprop:
+                    first = RMSProp(learning_rate=sgo._learning_rate, diagnostics=diagnostics)
+                    first.progress = getattr(sgo, 'progress', True)
+                    opt = FASO(sgo=first).optimize(K_max, objective, current)
+                else:
+                    opt = FASO.optimize(self, K_max, objective, current)
+                if opt['k_stopped'] is not None and k != 0:
+                    h['conv_iters_hist'].append(opt['k_stopped'])
+                current = opt['opt_param']
+                h['iterate_average_curr_hist'].append(current)
+                k_new = opt['k_stopped']
+                shift = k_new is not None
+                h['k_Rhat'].append(opt['k_Rhat'] + k_add if opt['k_Rhat'] is not None and shift else opt['k_Rhat'])
+                h['k_conv'].append(opt['k_conv'] + k_add if opt['k_conv'] is not None and shift else opt['k_conv'])
+                h['k_mcse'].append(k_new + k_add if shift else k_new)
+                for key in ('variational_param_history', 'value_history', 'grad_history'):
+                    h[key].extend(opt[key])
+                if diagnostics:
+                    h['descent_dir_history'].extend(opt['descent_dir_history'])
+                    if opt['k_conv'] is not None:
+                        h['ess_history'].extend(opt.get('ess_history', []))
+                        h['mcse_history'].extend(opt.get('mcse_history', []))
+                        h['final_mcse_history'].append(h['mcse_history'][-1] if len(h['mcse_history'])
+                                                       else h['mcse_history'])
+                    if k == 0:
+                        h['iterate_average_k_history'].extend(opt['iterate_average_k_history'])
+                        h['iterate_average_history'].extend(opt['iterate_average_history'])
+                    else:
+                        h['iterate_average_k_history'].extend(opt['iterate_average_k_history'][1:] + k_add)
+                        h['iterate_average_history'].extend(opt['iterate_average_history'][1:, :])
+                k_add = h['iterate_average_k_history'][-1] if len(h['iterate_average_k_history']) else k_add
+                if k_new is None:
+                    break
+                k_total += k_new
+                sgo._learning_rate *= rho
+                self._mcse_threshold *= rho
+                if self._averaged():
+                    sgo.reset_state()
+                if len(h['learning_rate_hist']) > 0:
+                    approx = objective.approx
+                    h['SKL_history'].append(approx.kl(previous, current) + approx.kl(current, previous))
+                    y_wlr = np.log(h['SKL_history'])
+                    x_wlr = np.log(h['learning_rate_hist'])
+                    _, kappa, c = self.weighted_linear_regression(None, y_wlr, x_wlr)
+                    h['kappa_hist'].append(kappa)
+                    h['c_hist'].append(c)
+                    if len(h['learning_rate_hist']) > 1:
+                        last_lr = h['learning_rate_hist'][-1]
+                        relative_skl = rho ** kappa + self._accuracy_threshold / (np.sqrt(c) * last_lr ** kappa)
+                        curr_iters = h['conv_iters_hist'][-1]
+                        _, slope = self.wls(np.log(h['learning_rate_hist']), np.log(h['conv_iters_hist']))
+                        if self.convg_iteration_trend_detection(slope):
+                            xs, ys = h['learning_rate_hist'], h['conv_iters_hist']
+                        else:
+                            xs, ys = h['learning_rate_hist'][1:], h['conv_iters_hist'][1:]
+                        b0, b1 = self.wls(np.log(xs), np.log(ys))
+                        pred_iters = int(np.exp(b0) * (rho * last_lr) ** b1)
+                        h['predicted_iters_hist'].append(pred_iters)
+                        relative_iters = pred_iters / (curr_iters + self._iters0)
+                        index = relative_skl * relative_iters
+                        h['stopping_crt'].append(index)
+                        if index > self._inefficiency_threshold:
+                            stopped = True
+                            k_stopped_final = k_total
+                            h['k_stopped_final_hist'].append(k_total)
+                            break
+                h['learning_rate_hist'].append(sgo._learning_rate)
+                k += 1
+        except (KeyboardInterrupt, StopIteration):  # pragma: no cover
+            pass
+        if stopped:
+            print('Termination rule reached at iteration', k_total)
+            print('Inefficiency Index:', index)
+        else:
+            print('WARNING: maximum number of iterations reached before stopping rule was triggered')
+        results = {key: np.array(v) for key, v in h.items() if key not in ('k_Rhat', 'k_mcse', 'k_conv')}
+        results['opt_param'] = current
+        results['k_stopped_final'] = k_stopped_final
+        results['k_Rhat'] = h['k_Rhat']
+        results['k_mcse'] = h['k_mcse']
+        results['k_conv'] = h['k_conv']
+        return results
