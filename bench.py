@@ -39,6 +39,8 @@ def parse():
     ap.add_argument('--dim', type=int, default=DIM)
     ap.add_argument('--mc', type=int, default=S_MC)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-psis', action='store_true')
+    ap.add_argument('--psis-draws', type=int, default=100000000)
     return ap.parse_args()
 
 
@@ -179,6 +181,68 @@ def matmul_peak_tflops(torch, dtype, tf32, n):
     return 2.0 * n ** 3 / best / 1e12
 
 
+def bench_psis(torch, vb, args):
+    """Second headline metric (BASELINE.json: 'PSIS draws/s'): psislw + CUBO/ELBO moments on n
+    float64 log-weights resident in HBM (BASELINE configs[4] size, one GPU).  HBM roofline with
+    24 algorithmic bytes per draw (lw read twice, smoothed weights written once)."""
+    n = args.psis_draws
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(DATA_SEED + 5)
+    # log p - log q for p = t_10, q = t_40 per coordinate summed over 4 coordinates (heavy-ish tail)
+    lw = torch.zeros(n, device='cuda', dtype=torch.float64)
+    for _ in range(2):
+        z = torch.randn(n, generator=gen, device='cuda', dtype=torch.float64)
+        lw += -5.5 * torch.log1p(z * z / 10.0) + 20.5 * torch.log1p(z * z / 40.0)
+        del z
+    out = torch.empty_like(lw)
+    for _ in range(3):
+        vb.psislw_device(lw, out)
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        _, res, _, _ = vb.psislw_device(lw, out)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / reps
+    r = res.cpu().numpy()
+    hbm, how = measured_peak('hbm_gbs', 6650.0)
+    achieved = 24.0 * n / sec / 1e9
+    # end to end from HOST memory: H2D of the weights, PSIS, D2H of k-hat and the smoothed weights
+    host = torch.empty(min(n, 20000000), dtype=torch.float64).pin_memory()
+    host.copy_(lw[:host.numel()])
+    hout = torch.empty_like(host).pin_memory()
+    dev_in = torch.empty(host.numel(), device='cuda', dtype=torch.float64)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dev_in.copy_(host, non_blocking=True)
+    _, res2, _, _ = vb.psislw_device(dev_in, dev_in)
+    hout.copy_(dev_in, non_blocking=True)
+    k2 = float(res2[0].item())
+    torch.cuda.synchronize()
+    e2e = host.numel() / (time.perf_counter() - t0)
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import viabel_oracle as vo
+        m = min(n, 5000000)
+        sample = lw[:m].cpu().numpy()
+        t0 = time.perf_counter()
+        with np.errstate(all='ignore'):
+            o, k = vo.psislw_1d(sample)
+            vo.divergence_bound(o)
+        cpu = {'value': m / (time.perf_counter() - t0), 'unit': 'draws/s', 'cores': 1, 'kind': 'port',
+               'sample': 'numpy oracle psislw + divergence_bound on the first %d draws' % m}
+    del lw, out
+    return {'metric': 'psis_draws_per_sec', 'value': n / sec, 'unit': 'draws/s', 'n_draws': n, 'ms': sec * 1e3,
+            'khat': float(r[0]), 'n_tail': int(r[2]), 'status': int(r[6]),
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s', 'frac': achieved / hbm,
+                         'traffic': None, 'peak_source': how, 'algorithmic_bytes_per_draw': 24},
+            'e2e': {'value': e2e, 'unit': 'draws/s', 'n_draws': host.numel(), 'h2d_bytes': host.numel() * 8,
+                    'd2h_bytes': host.numel() * 8 + 8, 'khat': k2},
+            'cpu_baseline': cpu}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -292,6 +356,8 @@ def run_b200(args):
                 'bf16_peak_tflops': bf16_peak, 'bf16_peak_source': how,
                 'algorithmic_flops_per_launch': flops, 'algorithmic_bytes_per_launch': (hi - lo) * d * 8.0}
 
+    psis = bench_psis(torch, vb, args) if world == 1 and not args.no_psis else None
+
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         rows = min(CPU_SAMPLE_ROWS, N)
@@ -314,6 +380,7 @@ def run_b200(args):
         'gpu_launches': launches_per_step * args.steps,
         'roofline': roofline,
         'cpu_baseline': cpu_baseline,
+        'psis': psis,
     }
     print(json.dumps(line))
     if world > 1:
