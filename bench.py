@@ -268,9 +268,12 @@ def run_b200(args):
     y = torch.where(torch.rand(hi - lo, generator=gen, device=dev, dtype=torch.float64) < p, 1.0, -1.0)
     del p
 
-    path = 'f64' if args.path == 'auto' else args.path
+    path = 'fast' if args.path == 'auto' else args.path
     model = vb.LogisticRegression(X, y, prior_scale=10.0, sharded=world > 1)
     approx = vb.MFGaussian(d, seed=DRAW_SEED)
+    if path == 'fast':
+        model.enable_fast_path()          # tcgen05 + TMA, fp16 hi/lo operand splits, 1e-4 tolerance
+        approx.quantize_draws = 2         # fp16-exact Philox normals (exact tensor-core operands)
     objective = vb.ExclusiveKL(approx, model, S)
     opt = vb.RMSProp(0.01)
     vp = torch.as_tensor(approx.init_param(), device=dev)

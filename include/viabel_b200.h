@@ -58,8 +58,8 @@ int vb_device_sm_count(void);
  * Base draws.  Replaces numpy RandomState.randn / standard_t / chisquare at
  * approximations.py:216, :274, :345-347.  Philox4x32-10, counter = element index + offset,
  * so any sub-range can be regenerated and every rank draws identical values.
- * quantize: 0 = full precision; 1 = round each draw to bfloat16 (8-bit mantissa), which
- * makes the draws exact operands of the tensor-core fast path.
+ * quantize: 0 = full precision; 1 = round each draw to bfloat16 (8-bit mantissa); 2 = round to
+ * float16 (11-bit mantissa).  Quantised draws are exact operands of the tensor-core fast path.
  * ------------------------------------------------------------------------------------- */
 int vb_philox_normal_f64(double* out, int64_t n, uint64_t seed, uint64_t offset, int quantize,
                          cudaStream_t stream);
@@ -97,6 +97,30 @@ int vb_glm_sweep_f64(const double* X, int64_t ldx, const double* y, int64_t N, i
                      const double* theta, const double* base, const double* w, const double* aux,
                      int64_t S, int want_grad, double* out_ll, double* out_gmu, double* out_ge,
                      void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * GLM model plugin, tensor-core fast path (logistic link; tolerance 1e-4 relative).
+ * Same contract and outputs (float64 sums) as vb_glm_sweep_f64, but the two contractions run
+ * as tcgen05.mma on fp16 hi+lo operand splits fed by TMA, with fp32 accumulators in TMEM.
+ *
+ * vb_glm_fast_create: one-off preprocessing of the model data into `model_mem` (1024-byte
+ *   aligned device memory of vb_glm_fast_model_bytes(N,d) bytes, owned by the caller and kept
+ *   alive for the lifetime of the handle): y*X split into fp16 hi and lo, zero padded.
+ *   absmax_host (optional, HOST pointer) receives max|y*X|; values above 3e4 do not fit the
+ *   fp16 operand range and are rejected with VB_ERR_UNSUPPORTED (use the float64 path).
+ * vb_glm_fast_sweep: S <= 256 samples per call.  `debug` (optional, device, 49152 floats per
+ *   CTA) receives the raw accumulators of each CTA's first tile for testing.
+ * Workspace and model_mem must be 1024-byte aligned.
+ * ------------------------------------------------------------------------------------- */
+size_t vb_glm_fast_model_bytes(int64_t N, int d);
+size_t vb_glm_fast_workspace_bytes(int64_t N, int d, int64_t S);
+int vb_glm_fast_create(void** handle, const double* X, int64_t ldx, const double* y, int64_t N, int d,
+                       int link, void* model_mem, size_t model_bytes, float* absmax_host,
+                       cudaStream_t stream);
+int vb_glm_fast_destroy(void* handle);
+int vb_glm_fast_sweep(void* handle, const double* theta, const double* base, const double* w,
+                      int64_t S, int want_grad, double* out_ll, double* out_gmu, double* out_ge,
+                      void* workspace, size_t workspace_bytes, float* debug, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Objective assembly for mean-field families on "GLM likelihood + iid Gaussian prior"

@@ -53,7 +53,7 @@ def test_philox_normal(vb):
     c = vb.MFGaussian(8, seed=4).base_draws(4)
     assert torch.equal(a, b) and not torch.equal(a, c)
     # bf16-quantised draws are exactly representable in bfloat16
-    fam.quantize_draws = True
+    fam.quantize_draws = 1
     q = fam.base_draws(100)
     assert torch.equal(q, q.to(torch.bfloat16).to(torch.float64))
 

@@ -44,6 +44,11 @@ _PROTOS = {
                                            c_int, c_double, P, P, P, P]),
     'vb_rmsprop_step_f64': (c_int, [P, P, P, P, c_int64, c_double, c_double, c_double, c_int, P]),
     'vb_adam_step_f64': (c_int, [P, P, P, P, P, c_int64, c_double, c_double, c_double, c_double, c_int, P]),
+    'vb_glm_fast_model_bytes': (c_size_t, [c_int64, c_int]),
+    'vb_glm_fast_workspace_bytes': (c_size_t, [c_int64, c_int, c_int64]),
+    'vb_glm_fast_create': (c_int, [P, P, c_int64, P, c_int64, c_int, c_int, P, c_size_t, P, P]),
+    'vb_glm_fast_destroy': (c_int, [P]),
+    'vb_glm_fast_sweep': (c_int, [P, P, P, P, c_int64, c_int, P, P, P, P, c_size_t, P, P]),
     'vb_psis_workspace_bytes': (c_size_t, [c_int64, c_double]),
     'vb_psis_tail_capacity': (c_int64, [c_int64, c_double]),
     'vb_psislw_f64': (c_int, [P, P, c_int64, c_double, c_int, P, P, P, P, c_size_t, P]),

@@ -100,7 +100,7 @@ class _MeanField(ApproximationFamily):
     def __init__(self, dim, supports_kl, seed):
         self._seed = int(seed)
         self._offset = 0
-        self.quantize_draws = False      # True: bf16-exact draws for the tensor-core fast path
+        self.quantize_draws = 0          # 1: bf16-exact, 2: fp16-exact draws (exact tensor-core operands)
         self.last_base = None
         super().__init__(dim, 2 * dim, True, supports_kl)
 

@@ -2,12 +2,16 @@
 // Replaces numpy RandomState.randn / chisquare / standard_t (reference approximations.py:216,
 // :274, :345-347).  The numpy MT19937 streams are NOT reproduced; parity is by draw injection.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
 namespace vb {
 
-__device__ __forceinline__ double quantize_bf16(double x) {
+// quantize: 1 = bfloat16 (8-bit mantissa), 2 = float16 (11-bit mantissa); both are exact operands
+// of the fp16 tensor-core path (a bf16 value in the normal fp16 range is an fp16 value)
+__device__ __forceinline__ double quantize_draw(double x, int mode) {
+  if (mode == 2) return (double)__half2float(__float2half_rn((float)x));
   return (double)__bfloat162float(__float2bfloat16_rn((float)x));
 }
 
@@ -43,8 +47,8 @@ __global__ void philox_normal_kernel(T* __restrict__ out, int64_t n, uint64_t se
       z1 = a0;
     }
     if (quantize) {
-      z0 = quantize_bf16(z0);
-      z1 = quantize_bf16(z1);
+      z0 = quantize_draw(z0, quantize);
+      z1 = quantize_draw(z1, quantize);
     }
     out[2 * p] = (T)z0;
     if (2 * p + 1 < n) out[2 * p + 1] = (T)z1;
@@ -93,7 +97,7 @@ __global__ void philox_student_t_kernel(double* __restrict__ out, int64_t n, dou
     normal_pair(ph, e, 2, z, unused);
     const double chi2 = 2.0 * gamma_draw(ph, e, 3, 0.5 * df);
     double tv = z / sqrt(chi2 / df);
-    out[i] = quantize ? quantize_bf16(tv) : tv;
+    out[i] = quantize ? quantize_draw(tv, quantize) : tv;
   }
 }
 

@@ -5,6 +5,8 @@ The reference calls user Python under autograd (models.py:27-39).  Here a model 
 built-in plugin whose S x N likelihood contraction runs as one fused CUDA sweep, or wraps a
 user callable on CUDA tensors with an explicit gradient (`Model(log_density, grad)`).
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -79,7 +81,51 @@ class GLMModel(Model):
         self.process_group = process_group
         self._ws = None
         self._ws_S = -1
+        self._fast = None          # (handle, model_mem, workspace) of the tensor-core path
+        self.path = 'f64'
         super().__init__(self._logp)
+
+    # -- tensor-core fast path ---------------------------------------------------------------------
+    @staticmethod
+    def _aligned_bytes(nbytes, align=1024):
+        buf = torch.empty(nbytes + align, dtype=torch.uint8, device=device())
+        off = (-buf.data_ptr()) % align
+        return buf[off:off + nbytes]
+
+    def enable_fast_path(self):
+        """Preprocess the data for the tcgen05 path (fp16 hi+lo split of y*X) and route sweeps of
+        up to 256 samples through it.  Raises NotImplementedError when the link or the data range
+        is not supported; the float64 path stays available via `path = 'f64'`."""
+        if self._fast is None:
+            lib = _lib.lib
+            nbytes = lib.vb_glm_fast_model_bytes(self.N, self.dim)
+            mem = self._aligned_bytes(nbytes)
+            handle = ctypes.c_void_p()
+            absmax = ctypes.c_float(0.0)
+            _lib.check(lib.vb_glm_fast_create(ctypes.byref(handle), _lib.ptr(self.X), self.X.stride(0),
+                                              _lib.ptr(self.y), self.N, self.dim, self.link, _lib.ptr(mem),
+                                              mem.numel(), ctypes.byref(absmax), _lib.stream()))
+            ws = self._aligned_bytes(lib.vb_glm_fast_workspace_bytes(self.N, self.dim, 256))
+            self._fast = (handle, mem, ws)
+            self.absmax = absmax.value
+        self.path = 'fast'
+        return self
+
+    def __del__(self):
+        try:
+            if self._fast is not None:
+                _lib.lib.vb_glm_fast_destroy(self._fast[0])
+        except Exception:
+            pass
+
+    def _sweep_fast(self, theta, base, w, want_grad, out, debug=None):
+        S, d = int(theta.shape[0]), self.dim
+        handle, _, ws = self._fast
+        ll, gmu, ge = out[:S], out[S:S + d], out[S + d:]
+        _lib.check(_lib.lib.vb_glm_fast_sweep(
+            handle, _lib.ptr(theta), _lib.ptr(base) if want_grad else None, _lib.ptr(w), S,
+            int(bool(want_grad)), _lib.ptr(ll), _lib.ptr(gmu) if want_grad else None,
+            _lib.ptr(ge) if want_grad else None, _lib.ptr(ws), ws.numel(), _lib.ptr(debug), _lib.stream()))
 
     # -- fused sweep -----------------------------------------------------------------------------
     def _workspace(self, S):
@@ -100,9 +146,16 @@ class GLMModel(Model):
         when want_grad is False.  Sums are all-reduced across ranks when sharded."""
         S = int(theta.shape[0])
         d = self.dim
-        ws = self._workspace(S)
         out = torch.empty(S + 2 * d, dtype=F64, device=device())
         ll, gmu, ge = out[:S], out[S:S + d], out[S + d:]
+        if self.path == 'fast' and S <= 256 and aux is None:
+            self._sweep_fast(theta, base, w, want_grad, out)
+            if want_grad:
+                self._allreduce(out)
+                return ll, gmu, ge
+            self._allreduce(ll)
+            return ll, None, None
+        ws = self._workspace(S)
         _lib.check(_lib.lib.vb_glm_sweep_f64(
             _lib.ptr(self.X), self.X.stride(0), _lib.ptr(self.y), self.N, d, self.link,
             _lib.ptr(theta), _lib.ptr(base) if want_grad else None, _lib.ptr(w), _lib.ptr(aux), S,
