@@ -13,7 +13,16 @@
 // models.py:27-39, objectives.py:161-167).  Tolerance of this path: 1e-4 relative (BASELINE.json).
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue.
-// Shared memory: 5 x 32 KB operand ring, 64 KB R tile, barriers.  TMEM: Z 256 cols, Tt 2 x 128 cols.
+// Shared memory: 10 x 16 KB operand ring, 64 KB R tile, barriers.  TMEM: Z 256 cols, Tt 2 x 128 cols.
+//
+// HBM layout (chosen for the kernel, produced once by vb_glm_fast_create):
+//   Xt_h, Xt_l : fp16 [numTiles * d_pad][128]   "tile-transposed": for each 128-row tile the d_pad x 128
+//                block (column j of the tile = one 256-byte row) is contiguous, so GEMM1 reads it as an
+//                MN-major A operand and E2's column-owning threads read 128-byte rows with LDS.128.
+//   Tt_h, Tt_l : fp16 [d_pad][256]  Theta^T (MN-major B operand), rebuilt every sweep
+//   E          : fp16 [256][d_pad]  base draws (MN-major A operand of GEMM2), rebuilt every sweep
+// All operands are MN-major with the 128-byte swizzle, so the K extent of a pipeline stage is free:
+// GEMM1 streams K = 32 per stage (16 KB for X hi+lo, 16 KB each for Theta lo / hi).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -24,8 +33,8 @@ namespace fast {
 
 constexpr int kBM = 128;
 constexpr int kSP = 256;                 // padded sample count (UMMA N of GEMM1, K of GEMM2)
-constexpr int kSlotBytes = 32768;
-constexpr int kNumSlots = 5;
+constexpr int kSlotBytes = 16384;
+constexpr int kNumSlots = 10;
 constexpr int kRingBytes = kSlotBytes * kNumSlots;      // 163840
 constexpr int kRBytes = kBM * kSP * 2;                  // 65536
 constexpr int kMiscBytes = 3072;
@@ -135,27 +144,52 @@ struct Params {
   int S;           // valid samples (<= 256)
   int numTiles;
   int want_grad;
+  int ll_total_only;  // 1: only sum_s ll[s] is needed (plain ExclusiveKL value): skip the per-sample column sums
   const float* w;  // [256] sample weights, 0 beyond S
   double* ll_part;   // [grid][256]
   double* gmu_part;  // [grid][d_pad]
   double* ge_part;   // [grid][d_pad]
   float* dbg;        // optional: Z of this CTA's first tile [128][256], then Tt of j-block 0 [128][128]
+  long long* tim;    // optional: clock64 timestamps of CTA 0
 };
 
 struct Misc {
-  uint64_t full[kNumSlots], empty[kNumSlots];
+  uint64_t empty[kNumSlots];          // per 16 KB slot: consumer -> producer
+  uint64_t g1_full[4];                // per GEMM1 stage (3 slots, 48 KB), ring of 4 phases
+  uint64_t e_full[2];                 // per GEMM2 block: the 4 E slots (64 KB)
+  uint64_t x_full[2][2];              // per GEMM2 block and tile-row half: X hi + lo slots (32 KB)
   uint64_t z_full, r_full, t_full[2], t_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
-  float w[kSP];
-  float rbar[2][kBM];
+  alignas(16) float w[kSP];
+  alignas(16) float rbar[2][kBM];
+  alignas(16) float rb[kBM];
 };
 static_assert(sizeof(Misc) <= kMiscBytes, "misc smem overflow");
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// fill sequence of one tile (identical in every role):
+//   GEMM1 stage kc (K = 32):  3*kc + 0 : X  (hi n0 | hi n1 | lo n0 | lo n1, 4 KB each)
+//                             3*kc + 1 : Theta_lo^T (4 sample groups of 64, 4 KB each)
+//                             3*kc + 2 : Theta_hi^T
+//   GEMM2 block jb (128 j):   G + 8*jb + g   (g = 0..3): E rows 64g..64g+63 (2 boxes of 64 j, 8 KB each)
+//                             G + 8*jb + 4 + a (a = 0,1): X hi, n-half a (2 boxes of 64 j-rows, 8 KB each)
+//                             G + 8*jb + 6 + a          : X lo, n-half a            with G = 3*KC
 __global__ void __launch_bounds__(kThreads, 1)
 glm_fast_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
+                const __grid_constant__ CUtensorMap tmXh2, const __grid_constant__ CUtensorMap tmXl2,
                 const __grid_constant__ CUtensorMap tmTh, const __grid_constant__ CUtensorMap tmTl,
                 const __grid_constant__ CUtensorMap tmE, Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -165,13 +199,17 @@ glm_fast_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
   const uint32_t ring_u = smem_u32(ring), rtile_u = smem_u32(rtile);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KC = p.d_pad / 64, JB = p.d_pad / 128;
-  const int fillsPerTile = 3 * KC + (p.want_grad ? 4 * JB : 0);
+  const int KC = p.d_pad / 32, JB = p.d_pad / 128;
+  const int G = 3 * KC;
+  const int fillsPerTile = G + (p.want_grad ? 8 * JB : 0);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kNumSlots; ++i) {
-      mbar_init(smem_u32(&misc->full[i]), 1);
-      mbar_init(smem_u32(&misc->empty[i]), 1);
+    for (int i = 0; i < kNumSlots; ++i) mbar_init(smem_u32(&misc->empty[i]), 1);
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&misc->g1_full[i]), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&misc->e_full[i]), 1);
+      mbar_init(smem_u32(&misc->x_full[i][0]), 1);
+      mbar_init(smem_u32(&misc->x_full[i][1]), 1);
     }
     mbar_init(smem_u32(&misc->z_full), 1);
     mbar_init(smem_u32(&misc->r_full), 1);
@@ -196,116 +234,122 @@ glm_fast_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      prefetch_tmap(&tmXh); prefetch_tmap(&tmXl); prefetch_tmap(&tmTh); prefetch_tmap(&tmTl); prefetch_tmap(&tmE);
-      uint32_t fill = 0;
-      auto acquire = [&](uint32_t bytes, uint32_t& dst, uint32_t& bar) {
+      prefetch_tmap(&tmXh); prefetch_tmap(&tmXl); prefetch_tmap(&tmXh2); prefetch_tmap(&tmXl2);
+      prefetch_tmap(&tmTh); prefetch_tmap(&tmTl); prefetch_tmap(&tmE);
+      uint32_t fill = 0, sc = 0, bc = 0;
+      auto acquire = [&]() -> uint32_t {       // next ring slot, once its previous contents are consumed
         const uint32_t slot = fill % kNumSlots, par = (fill / kNumSlots) & 1;
         mbar_wait(smem_u32(&misc->empty[slot]), par ^ 1);
-        bar = smem_u32(&misc->full[slot]);
-        mbar_expect_tx(bar, bytes);
-        dst = ring_u + slot * kSlotBytes;
         ++fill;
+        return ring_u + slot * kSlotBytes;
       };
       for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
-        const int n0 = tile * kBM;
-        uint32_t dst, bar;
-        for (int kc = 0; kc < KC; ++kc) {
-          acquire(32768, dst, bar);
-          tma_load_2d(dst, &tmXh, kc * 64, n0, bar);
-          tma_load_2d(dst + 16384, &tmXl, kc * 64, n0, bar);
-          acquire(32768, dst, bar);
-          tma_load_2d(dst, &tmTh, kc * 64, 0, bar);
-          tma_load_2d(dst + 16384, &tmTh, kc * 64, 128, bar);
-          acquire(32768, dst, bar);
-          tma_load_2d(dst, &tmTl, kc * 64, 0, bar);
-          tma_load_2d(dst + 16384, &tmTl, kc * 64, 128, bar);
+        const int r0 = tile * p.d_pad;          // first row of this tile in the tile-transposed X arrays
+        for (int kc = 0; kc < KC; ++kc, ++sc) {
+          const int j0 = kc * 32;
+          const uint32_t bar = smem_u32(&misc->g1_full[sc & 3]);
+          mbar_expect_tx(bar, 3 * kSlotBytes);
+          uint32_t dst = acquire();
+          tma_load_2d(dst, &tmXh, 0, r0 + j0, bar);
+          tma_load_2d(dst + 4096, &tmXh, 64, r0 + j0, bar);
+          tma_load_2d(dst + 8192, &tmXl, 0, r0 + j0, bar);
+          tma_load_2d(dst + 12288, &tmXl, 64, r0 + j0, bar);
+          dst = acquire();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tma_load_2d(dst + g * 4096, &tmTl, 64 * g, j0, bar);
+          dst = acquire();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tma_load_2d(dst + g * 4096, &tmTh, 64 * g, j0, bar);
         }
         if (p.want_grad) {
-          for (int jb = 0; jb < JB; ++jb) {
+          for (int jb = 0; jb < JB; ++jb, ++bc) {
             const int j0 = jb * 128;
-            for (int half = 0; half < 2; ++half) {      // E for K-groups (2*half, 2*half+1)
-              acquire(32768, dst, bar);
-#pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                const int s0 = (2 * half + g) * 64;
-                tma_load_2d(dst + g * 16384, &tmE, j0, s0, bar);
-                tma_load_2d(dst + g * 16384 + 8192, &tmE, j0 + 64, s0, bar);
-              }
+            const uint32_t ebar = smem_u32(&misc->e_full[bc & 1]);
+            mbar_expect_tx(ebar, 4 * kSlotBytes);
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t dst = acquire();
+              tma_load_2d(dst, &tmE, j0, 64 * g, ebar);
+              tma_load_2d(dst + 8192, &tmE, j0 + 64, 64 * g, ebar);
             }
-            acquire(32768, dst, bar);
-            tma_load_2d(dst, &tmXh, j0, n0, bar);
-            tma_load_2d(dst + 16384, &tmXh, j0 + 64, n0, bar);
-            acquire(32768, dst, bar);
-            tma_load_2d(dst, &tmXl, j0, n0, bar);
-            tma_load_2d(dst + 16384, &tmXl, j0 + 64, n0, bar);
+            mbar_expect_tx(smem_u32(&misc->x_full[bc & 1][0]), 2 * kSlotBytes);
+            mbar_expect_tx(smem_u32(&misc->x_full[bc & 1][1]), 2 * kSlotBytes);
+            for (int a = 0; a < 2; ++a) {
+              const uint32_t dst = acquire(), xbar = smem_u32(&misc->x_full[bc & 1][a]);
+              tma_load_2d(dst, &tmXh2, 64 * a, r0 + j0, xbar);
+              tma_load_2d(dst + 8192, &tmXh2, 64 * a, r0 + j0 + 64, xbar);
+            }
+            for (int a = 0; a < 2; ++a) {
+              const uint32_t dst = acquire(), xbar = smem_u32(&misc->x_full[bc & 1][a]);
+              tma_load_2d(dst, &tmXl2, 64 * a, r0 + j0, xbar);
+              tma_load_2d(dst + 8192, &tmXl2, 64 * a, r0 + j0 + 64, xbar);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc(128, 256, 0, 0);   // Z: A = X (K-major), B = Theta (K-major)
-      constexpr uint32_t idesc2 = make_idesc(128, 128, 1, 0);   // Tt: A = E (MN-major), B = R (K-major)
-      uint32_t ltile = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x, ++ltile) {
-        const uint32_t fbase = ltile * fillsPerTile;
-        // ---- GEMM1 ----
-        for (int kc = 0; kc < KC; ++kc) {
-          uint32_t sa[3];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const uint32_t f = fbase + 3 * kc + i, slot = f % kNumSlots, par = (f / kNumSlots) & 1;
-            mbar_wait(smem_u32(&misc->full[slot]), par);
-            sa[i] = ring_u + slot * kSlotBytes;
-          }
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t xh = make_desc(sa[0] + k * 32, 16, 1024);
-            const uint64_t xl = make_desc(sa[0] + 16384 + k * 32, 16, 1024);
-            const uint64_t th = make_desc(sa[1] + k * 32, 16, 1024);
-            const uint64_t tl = make_desc(sa[2] + k * 32, 16, 1024);
-            umma_f16(tmem, xh, th, idesc1, (kc | k) ? 1u : 0u);
-            umma_f16(tmem, xl, th, idesc1, 1u);
-            umma_f16(tmem, xh, tl, idesc1, 1u);
-          }
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const uint32_t f = fbase + 3 * kc + i;
-            umma_commit(smem_u32(&misc->empty[f % kNumSlots]));
-          }
-        }
-        umma_commit(smem_u32(&misc->z_full));
-        // ---- GEMM2 ----  (r_full also means "Z has been read": the next tile may overwrite it)
-        mbar_wait(smem_u32(&misc->r_full), ltile & 1);
+    // ================================ MMA issuer (whole warp converged, one elected lane issues) ==========
+    constexpr uint32_t idesc1 = make_idesc(128, 256, 1, 1);   // Z : A = Xt (MN-major), B = Theta^T (MN-major)
+    constexpr uint32_t idesc2 = make_idesc(128, 128, 1, 0);   // Tt: A = E (MN-major),  B = R (K-major)
+    uint32_t ltile = 0, sc = 0, bc = 0;
+    for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x, ++ltile) {
+      const uint32_t fbase = ltile * fillsPerTile;
+      if (p.tim && blockIdx.x == 0 && ltile < 8 && lane == 0) p.tim[ltile * 16 + 0] = clock64();
+      // ---- GEMM1: per stage, pass 1 = Xh.Tl (Theta_lo released right after), then Xh.Th, Xl.Th ----
+      for (int kc = 0; kc < KC; ++kc, ++sc) {
+        const uint32_t f0 = fbase + 3 * kc;
+        const uint32_t s0 = f0 % kNumSlots, s1 = (f0 + 1) % kNumSlots, s2 = (f0 + 2) % kNumSlots;
+        const uint32_t ax = ring_u + s0 * kSlotBytes, bl = ring_u + s1 * kSlotBytes, bh = ring_u + s2 * kSlotBytes;
+        mbar_wait(smem_u32(&misc->g1_full[sc & 3]), (sc >> 2) & 1);
         tc_fence_after();
-        if (p.want_grad) {
-          for (int jb = 0; jb < JB; ++jb, ++tcount) {
-            const uint32_t buf = tcount & 1;
-            mbar_wait(smem_u32(&misc->t_empty[buf]), ((tcount >> 1) & 1) ^ 1);
-            tc_fence_after();
+        if (elect_one()) {
+          // MN-major operands: 16 K-rows of 128 bytes per K step (2048 B), 64-element groups along M/N at +4096
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_f16(tmem, make_desc(ax + k * 2048, 4096, 1024), make_desc(bl + k * 2048, 4096, 1024), idesc1,
+                     (kc | k) ? 1u : 0u);
+          umma_commit(smem_u32(&misc->empty[s1]));
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_f16(tmem, make_desc(ax + k * 2048, 4096, 1024), make_desc(bh + k * 2048, 4096, 1024), idesc1, 1u);
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_f16(tmem, make_desc(ax + 8192 + k * 2048, 4096, 1024), make_desc(bh + k * 2048, 4096, 1024), idesc1, 1u);
+          umma_commit(smem_u32(&misc->empty[s0]));
+          umma_commit(smem_u32(&misc->empty[s2]));
+          if (kc == KC - 1) umma_commit(smem_u32(&misc->z_full));
+        }
+        __syncwarp();
+      }
+      if (p.tim && blockIdx.x == 0 && ltile < 8 && lane == 0) p.tim[ltile * 16 + 1] = clock64();
+      // ---- GEMM2 ----  (r_full also means "Z has been read": the next tile may overwrite it)
+      mbar_wait(smem_u32(&misc->r_full), ltile & 1);
+      tc_fence_after();
+      if (p.tim && blockIdx.x == 0 && ltile < 8 && lane == 0) p.tim[ltile * 16 + 2] = clock64();
+      if (p.want_grad) {
+        for (int jb = 0; jb < JB; ++jb, ++bc) {
+          const uint32_t buf = bc & 1;
+          mbar_wait(smem_u32(&misc->t_empty[buf]), ((bc >> 1) & 1) ^ 1);
+          mbar_wait(smem_u32(&misc->e_full[buf]), (bc >> 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
             const uint32_t dT = tmem + 256 + 128 * buf;
-            for (int half = 0; half < 2; ++half) {
-              const uint32_t f = fbase + 3 * KC + 4 * jb + half, slot = f % kNumSlots, par = (f / kNumSlots) & 1;
-              mbar_wait(smem_u32(&misc->full[slot]), par);
-              tc_fence_after();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t slot = (fbase + G + 8 * jb + g) % kNumSlots;
               const uint32_t es = ring_u + slot * kSlotBytes;
 #pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                const int kg = 2 * half + g;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  // A = E^T tile: 64 j per 128-byte row, 16 s rows per K step, second 64-j group at +8 KB
-                  const uint64_t ea = make_desc(es + g * 16384 + k * 2048, 8192, 1024);
-                  const uint64_t rb = make_desc(rtile_u + kg * 16384 + k * 32, 16, 1024);
-                  umma_f16(dT, ea, rb, idesc2, (kg | k) ? 1u : 0u);
-                }
+              for (int k = 0; k < 4; ++k) {
+                // A = E^T tile: 64 j per 128-byte row, 16 s rows per K step, second 64-j group at +8 KB
+                umma_f16(dT, make_desc(es + k * 2048, 8192, 1024), make_desc(rtile_u + g * 16384 + k * 32, 16, 1024),
+                         idesc2, (g | k) ? 1u : 0u);
               }
               umma_commit(smem_u32(&misc->empty[slot]));
             }
             umma_commit(smem_u32(&misc->t_full[buf]));
           }
+          __syncwarp();
+          if (p.tim && blockIdx.x == 0 && ltile < 8 && jb < 4 && lane == 0) p.tim[ltile * 16 + 3 + jb] = clock64();
         }
       }
     }
@@ -313,7 +357,7 @@ glm_fast_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
     // ================================ epilogue warps ================================
     const int ew = warp - 2;
     const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int h = ew >> 2;             // column half
+    const int h = ew >> 2;             // column half (E1: samples, E2: tile rows)
     const int row = 32 * q + lane;     // TMEM lane = tile row (E1) or j within block (E2)
     const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
     double ll_acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -328,6 +372,7 @@ glm_fast_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
       // -------- E1: link epilogue on Z --------
       mbar_wait(smem_u32(&misc->z_full), ltile & 1);
       tc_fence_after();
+      if (p.tim && blockIdx.x == 0 && ltile < 8 && threadIdx.x == 64) p.tim[ltile * 16 + 8] = clock64();
       float rsum = 0.0f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -339,6 +384,7 @@ glm_fast_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
           for (int i = 0; i < 32; ++i) p.dbg[(size_t)blockIdx.x * 49152 + row * 256 + col0 + i] = v[i];
         }
         uint32_t packed[16];
+        float spsum = 0.0f;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float r2[2];
@@ -348,7 +394,9 @@ glm_fast_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
             const float t = fast_exp2(-fabsf(a) * 1.4426950408889634f);
             const float den = 1.0f + t;
             const float l1p = __log2f(den) * 0.6931471805599453f;
-            v[i + u] = (fmaxf(-a, 0.0f) + l1p) * rowvalid;                 // softplus(-a)
+            const float sp = (fmaxf(-a, 0.0f) + l1p) * rowvalid;           // softplus(-a)
+            v[i + u] = sp;
+            spsum += sp;
             const float sg = __fdividef(a >= 0.0f ? t : 1.0f, den);        // sigmoid(-a)
             r2[u] = sg * misc->w[col0 + i + u] * rowvalid;
             rsum += r2[u];
@@ -368,39 +416,45 @@ glm_fast_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
                 make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
           }
         }
-        // column sums of softplus over this warp's 32 rows (transpose-reduce): lane l ends with column l
+        if (p.ll_total_only) {
+          ll_acc[0] += (double)spsum;       // only the grand total is needed
+        } else {
+          // column sums of softplus over this warp's 32 rows (transpose-reduce): lane l ends with column l
 #pragma unroll
-        for (int o = 16, cnt = 16; o >= 1; o >>= 1, cnt >>= 1) {
-          const bool up = (lane & o) != 0;
+          for (int o = 16, cnt = 16; o >= 1; o >>= 1, cnt >>= 1) {
+            const bool up = (lane & o) != 0;
 #pragma unroll
-          for (int i = 0; i < cnt; ++i) {
-            const float send = up ? v[i] : v[i + cnt];
-            const float keep = up ? v[i + cnt] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            for (int i = 0; i < cnt; ++i) {
+              const float send = up ? v[i] : v[i + cnt];
+              const float keep = up ? v[i + cnt] : v[i];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
           }
+          ll_acc[c] += (double)v[0];
         }
-        ll_acc[c] += (double)v[0];
       }
       misc->rbar[h][row] = rsum;
       fence_proxy_async();       // R tile writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       epi_barrier();
       if (threadIdx.x == 64) mbar_arrive(smem_u32(&misc->r_full));
+      if (p.tim && blockIdx.x == 0 && ltile < 8 && threadIdx.x == 64) p.tim[ltile * 16 + 9] = clock64();
       if (!p.want_grad) continue;
-      // -------- E2: thread owns column j = 128*jb + row --------
+      if (h == 0) misc->rb[row] = misc->rbar[0][row] + misc->rbar[1][row];
+      epi_barrier();
+      // -------- E2: thread owns column j = 128*jb + row and the tile rows [64h, 64h+64) --------
 #pragma unroll 1
       for (int jb = 0; jb < JB; ++jb, ++tcount) {
         const uint32_t buf = tcount & 1;
-        const uint32_t fh = fbase + 3 * KC + 4 * jb + 2, fl = fh + 1;
+        const uint32_t fh = fbase + G + 8 * jb + 4 + h, fl = fh + 2;
         const uint32_t sh = fh % kNumSlots, sl = fl % kNumSlots;
+        mbar_wait(smem_u32(&misc->x_full[buf][h]), (tcount >> 1) & 1);
         mbar_wait(smem_u32(&misc->t_full[buf]), (tcount >> 1) & 1);
-        mbar_wait(smem_u32(&misc->full[sh]), (fh / kNumSlots) & 1);
-        mbar_wait(smem_u32(&misc->full[sl]), (fl / kNumSlots) & 1);
         tc_fence_after();
-        const uint8_t* xh = ring + sh * kSlotBytes + (row >> 6) * 16384;
-        const uint8_t* xl = ring + sl * kSlotBytes + (row >> 6) * 16384;
-        const int cj = row & 63;
-        const int cchunk = (cj * 2) >> 4, cbyte = (cj * 2) & 15;
+        if (p.tim && blockIdx.x == 0 && ltile < 8 && threadIdx.x == 64 && jb < 4) p.tim[ltile * 16 + 10 + jb] = clock64();
+        const int rr = row & 63;
+        const uint8_t* xh = ring + sh * kSlotBytes + (row >> 6) * 8192 + rr * 128;
+        const uint8_t* xl = ring + sl * kSlotBytes + (row >> 6) * 8192 + rr * 128;
         float ge = 0.0f, gm = 0.0f;
 #pragma unroll 1
         for (int part = 0; part < 2; ++part) {
@@ -412,36 +466,68 @@ glm_fast_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
             for (int i = 0; i < 32; ++i) p.dbg[(size_t)blockIdx.x * 49152 + 32768 + row * 128 + nb + i] = tv[i];
           }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int nn = nb + i;
-            const int off = nn * 128 + ((cchunk ^ (nn & 7)) << 4) + cbyte;
-            const float x = __half2float(*reinterpret_cast<const __half*>(xh + off)) +
-                            __half2float(*reinterpret_cast<const __half*>(xl + off));
-            ge = fmaf(x, tv[i], ge);
-            gm = fmaf(x, misc->rbar[0][nn] + misc->rbar[1][nn], gm);
+          for (int c = 0; c < 4; ++c) {
+            const int cc = 4 * part + c;                       // 16-byte chunk = 8 consecutive tile rows
+            const uint4 vh = *reinterpret_cast<const uint4*>(xh + ((cc ^ (rr & 7)) << 4));
+            const uint4 vl = *reinterpret_cast<const uint4*>(xl + ((cc ^ (rr & 7)) << 4));
+            const float4 rb0 = *reinterpret_cast<const float4*>(&misc->rb[nb + 8 * c]);
+            const float4 rb1 = *reinterpret_cast<const float4*>(&misc->rb[nb + 8 * c + 4]);
+            const float rbv[8] = {rb0.x, rb0.y, rb0.z, rb0.w, rb1.x, rb1.y, rb1.z, rb1.w};
+            const uint32_t hw[4] = {vh.x, vh.y, vh.z, vh.w}, lw[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 fh2 = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+              const float2 fl2 = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+              const float x0 = fh2.x + fl2.x, x1 = fh2.y + fl2.y;
+              ge = fmaf(x0, tv[8 * c + 2 * e], ge);
+              ge = fmaf(x1, tv[8 * c + 2 * e + 1], ge);
+              gm = fmaf(x0, rbv[2 * e], gm);
+              gm = fmaf(x1, rbv[2 * e + 1], gm);
+            }
           }
         }
         ge_acc[jb & 15] += (double)ge;
         gmu_acc[jb & 15] += (double)gm;
         tc_fence_before();
         epi_barrier();
+        if (p.tim && blockIdx.x == 0 && ltile < 8 && threadIdx.x == 64 && jb == JB - 1) p.tim[ltile * 16 + 14] = clock64();
         if (threadIdx.x == 64) {
           mbar_arrive(smem_u32(&misc->t_empty[buf]));
-          mbar_arrive(smem_u32(&misc->empty[sh]));
-          mbar_arrive(smem_u32(&misc->empty[sl]));
+#pragma unroll
+          for (int i = 4; i < 8; ++i) mbar_arrive(smem_u32(&misc->empty[(fbase + G + 8 * jb + i) % kNumSlots]));
         }
       }
     }
     // -------- per-CTA partial sums (the operand ring is idle by now: use it as scratch) --------
     double (*red)[kBM] = reinterpret_cast<double (*)[kBM]>(ring);
-    // ll: lane l of (q,h) holds column 128h + 32c + l summed over rows of quarter q -> sum the 4 quarters
-    for (int c = 0; c < 4; ++c) {
+    if (p.ll_total_only) {
+      // every thread holds a partial of the grand total: spread total / 256 over the columns
+      double tot = ll_acc[0];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
       epi_barrier();
-      if (q != 0) red[h][(q - 1) * 32 + lane] = ll_acc[c];       // 3 x 32 slots per column half
+      if (lane == 0) red[0][ew] = tot;
       epi_barrier();
-      if (q == 0) {
-        const double s = ll_acc[c] + red[h][lane] + red[h][32 + lane] + red[h][64 + lane];
-        p.ll_part[(size_t)blockIdx.x * kSP + 128 * h + 32 * c + lane] = s;
+      double s = 0.0;
+      for (int i = 0; i < kEpiWarps; ++i) s += red[0][i];
+      // padded sample columns (theta = 0) each contributed softplus(0) = ln2 (as computed in fp32) per valid row
+      int64_t rows = 0;
+      for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
+        const int64_t left = p.N - (int64_t)tile * kBM;
+        rows += left < kBM ? left : kBM;
+      }
+      s -= (double)(kSP - p.S) * (double)rows * (double)(1.0f * 0.6931471805599453f);
+      p.ll_part[(size_t)blockIdx.x * kSP + (threadIdx.x - 64)] = s / (double)p.S;
+    } else {
+      // lane l of (q,h) holds column 128h + 32c + l summed over rows of quarter q -> sum the 4 quarters
+      for (int c = 0; c < 4; ++c) {
+        epi_barrier();
+        if (q != 0) red[h][(q - 1) * 32 + lane] = ll_acc[c];       // 3 x 32 slots per column half
+        epi_barrier();
+        if (q == 0) {
+          const double s = ll_acc[c] + red[h][lane] + red[h][32 + lane] + red[h][64 + lane];
+          p.ll_part[(size_t)blockIdx.x * kSP + 128 * h + 32 * c + lane] = s;
+        }
       }
     }
     if (p.want_grad) {
@@ -468,49 +554,67 @@ glm_fast_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
 }
 
 // ---- operand preparation ------------------------------------------------------------------------
-// Xy = y*X split into fp16 hi + lo, zero padded to [N_pad][d_pad]
+// Xy = y*X split into fp16 hi + lo, written tile-transposed: Xt[(tile*d_pad + j)*128 + (n % 128)]
 __global__ void fast_prepare_x_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ y, int64_t N,
-                                      int d, int64_t N_pad, int d_pad, __half* __restrict__ Xh, __half* __restrict__ Xl,
+                                      int d, int64_t numTiles, int d_pad, __half* __restrict__ Xh, __half* __restrict__ Xl,
                                       float* __restrict__ absmax) {
-  const int64_t total = N_pad * d_pad;
+  __shared__ float tile[32][33];
   float mx = 0.0f;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t n = i / d_pad;
-    const int j = (int)(i - n * d_pad);
-    float v = 0.0f;
-    if (n < N && j < d) v = (float)(X[n * ldx + j] * y[n]);
-    const __half hi = __float2half_rn(v);
-    const __half lo = __float2half_rn(v - __half2float(hi));
-    Xh[i] = hi;
-    Xl[i] = lo;
-    mx = fmaxf(mx, fabsf(v));
+  // 32 x 32 transposes: coalesced reads along j, coalesced writes along n
+  const int64_t blocksPerTile = (int64_t)(d_pad / 32) * 4;
+  const int64_t total = numTiles * blocksPerTile;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8 threads
+  for (int64_t b = blockIdx.x; b < total; b += gridDim.x) {
+    const int64_t t = b / blocksPerTile;
+    const int rem = (int)(b - t * blocksPerTile);
+    const int jblk = rem >> 2, nblk = rem & 3;
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      const int64_t n = t * 128 + nblk * 32 + r;
+      const int j = jblk * 32 + tx;
+      float v = 0.0f;
+      if (n < N && j < d) v = (float)(X[n * ldx + j] * y[n]);
+      tile[r][tx] = v;
+      mx = fmaxf(mx, fabsf(v));
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      const int j = jblk * 32 + r;
+      const float v = tile[tx][r];
+      const __half hi = __float2half_rn(v);
+      const size_t o = ((size_t)t * d_pad + j) * 128 + nblk * 32 + tx;
+      Xh[o] = hi;
+      Xl[o] = __float2half_rn(v - __half2float(hi));
+    }
   }
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(absmax), __float_as_int(mx));
 }
 
-// Theta hi/lo, E (fp16) and weights, zero padded to [256][d_pad]
+// Theta^T hi/lo [d_pad][256], E [256][d_pad] (fp16) and weights, zero padded
 __global__ void fast_prepare_theta_kernel(const double* __restrict__ theta, const double* __restrict__ base,
                                           const double* __restrict__ w, int64_t S, int d, int d_pad,
                                           __half* __restrict__ Th, __half* __restrict__ Tl, __half* __restrict__ E,
                                           float* __restrict__ wf) {
   const int64_t total = (int64_t)kSP * d_pad;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t s = i / d_pad;
-    const int j = (int)(i - s * d_pad);
-    float t = 0.0f, e = 0.0f;
-    if (s < S && j < d) {
-      t = (float)theta[s * d + j];
-      if (base) e = (float)base[s * d + j];
+    {   // E: [s][j]
+      const int64_t s = i / d_pad;
+      const int j = (int)(i - s * d_pad);
+      float e = 0.0f;
+      if (base && s < S && j < d) e = (float)base[s * d + j];
+      E[i] = __float2half_rn(e);
     }
-    const __half hi = __float2half_rn(t);
-    Th[i] = hi;
-    Tl[i] = __float2half_rn(t - __half2float(hi));
-    E[i] = __float2half_rn(e);
+    {   // Theta^T: [j][s]
+      const int j = (int)(i / kSP);
+      const int64_t s = i - (int64_t)j * kSP;
+      float t = 0.0f;
+      if (s < S && j < d) t = (float)theta[s * d + j];
+      const __half hi = __float2half_rn(t);
+      Th[i] = hi;
+      Tl[i] = __float2half_rn(t - __half2float(hi));
+    }
   }
   for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < kSP; s += (int64_t)gridDim.x * blockDim.x)
     wf[s] = s < S ? (w ? (float)w[s] : 1.0f) : 0.0f;
@@ -542,7 +646,7 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D fp16 row-major [rows][cols] tensor, box = [box_rows][64 cols], 128-byte swizzle
+// 2-D fp16 row-major [rows][cols] tensor, box = [box_rows][64 cols] (128-byte rows), 128-byte swizzle
 static bool encode_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
@@ -557,15 +661,15 @@ static bool encode_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_
 }
 
 struct FastModel {
-  int64_t N, N_pad;
+  int64_t N, numTiles;
   int d, d_pad;
   const __half* Xh;
   const __half* Xl;
-  CUtensorMap tmXh, tmXl;
+  CUtensorMap tmXh, tmXl, tmXh2, tmXl2;
 };
 
 struct FastLayout {
-  size_t off_Th, off_Tl, off_E, off_w, off_ll, off_gmu, off_ge, off_dbg, total;
+  size_t off_Th, off_Tl, off_E, off_w, off_ll, off_gmu, off_ge, total;
   int grid;
 };
 
@@ -618,16 +722,17 @@ extern "C" int vb_glm_fast_create(void** handle, const double* X, int64_t ldx, c
   FastModel* m = new FastModel();
   m->N = N;
   m->d = d;
-  m->N_pad = ceil_div(N, kBM) * kBM;
+  m->numTiles = ceil_div(N, kBM);
   m->d_pad = (int)(ceil_div(d, 128) * 128);
+  const size_t elems = (size_t)m->numTiles * kBM * m->d_pad;
   __half* Xh = static_cast<__half*>(model_mem);
-  __half* Xl = Xh + m->N_pad * m->d_pad;
-  float* absmax = reinterpret_cast<float*>(Xl + m->N_pad * m->d_pad);
+  __half* Xl = Xh + elems;
+  float* absmax = reinterpret_cast<float*>(Xl + elems);
   m->Xh = Xh;
   m->Xl = Xl;
   cudaError_t e = cudaMemsetAsync(absmax, 0, sizeof(float), stream);
   if (e != cudaSuccess) { delete m; return set_cuda_error(e); }
-  fast_prepare_x_kernel<<<sm_count() * 8, 256, 0, stream>>>(X, ldx, y, N, d, m->N_pad, m->d_pad, Xh, Xl, absmax);
+  fast_prepare_x_kernel<<<sm_count() * 8, 256, 0, stream>>>(X, ldx, y, N, d, m->numTiles, m->d_pad, Xh, Xl, absmax);
   e = cudaGetLastError();
   if (e != cudaSuccess) { delete m; return set_cuda_error(e); }
   if (absmax_host) {
@@ -639,7 +744,9 @@ extern "C" int vb_glm_fast_create(void** handle, const double* X, int64_t ldx, c
       return set_error(VB_ERR_UNSUPPORTED, "glm_fast: |y*X| exceeds the fp16 operand range; use the float64 path");
     }
   }
-  if (!encode_2d(&m->tmXh, Xh, m->N_pad, m->d_pad, 128) || !encode_2d(&m->tmXl, Xl, m->N_pad, m->d_pad, 128)) {
+  const uint64_t rows = (uint64_t)m->numTiles * m->d_pad;
+  if (!encode_2d(&m->tmXh, Xh, rows, 128, 32) || !encode_2d(&m->tmXl, Xl, rows, 128, 32) ||
+      !encode_2d(&m->tmXh2, Xh, rows, 128, 64) || !encode_2d(&m->tmXl2, Xl, rows, 128, 64)) {
     delete m;
     return set_error(VB_ERR_CUDA, "glm_fast_create: cuTensorMapEncodeTiled failed");
   }
@@ -655,7 +762,11 @@ extern "C" int vb_glm_fast_destroy(void* handle) {
 extern "C" int vb_glm_fast_sweep(void* handle, const double* theta, const double* base, const double* w, int64_t S,
                                  int want_grad, double* out_ll, double* out_gmu, double* out_ge, void* workspace,
                                  size_t workspace_bytes, float* debug, cudaStream_t stream) {
+  // want_grad bit 0: gradients wanted; bit 1: only sum_s ll[s] is needed (each out_ll[s] receives the mean)
+  // (debug + 49152*grid floats, when debug is given, is followed by 128 int64 timestamp slots)
   FastModel* m = static_cast<FastModel*>(handle);
+  const int ll_total_only = (want_grad >> 1) & 1;
+  want_grad &= 1;
   if (!m || !theta || !out_ll || S <= 0) return set_error(VB_ERR_INVALID_ARG, "glm_fast_sweep: bad arguments");
   if (S > kSP) return set_error(VB_ERR_UNSUPPORTED, "glm_fast_sweep: at most 256 samples per sweep");
   if (want_grad && (!base || !out_gmu || !out_ge)) return set_error(VB_ERR_INVALID_ARG, "glm_fast_sweep: want_grad needs base, out_gmu, out_ge");
@@ -674,7 +785,7 @@ extern "C" int vb_glm_fast_sweep(void* handle, const double* theta, const double
   static thread_local int cached_dpad = 0;
   static thread_local CUtensorMap tmTh, tmTl, tmE;
   if (cached_ws != workspace || cached_dpad != m->d_pad) {
-    if (!encode_2d(&tmTh, Th, kSP, m->d_pad, 128) || !encode_2d(&tmTl, Tl, kSP, m->d_pad, 128) ||
+    if (!encode_2d(&tmTh, Th, m->d_pad, kSP, 32) || !encode_2d(&tmTl, Tl, m->d_pad, kSP, 32) ||
         !encode_2d(&tmE, E, kSP, m->d_pad, 64))
       return set_error(VB_ERR_CUDA, "glm_fast_sweep: cuTensorMapEncodeTiled failed");
     cached_ws = workspace;
@@ -688,19 +799,21 @@ extern "C" int vb_glm_fast_sweep(void* handle, const double* theta, const double
   p.N = m->N;
   p.d_pad = m->d_pad;
   p.S = (int)S;
-  p.numTiles = (int)ceil_div(m->N, kBM);
+  p.numTiles = (int)m->numTiles;
   p.want_grad = want_grad;
+  p.ll_total_only = ll_total_only;
   p.w = wf;
   p.ll_part = reinterpret_cast<double*>(ws + L.off_ll);
   p.gmu_part = reinterpret_cast<double*>(ws + L.off_gmu);
   p.ge_part = reinterpret_cast<double*>(ws + L.off_ge);
   p.dbg = debug;
+  p.tim = debug ? reinterpret_cast<long long*>(debug + (size_t)49152 * L.grid) : nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     VB_CUDA(cudaFuncSetAttribute(glm_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  glm_fast_kernel<<<L.grid, kThreads, kSmemBytes, stream>>>(m->tmXh, m->tmXl, tmTh, tmTl, tmE, p);
+  glm_fast_kernel<<<L.grid, kThreads, kSmemBytes, stream>>>(m->tmXh, m->tmXl, m->tmXh2, m->tmXl2, tmTh, tmTl, tmE, p);
   VB_CHECK_LAUNCH();
   // ll = -sum softplus
   reduce_partials_kernel<<<1, 256, 0, stream>>>(p.ll_part, L.grid, kSP, S, -1.0, out_ll);

@@ -118,13 +118,13 @@ class GLMModel(Model):
         except Exception:
             pass
 
-    def _sweep_fast(self, theta, base, w, want_grad, out, debug=None):
+    def _sweep_fast(self, theta, base, w, want_grad, out, debug=None, ll_total_only=False):
         S, d = int(theta.shape[0]), self.dim
         handle, _, ws = self._fast
         ll, gmu, ge = out[:S], out[S:S + d], out[S + d:]
         _lib.check(_lib.lib.vb_glm_fast_sweep(
             handle, _lib.ptr(theta), _lib.ptr(base) if want_grad else None, _lib.ptr(w), S,
-            int(bool(want_grad)), _lib.ptr(ll), _lib.ptr(gmu) if want_grad else None,
+            int(bool(want_grad)) | (2 if ll_total_only else 0), _lib.ptr(ll), _lib.ptr(gmu) if want_grad else None,
             _lib.ptr(ge) if want_grad else None, _lib.ptr(ws), ws.numel(), _lib.ptr(debug), _lib.stream()))
 
     # -- fused sweep -----------------------------------------------------------------------------
@@ -141,15 +141,17 @@ class GLMModel(Model):
         if self.sharded and torch.distributed.is_available() and torch.distributed.is_initialized():
             torch.distributed.all_reduce(buf, group=self.process_group)
 
-    def sweep(self, theta, base=None, w=None, want_grad=True, aux=None):
+    def sweep(self, theta, base=None, w=None, want_grad=True, aux=None, ll_total_only=False):
         """One pass over the observations.  Returns (ll[S], gmu[d], ge[d]); the last two are None
-        when want_grad is False.  Sums are all-reduced across ranks when sharded."""
+        when want_grad is False.  Sums are all-reduced across ranks when sharded.
+        ll_total_only: the caller only needs sum_s ll[s] (plain ExclusiveKL value); the fast path
+        then skips the per-sample column sums and returns the mean in every ll[s]."""
         S = int(theta.shape[0])
         d = self.dim
         out = torch.empty(S + 2 * d, dtype=F64, device=device())
         ll, gmu, ge = out[:S], out[S:S + d], out[S + d:]
         if self.path == 'fast' and S <= 256 and aux is None:
-            self._sweep_fast(theta, base, w, want_grad, out)
+            self._sweep_fast(theta, base, w, want_grad, out, ll_total_only=ll_total_only)
             if want_grad:
                 self._allreduce(out)
                 return ll, gmu, ge

@@ -101,7 +101,9 @@ def _mf_objective(approx, model, S, objective, alpha, var_param, base=None, seed
 
     def sweep(w):
         if glm:
-            return model.sweep(theta, e, w, True)
+            # plain ExclusiveKL only needs mean_s ll[s]; per-sample values are kept when asked for
+            total_only = objective == _lib.OBJ_EXCLUSIVE_KL and not want_logp
+            return model.sweep(theta, e, w, True, ll_total_only=total_only)
         f, G = model.logp_and_grad(theta)
         Gw = G if w is None else G * w[:, None]
         return f.contiguous(), Gw.sum(dim=0).contiguous(), (Gw * e).sum(dim=0).contiguous()
