@@ -4,11 +4,12 @@
 //
 // The reference does a full argsort of n values to find one order statistic.  Here:
 //   pass A (1 read of lw)   : global max, compaction of "candidates" >= t0 (a threshold estimated
-//                             from a strided sample so that #candidates ~ 2-3x the tail length M),
-//                             and sum exp(x - t0) over everything below t0;
-//   small kernels           : radix-select the (M+1)-th largest among the candidates (the cutoff is
-//                             an order-statistic VALUE, so this is exact), rank the <= M tail
-//                             entries by counting, Zhang-Stephens GPD fit, smoothed quantiles, LSE;
+//                             from a strided sample so that #candidates is a few times the tail
+//                             length M), and sum exp(x - t0) over everything below t0;
+//   small kernels           : histogram select of the (M+1)-th largest among the candidates (the
+//                             cutoff is an order-statistic VALUE, so this is exact), bucketed
+//                             counting rank of the <= M tail entries, Zhang-Stephens GPD fit,
+//                             smoothed quantiles, log-sum-exp;
 //   pass B (1 read, 1 write): out = x - max - lse, tail entries replaced by their smoothed values,
 //                             and sum(out), sum exp(2 out) for the CUBO / ELBO bounds.
 // Algorithmic traffic: 24 bytes per draw.  If the sample-based threshold fails (candidate buffer
@@ -20,10 +21,13 @@
 
 namespace vb {
 
-constexpr int kSampleMax = 1 << 17;
+constexpr int kSampleMax = 16384;        // 1024 threads x 16 keys held in registers
 constexpr int kSelThreads = 1024;
 constexpr int kDigitBits = 11;
 constexpr int kBins = 1 << kDigitBits;
+constexpr int kGather = 8192;            // boundary-bucket members selected in shared memory
+constexpr int kVBins = 8192;             // linear bins on the shifted tail values
+constexpr int kGpdSplit = 8;             // CTAs per quadrature point
 
 // result[] slots (doubles, device memory)
 enum { R_KHAT = 0, R_SIGMA, R_N2, R_CUTOFF, R_LSE, R_MAX, R_STATUS, R_SUMV, R_SUMEXP2V, R_M, R_NCAND, R_SMOOTHED,
@@ -35,17 +39,23 @@ struct PsisScalars {           // device-resident control block
   unsigned long long cutkey;   // key of the (M+1)-th largest raw value
   unsigned int ncand;          // candidates found by pass A
   unsigned int ntail;          // n2
-  unsigned int status;         // 0 ok, 1 fast path failed (rerun exact)
+  unsigned int status;         // 0 ok, 1 fast path failed (rerun exact), 2 internal overflow
   unsigned int strict;         // exact mode: candidates are strictly above t0
   double t0;                   // threshold as a double
   double maxv, cutoff, expcut; // max, shifted cutoff, exp(shifted cutoff)
   double body_below;           // sum exp(x - t0) over x below the threshold
   double body_cand;            // sum exp(x - max) over candidates that are not tail
   double tail_sum;             // sum exp(v) over (smoothed) tail values
-  double k, sigma, lse;
-  double sumv, sumexp2v;       // moments of v = out + lse
+  double k, sigma, lse, bhat;
+  double sumv, sumexp2v;       // moments of v = out + lse over the tail
+  double vscale;               // bins per unit of (v - cutoff)
   int smoothed;
   int M;
+  int shift;                   // digit position of the candidate histogram
+  unsigned int bstar;          // boundary bin of the candidate histogram
+  unsigned int need;           // rank (from the top) of the cutoff inside the boundary bin
+  unsigned int members;        // population of the boundary bin
+  unsigned int gcount;         // keys gathered from it
   unsigned long long prefix;   // exact-mode radix state
   unsigned long long kth;
 };
@@ -59,12 +69,87 @@ __device__ __forceinline__ double dkey_inv(unsigned long long k) {
   return __longlong_as_double((long long)b);
 }
 
+// exp(x) for x <= 0 (to ~1 ulp): x = (32 k + j) ln2/32 + r, exp = 2^k * 2^(j/32) * e^r, |r| <= ln2/64
+__constant__ double c_exp2_tab[32];
+// polynomial / reduction constants live in the constant bank so every DFMA takes them as a direct
+// operand (no per-call re-materialisation of 64-bit immediates)
+__constant__ double c_expk[10] = {46.166241308446828384 /* 32/ln2 */, 6755399441055744.0 /* 1.5 * 2^52 */,
+                                  -2.16608493865351192653e-02 /* -ln2_hi/32 */, -5.96317165397058656257e-12 /* -ln2_lo/32 */,
+                                  1.3888888888888889e-03, 8.3333333333333332e-03, 4.1666666666666664e-02,
+                                  1.6666666666666666e-01, 0.5, 8.6736173798840355e-19 /* 2^-60 */};
+// `tab` is the 32-bit shared-memory address of a per-CTA copy of c_exp2_tab (per-lane indices would
+// serialise on the constant cache)
+__device__ __forceinline__ uint32_t load_exp_table(double* tab) {
+  if (threadIdx.x < 32) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+  __syncthreads();
+  return (uint32_t)__cvta_generic_to_shared(tab);
+}
+__device__ __forceinline__ double exp_nonpos(double x, uint32_t tab) {
+  const double t = fma(x, c_expk[0], c_expk[1]);
+  const int n = __double2loint(t);
+  const double kf = t - c_expk[1];
+  double r = fma(kf, c_expk[2], x);
+  r = fma(kf, c_expk[3], r);
+  double p = c_expk[4];
+  p = fma(p, r, c_expk[5]);
+  p = fma(p, r, c_expk[6]);
+  p = fma(p, r, c_expk[7]);
+  p = fma(p, r, c_expk[8]);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const int k = n >> 5;
+  double tj;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab + ((uint32_t)(n & 31) << 3)));
+  const double v = p * tj;                           // in [1, 2.05)
+  const double res = __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
+  // x <= -707.75 (incl. -inf): the result would be subnormal (< 2^-1021).  Every sum these terms enter is
+  // >= 1 (it contains exp(0) for the maximum), so they are below half an ulp of it: flushed to zero.
+  return ((unsigned int)__double2hiint(x) >= 0xC0861E00u) ? 0.0 : res;
+}
+
 // ---------------------------------------------------------------------------------------------
-// single-CTA radix select: key of the K-th largest (K >= 1) among keys[0..cnt)
+// single-CTA radix select over keys in GLOBAL/SHARED memory: key of the K-th largest (K >= 1)
 // ---------------------------------------------------------------------------------------------
-__device__ unsigned long long cta_select_kth_largest(const unsigned long long* __restrict__ keys, unsigned int cnt,
-                                                     unsigned long long K, unsigned int* hist /*[kBins]*/,
-                                                     unsigned long long* sh /*[2]*/) {
+// all threads of a 1024-thread CTA: find the bin (scanning from the TOP bin down) that holds rank K;
+// sh[0] = bin, sh[1] = rank inside that bin.  nb <= 2048.  Ends with a __syncthreads().
+__device__ void cta_find_bin(const unsigned int* hist, unsigned int nb, unsigned long long K, unsigned long long* sh,
+                             unsigned int* wtot /*[32]*/) {
+  const unsigned int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int b0 = (int)nb - 1 - 2 * (int)t, b1 = b0 - 1;          // this thread's two bins, higher first
+  const unsigned int c0 = b0 >= 0 ? hist[b0] : 0u, c1 = b1 >= 0 ? hist[b1] : 0u;
+  unsigned int incl = c0 + c1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (unsigned)o) incl += v;
+  }
+  if (lane == 31) wtot[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    const unsigned int v = wtot[lane];
+    unsigned int in = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int u = __shfl_up_sync(0xffffffffu, in, o);
+      if (lane >= (unsigned)o) in += u;
+    }
+    wtot[lane] = in - v;                                          // exclusive warp offsets
+  }
+  __syncthreads();
+  const unsigned long long ex = (unsigned long long)wtot[w] + incl - (c0 + c1);   // entries in higher bins
+  if (ex < K && K <= ex + c0) {
+    sh[0] = (unsigned long long)b0;
+    sh[1] = K - ex;
+  } else if (ex + c0 < K && K <= ex + c0 + c1) {
+    sh[0] = (unsigned long long)b1;
+    sh[1] = K - ex - c0;
+  }
+  __syncthreads();
+}
+
+__device__ unsigned long long cta_select_kth_largest(const unsigned long long* keys, unsigned int cnt, unsigned long long K,
+                                                     unsigned int* hist /*[kBins]*/, unsigned long long* sh /*[2]*/,
+                                                     unsigned int* wtot /*[32]*/) {
   unsigned long long prefix = 0, mask = 0;
   int shift = 64;
   while (shift > 0) {
@@ -75,40 +160,14 @@ __device__ unsigned long long cta_select_kth_largest(const unsigned long long* _
     __syncthreads();
     for (unsigned int i0 = 0; i0 < cnt; i0 += blockDim.x) {
       const unsigned int i = i0 + threadIdx.x;
-      const bool ok = i < cnt && ((keys[i] & mask) == prefix);
-      const unsigned int dig = ok ? (unsigned int)((keys[i] >> shift) & (nb - 1)) : 0xffffffffu;
-      // warp-aggregated histogram update (top digits are heavily concentrated)
+      const unsigned long long key = i < cnt ? keys[i] : 0ull;
+      const bool ok = i < cnt && ((key & mask) == prefix);
+      const unsigned int dig = ok ? (unsigned int)((key >> shift) & (nb - 1)) : 0xffffffffu;
       const unsigned int peers = __match_any_sync(0xffffffffu, dig);
       if (ok && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[dig], __popc(peers));
     }
     __syncthreads();
-    if (threadIdx.x < 32) {          // warp 0 scans from the top bin down
-      unsigned long long cum = 0;
-      unsigned long long found = ~0ull, newK = 0;
-      for (int base = (int)nb - 32; base >= 0 && found == ~0ull; base -= 32) {
-        const int b = base + 31 - (int)threadIdx.x;        // lane 0 = highest bin of this group
-        unsigned long long c = hist[b];
-        unsigned long long incl = c;                        // inclusive scan over lanes (descending bins)
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-          if ((int)threadIdx.x >= o) incl += t;
-        }
-        const bool hit = (cum + incl >= K) && (cum + incl - c < K);
-        const unsigned int ball = __ballot_sync(0xffffffffu, hit);
-        if (ball) {
-          const int src = __ffs(ball) - 1;
-          found = (unsigned long long)__shfl_sync(0xffffffffu, b, src);
-          newK = K - (__shfl_sync(0xffffffffu, cum + incl - c, src));
-        }
-        cum += __shfl_sync(0xffffffffu, incl, 31);
-      }
-      if (threadIdx.x == 0) {
-        sh[0] = found;
-        sh[1] = newK;
-      }
-    }
-    __syncthreads();
+    cta_find_bin(hist, nb, K, sh, wtot);
     prefix |= sh[0] << shift;
     mask |= (unsigned long long)(nb - 1) << shift;
     K = sh[1];
@@ -118,129 +177,286 @@ __device__ unsigned long long cta_select_kth_largest(const unsigned long long* _
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void psis_init_kernel(PsisScalars* sc, int M) {
-  sc->maxkey = 0; sc->t0key = 0; sc->cutkey = 0; sc->ncand = 0; sc->ntail = 0; sc->status = 0; sc->strict = 0;
-  sc->t0 = -INFINITY; sc->maxv = 0; sc->cutoff = 0; sc->expcut = 0; sc->body_below = 0; sc->body_cand = 0;
-  sc->tail_sum = 0; sc->k = INFINITY; sc->sigma = 0; sc->lse = 0; sc->sumv = 0; sc->sumexp2v = 0;
-  sc->smoothed = 0; sc->M = M; sc->prefix = 0; sc->kth = 0;
+__global__ void psis_init_kernel(PsisScalars* sc, int M, unsigned int* hist, unsigned int* vhist) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    sc->maxkey = 0; sc->t0key = 0; sc->cutkey = 0; sc->ncand = 0; sc->ntail = 0; sc->status = 0; sc->strict = 0;
+    sc->t0 = -INFINITY; sc->maxv = 0; sc->cutoff = 0; sc->expcut = 0; sc->body_below = 0; sc->body_cand = 0;
+    sc->tail_sum = 0; sc->k = INFINITY; sc->sigma = 0; sc->lse = 0; sc->bhat = 0; sc->sumv = 0; sc->sumexp2v = 0;
+    sc->vscale = 0; sc->smoothed = 0; sc->M = M; sc->shift = 0; sc->bstar = 0; sc->need = 0; sc->members = 0; sc->gcount = 0; sc->prefix = 0; sc->kth = 0;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kBins; i += gridDim.x * blockDim.x) hist[i] = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * kVBins; i += gridDim.x * blockDim.x) vhist[i] = 0;
 }
 
-__global__ void psis_sample_kernel(const double* __restrict__ lw, int64_t n, int64_t stride, int m,
-                                   unsigned long long* __restrict__ skeys) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m) skeys[i] = dkey(lw[(int64_t)i * stride]);
+// register-resident radix select: K-th largest of NK keys per thread (invalid keys are 0 = below everything)
+template <int NK>
+__device__ unsigned long long reg_select_kth_largest(const unsigned long long (&kreg)[NK], unsigned long long K,
+                                                     unsigned int* hist, unsigned long long* sh, unsigned int* wtot) {
+  unsigned long long prefix = 0, mask = 0;
+  int shift = 64;
+  while (shift > 0) {
+    const int bits = shift >= kDigitBits ? kDigitBits : shift;
+    shift -= bits;
+    const unsigned int nb = 1u << bits;
+    for (unsigned int b = threadIdx.x; b < nb; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < NK; ++u) {
+      const bool ok = kreg[u] != 0ull && ((kreg[u] & mask) == prefix);
+      const unsigned int dig = ok ? (unsigned int)((kreg[u] >> shift) & (nb - 1)) : 0xffffffffu;
+      const unsigned int peers = __match_any_sync(0xffffffffu, dig);
+      if (ok && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[dig], __popc(peers));
+    }
+    __syncthreads();
+    cta_find_bin(hist, nb, K, sh, wtot);
+    prefix |= sh[0] << shift;
+    mask |= (unsigned long long)(nb - 1) << shift;
+    K = sh[1];
+    __syncthreads();
+  }
+  return prefix;
 }
 
-// threshold = R-th largest of the sample (R >= m means "everything is a candidate")
-__global__ void __launch_bounds__(kSelThreads) psis_sample_select_kernel(const unsigned long long* __restrict__ skeys,
+// candidate threshold t0 from a strided sample of m <= 16384 keys (16 per thread, in registers).
+// R <= 256: the R-th largest of the 1024 per-thread maxima, which is <= the R-th largest of the whole
+// sample (a subset's order statistic), i.e. errs on the side of a few more candidates and needs one key
+// per thread; larger R (only for n of a few 1e5 or less): the exact R-th largest of the sample.
+__global__ void __launch_bounds__(kSelThreads) psis_sample_select_kernel(const double* __restrict__ lw, int64_t stride,
                                                                           int m, unsigned int R, PsisScalars* sc) {
   __shared__ unsigned int hist[kBins];
   __shared__ unsigned long long sh[2];
+  __shared__ unsigned int wtot[32];
   if (R >= (unsigned)m) {
     if (threadIdx.x == 0) { sc->t0key = 0; sc->t0 = -INFINITY; }
     return;
   }
-  const unsigned long long key = cta_select_kth_largest(skeys, (unsigned)m, R, hist, sh);
+  unsigned long long kreg[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int i = u * kSelThreads + threadIdx.x;
+    kreg[u] = i < m ? dkey(lw[(int64_t)i * stride]) : 0ull;          // key 0 = below everything
+  }
+  unsigned long long key;
+  if (R <= 256) {
+    unsigned long long kmax[1] = {0ull};
+#pragma unroll
+    for (int u = 0; u < 16; ++u) kmax[0] = kreg[u] > kmax[0] ? kreg[u] : kmax[0];
+    key = reg_select_kth_largest<1>(kmax, R, hist, sh, wtot);
+  } else {
+    key = reg_select_kth_largest<16>(kreg, R, hist, sh, wtot);
+  }
   if (threadIdx.x == 0) { sc->t0key = key; sc->t0 = dkey_inv(key); }
 }
 
-// pass A: max, candidate compaction, sum exp(x - t0) below the threshold
+// pass A: candidate compaction (everything >= the threshold; the global max is among them) and
+// sum exp(x - t0) over everything below the threshold.  Candidates are staged per warp in shared
+// memory and flushed with ONE global atomic per CTA (same-address atomics with a return value
+// serialise at ~2 ns each in L2: one per candidate-bearing warp iteration cost more than the HBM pass).
+constexpr int kStage = 160;     // per-warp staging entries (>= 4 * 32)
 __global__ void __launch_bounds__(256) psis_pass_a_kernel(const double* __restrict__ lw, int64_t n, PsisScalars* sc,
                                                           double* __restrict__ cand_x, int64_t* __restrict__ cand_i,
-                                                          unsigned long long* __restrict__ cand_k, unsigned int cap,
-                                                          double* __restrict__ blk_sum) {
+                                                          unsigned int cap, double* __restrict__ blk_sum) {
   __shared__ double red[32];
   __shared__ unsigned long long redk[32];
+  __shared__ double etab_s[32];
+  __shared__ double sx[8][kStage];
+  __shared__ long long si[8][kStage];
+  __shared__ unsigned int wcnt[8], cta_base;
+  const uint32_t etab = load_exp_table(etab_s);
   const double t0 = sc->t0;
-  const bool strict = sc->strict != 0;
   const bool all = !(t0 > -INFINITY);       // threshold -inf: everything is a candidate
-  double mx = -INFINITY, acc = 0.0;
-  const int lane = threadIdx.x & 31;
+  // single comparison x >= thr: in exact mode candidates are STRICTLY above t0
+  const double thr = all ? -INFINITY : (sc->strict ? nextafter(t0, INFINITY) : t0);
+  double mx = -INFINITY, acc0 = 0.0, acc1 = 0.0;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t n4 = n / 4;
-  auto handle = [&](double x, int64_t i, bool valid) {
-    const bool is_cand = valid && (all || (strict ? (x > t0) : (x >= t0)));
-    if (valid) mx = fmax(mx, x);
-    if (valid && !is_cand) acc += exp(x - t0);
+  unsigned int staged = 0;                  // warp-uniform number of staged candidates
+  auto flush_warp = [&]() {
+    unsigned int base = 0;
+    if (lane == 0) base = atomicAdd(&sc->ncand, staged);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (unsigned int i = lane; i < staged; i += 32)
+      if (base + i < cap) {
+        cand_x[base + i] = sx[w][i];
+        cand_i[base + i] = si[w][i];
+      }
+    __syncwarp();
+    staged = 0;
+  };
+  auto push = [&](double x, int64_t i, bool is_cand) {
     const unsigned int ball = __ballot_sync(0xffffffffu, is_cand);
     if (ball) {
-      unsigned int base = 0;
-      const int leader = __ffs(ball) - 1;
-      if (lane == leader) base = atomicAdd(&sc->ncand, __popc(ball));
-      base = __shfl_sync(0xffffffffu, base, leader);
       if (is_cand) {
-        const unsigned int slot = base + __popc(ball & ((1u << lane) - 1));
-        if (slot < cap) {
-          cand_x[slot] = x;
-          cand_i[slot] = i;
-          cand_k[slot] = dkey(x);
-        }
+        mx = fmax(mx, x);
+        const unsigned int slot = staged + __popc(ball & ((1u << lane) - 1));
+        sx[w][slot] = x;
+        si[w][slot] = i;
       }
+      staged += __popc(ball);
     }
   };
   const bool aligned = (reinterpret_cast<uintptr_t>(lw) & 31) == 0;
-  if (aligned) {
+  int64_t done = 0;
+  if (aligned && !all) {
     // 2 x LDG.128 per thread per iteration (4 doubles), warp-uniform trip count
+    const int64_t n4 = n / 4;
     const int64_t iters = (n4 + nthreads - 1) / nthreads;
+    const double2 ninf = make_double2(-INFINITY, -INFINITY);
+    double2 na = ninf, nb = ninf;                     // software pipeline: next iteration's loads in flight
+    if (tid < n4) {
+      na = __ldcs(reinterpret_cast<const double2*>(lw) + 2 * tid);
+      nb = __ldcs(reinterpret_cast<const double2*>(lw) + 2 * tid + 1);
+    }
     for (int64_t it = 0; it < iters; ++it) {
       const int64_t q = it * nthreads + tid;
-      const bool v = q < n4;
-      double2 a = make_double2(0, 0), b = make_double2(0, 0);
-      if (v) {
-        a = __ldcs(reinterpret_cast<const double2*>(lw) + 2 * q);
-        b = __ldcs(reinterpret_cast<const double2*>(lw) + 2 * q + 1);
+      const double2 a = na, b = nb;
+      const int64_t qn = q + nthreads;
+      na = ninf;
+      nb = ninf;
+      if (qn < n4) {
+        na = __ldcs(reinterpret_cast<const double2*>(lw) + 2 * qn);
+        nb = __ldcs(reinterpret_cast<const double2*>(lw) + 2 * qn + 1);
       }
-      handle(a.x, 4 * q, v);
-      handle(a.y, 4 * q + 1, v);
-      handle(b.x, 4 * q + 2, v);
-      handle(b.y, 4 * q + 3, v);
+      const bool c0 = a.x >= thr, c1 = a.y >= thr, c2 = b.x >= thr, c3 = b.y >= thr;
+      // exponentials of the (overwhelmingly common) non-candidates: two independent chains
+      const double e0 = exp_nonpos(a.x - t0, etab), e1 = exp_nonpos(a.y - t0, etab);
+      const double e2 = exp_nonpos(b.x - t0, etab), e3 = exp_nonpos(b.y - t0, etab);
+      acc0 += (c0 ? 0.0 : e0) + (c2 ? 0.0 : e2);
+      acc1 += (c1 ? 0.0 : e1) + (c3 ? 0.0 : e3);
+      if (__any_sync(0xffffffffu, c0 | c1 | c2 | c3)) {
+        if (staged + 128 > kStage) flush_warp();
+        push(a.x, 4 * q, c0);
+        push(a.y, 4 * q + 1, c1);
+        push(b.x, 4 * q + 2, c2);
+        push(b.y, 4 * q + 3, c3);
+      }
     }
-    const int64_t rem0 = n4 * 4;
-    if (blockIdx.x == 0 && threadIdx.x < 32) {
-      const int64_t i = rem0 + lane;
-      handle(i < n ? lw[i] : 0.0, i, i < n);
-    }
-  } else {
-    const int64_t iters = (n + nthreads - 1) / nthreads;
+    done = n4 * 4;
+  }
+  {   // remainder (and the whole array when unaligned or when everything is a candidate)
+    const int64_t rest = n - done;
+    const int64_t iters = (rest + nthreads - 1) / nthreads;
     for (int64_t it = 0; it < iters; ++it) {
-      const int64_t i = it * nthreads + tid;
-      handle(i < n ? lw[i] : 0.0, i, i < n);
+      const int64_t i = done + it * nthreads + tid;
+      const bool v = i < n;
+      const double x = v ? lw[i] : -INFINITY;
+      const bool c = v && (all || x >= thr);
+      if (v && !c) acc0 += exp_nonpos(x - t0, etab);
+      if (staged + 32 > kStage) flush_warp();
+      push(x, i, c);
     }
   }
-  // block reductions
-  const int w = threadIdx.x >> 5;
-  acc = warp_sum(acc);
+  // block reductions and the single per-CTA flush of the staged candidates
+  double acc = warp_sum(acc0 + acc1);
   unsigned long long mk = dkey(mx);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     unsigned long long t = __shfl_xor_sync(0xffffffffu, mk, o);
     mk = t > mk ? t : mk;
   }
-  if (lane == 0) { red[w] = acc; redk[w] = mk; }
+  if (lane == 0) { red[w] = acc; redk[w] = mk; wcnt[w] = staged; }
   __syncthreads();
   if (w == 0) {
-    double a = lane < (blockDim.x >> 5) ? red[lane] : 0.0;
-    unsigned long long k = lane < (blockDim.x >> 5) ? redk[lane] : 0ull;
+    double a = lane < 8 ? red[lane] : 0.0;
+    unsigned long long k = lane < 8 ? redk[lane] : 0ull;
+    unsigned int c = lane < 8 ? wcnt[lane] : 0u;
     a = warp_sum(a);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       unsigned long long t = __shfl_xor_sync(0xffffffffu, k, o);
       k = t > k ? t : k;
+      c += __shfl_xor_sync(0xffffffffu, c, o);
     }
     if (lane == 0) {
       blk_sum[blockIdx.x] = a;
-      atomicMax(&sc->maxkey, k);
+      if (k > dkey(-INFINITY)) atomicMax(&sc->maxkey, k);
+      cta_base = c ? atomicAdd(&sc->ncand, c) : 0u;
+    }
+  }
+  __syncthreads();
+  unsigned int base = cta_base;
+  for (int u = 0; u < w; ++u) base += wcnt[u];
+  for (unsigned int i = lane; i < staged; i += 32)
+    if (base + i < cap) {
+      cand_x[base + i] = sx[w][i];
+      cand_i[base + i] = si[w][i];
+    }
+}
+
+// ---- cutoff among the candidates: one histogram pass on LINEAR value bins over [t0, max] (monotone in x,
+// so every entry of a higher bin is larger than every entry of a lower one), then an exact key select
+// of the boundary bin in shared memory
+__device__ __forceinline__ unsigned int cbin(double x, double lo, double scale) {
+  const double f = (x - lo) * scale;
+  const int b = (int)f;
+  return b < 0 ? 0u : (b >= kBins ? (unsigned)(kBins - 1) : (unsigned)b);
+}
+__device__ __forceinline__ double cand_scale(const PsisScalars* sc, double& lo) {
+  const double hi = dkey_inv(sc->maxkey);
+  lo = sc->t0;
+  return (lo > -INFINITY && hi > lo) ? (double)kBins / (hi - lo) : 0.0;      // 0: everything in bin 0
+}
+
+__global__ void __launch_bounds__(256) psis_cand_hist_kernel(PsisScalars* sc, const double* __restrict__ cand_x,
+                                                             unsigned int cap, unsigned int* __restrict__ ghist) {
+  __shared__ unsigned int hist[kBins];
+  const unsigned int C = sc->ncand;
+  if (sc->strict || C > cap || C < (unsigned)(sc->M + 1)) return;
+  double lo;
+  const double scale = cand_scale(sc, lo);
+  for (unsigned int b = threadIdx.x; b < kBins; b += blockDim.x) hist[b] = 0;
+  __syncthreads();
+  for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < C; i0 += gridDim.x * blockDim.x) {
+    const unsigned int i = i0 + threadIdx.x;
+    const bool ok = i < C;
+    const unsigned int dig = ok ? (scale > 0.0 ? cbin(cand_x[i], lo, scale) : 0u) : 0xffffffffu;
+    const unsigned int peers = __match_any_sync(0xffffffffu, dig);
+    if (ok && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[dig], __popc(peers));
+  }
+  __syncthreads();
+  for (unsigned int b = threadIdx.x; b < kBins; b += blockDim.x)
+    if (hist[b]) atomicAdd(&ghist[b], hist[b]);
+}
+
+// every CTA locates the boundary bin from the global histogram, then gathers the keys of its slice of
+// that bin into a small global buffer
+__global__ void __launch_bounds__(kSelThreads) psis_cand_gather_kernel(PsisScalars* sc, const double* __restrict__ cand_x,
+                                                                        unsigned int cap, const unsigned int* __restrict__ ghist,
+                                                                        unsigned long long* __restrict__ gbuf) {
+  __shared__ unsigned int hist[kBins];
+  __shared__ unsigned long long sh[2];
+  __shared__ unsigned int wtot[32];
+  const unsigned int C = sc->ncand;
+  if (sc->strict || C > cap || C < (unsigned)(sc->M + 1)) return;
+  for (unsigned int b = threadIdx.x; b < kBins; b += blockDim.x) hist[b] = ghist[b];
+  __syncthreads();
+  cta_find_bin(hist, kBins, (unsigned long long)(sc->M + 1), sh, wtot);
+  const unsigned int bstar = (unsigned int)sh[0];
+  const unsigned int members = hist[bstar];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    sc->bstar = bstar;
+    sc->need = (unsigned int)sh[1];
+    sc->members = members;
+  }
+  if (members > kGather) return;             // the cutoff kernel falls back to radix passes
+  double lo;
+  const double scale = cand_scale(sc, lo);
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < C; i += gridDim.x * blockDim.x) {
+    const double x = cand_x[i];
+    if ((scale > 0.0 ? cbin(x, lo, scale) : 0u) == bstar) {
+      const unsigned int slot = atomicAdd(&sc->gcount, 1u);
+      if (slot < kGather) gbuf[slot] = dkey(x);
     }
   }
 }
 
-// select the cutoff among the candidates, derive max / cutoff / exp(cutoff), fold the block sums
-__global__ void __launch_bounds__(kSelThreads) psis_cutoff_kernel(PsisScalars* sc, const unsigned long long* __restrict__ cand_k,
-                                                                   unsigned int cap, const double* __restrict__ blk_sum,
-                                                                   int nblk) {
+__global__ void __launch_bounds__(kSelThreads) psis_cutoff_kernel(PsisScalars* sc, const double* __restrict__ cand_x,
+                                                                   unsigned int cap, const unsigned long long* __restrict__ gbuf,
+                                                                   const double* __restrict__ blk_sum, int nblk) {
   __shared__ unsigned int hist[kBins];
   __shared__ unsigned long long sh[2];
+  __shared__ unsigned int wtot[32];
   __shared__ double red[32];
   const unsigned int C = sc->ncand;
   const int M = sc->M;
@@ -257,7 +473,41 @@ __global__ void __launch_bounds__(kSelThreads) psis_cutoff_kernel(PsisScalars* s
       if (threadIdx.x == 0) sc->status = 1;
       return;
     }
-    cutkey = cta_select_kth_largest(cand_k, C, (unsigned long long)(M + 1), hist, sh);
+    const unsigned int bstar = sc->bstar, members = sc->members;
+    const unsigned long long need = sc->need;
+    if (members <= kGather) {
+      // exact 64-bit radix select over the gathered boundary bin (<= 8192 keys, L2 resident)
+      cutkey = cta_select_kth_largest(gbuf, members, need, hist, sh, wtot);
+    } else {
+      // huge boundary bin (massive ties): radix passes over the candidates in global memory
+      double lo;
+      const double scale = cand_scale(sc, lo);
+      unsigned long long pfx = 0, msk = 0, K = need;
+      int sft = 64;
+      while (sft > 0) {
+        const int bits = sft >= kDigitBits ? kDigitBits : sft;
+        sft -= bits;
+        const unsigned int nb = 1u << bits;
+        for (unsigned int b = threadIdx.x; b < nb; b += blockDim.x) hist[b] = 0;
+        __syncthreads();
+        for (unsigned int i0 = 0; i0 < C; i0 += blockDim.x) {
+          const unsigned int i = i0 + threadIdx.x;
+          const double x = i < C ? cand_x[i] : 0.0;
+          const unsigned long long key = dkey(x);
+          const bool ok = i < C && (scale > 0.0 ? cbin(x, lo, scale) : 0u) == bstar && ((key & msk) == pfx);
+          const unsigned int dig = ok ? (unsigned int)((key >> sft) & (nb - 1)) : 0xffffffffu;
+          const unsigned int peers = __match_any_sync(0xffffffffu, dig);
+          if (ok && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[dig], __popc(peers));
+        }
+        __syncthreads();
+        cta_find_bin(hist, nb, K, sh, wtot);
+        pfx |= sh[0] << sft;
+        msk |= (unsigned long long)(nb - 1) << sft;
+        K = sh[1];
+        __syncthreads();
+      }
+      cutkey = pfx;
+    }
   }
   if (threadIdx.x == 0) {
     const double cutraw = dkey_inv(cutkey);
@@ -267,26 +517,28 @@ __global__ void __launch_bounds__(kSelThreads) psis_cutoff_kernel(PsisScalars* s
     sc->cutoff = cutoff;
     sc->expcut = exp(cutoff);
     sc->body_below = s;
+    sc->vscale = (cutoff < 0.0) ? (double)kVBins / (-cutoff) : 0.0;
   }
 }
 
-// split candidates into tail (shifted value > cutoff) and body; accumulate the body part of the LSE
-__global__ void psis_tail_compact_kernel(PsisScalars* sc, const double* __restrict__ cand_x,
-                                         const int64_t* __restrict__ cand_i, double* __restrict__ tail_x,
-                                         int64_t* __restrict__ tail_i, unsigned int tail_cap) {
+__device__ __forceinline__ int vbin(double v, double cutoff, double vscale) {
+  const double f = (v - cutoff) * vscale;
+  int b = (int)f;
+  return b < 0 ? 0 : (b >= kVBins ? kVBins - 1 : b);
+}
+
+// tail membership (shifted value > cutoff), per-bin tail counts, LSE contribution of the other candidates
+__global__ void __launch_bounds__(256) psis_tail_count_kernel(PsisScalars* sc, const double* __restrict__ cand_x,
+                                                              unsigned int* __restrict__ vhist) {
   __shared__ double red[32];
   if (sc->status) return;
   const unsigned int C = sc->ncand;
-  const double maxv = sc->maxv, cutoff = sc->cutoff;
+  const double maxv = sc->maxv, cutoff = sc->cutoff, vscale = sc->vscale;
   double acc = 0.0;
   for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < C; i += gridDim.x * blockDim.x) {
     const double v = cand_x[i] - maxv;
     if (v > cutoff) {
-      const unsigned int slot = atomicAdd(&sc->ntail, 1u);
-      if (slot < tail_cap) {
-        tail_x[slot] = v;
-        tail_i[slot] = cand_i[i];
-      }
+      atomicAdd(&vhist[vbin(v, cutoff, vscale)], 1u);
     } else {
       acc += exp(v);
     }
@@ -295,69 +547,201 @@ __global__ void psis_tail_compact_kernel(PsisScalars* sc, const double* __restri
   if (threadIdx.x == 0 && acc != 0.0) atomicAdd(&sc->body_cand, acc);
 }
 
-// rank tail entries by (value, index) and by index; build the ascending array for the GPD fit
-__global__ void __launch_bounds__(256) psis_tail_rank_kernel(PsisScalars* sc, const double* __restrict__ tail_x,
-                                                             const int64_t* __restrict__ tail_i,
-                                                             double* __restrict__ sorted_x, int* __restrict__ rank_of,
-                                                             int64_t* __restrict__ idx_sorted, int* __restrict__ order_rank) {
-  __shared__ double sx[256];
-  __shared__ int64_t si[256];
+// exclusive scan of the tail bins (ascending value) -> bin offsets; n2
+__global__ void __launch_bounds__(kSelThreads) psis_tail_scan_kernel(PsisScalars* sc, const unsigned int* __restrict__ vhist,
+                                                                      unsigned int* __restrict__ voff) {
+  __shared__ unsigned int wsum[32];
   if (sc->status) return;
-  const unsigned int n2 = sc->ntail;
-  const double expcut = sc->expcut;
-  for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < n2; i0 += gridDim.x * blockDim.x) {
-    const unsigned int i = i0 + threadIdx.x;
-    const bool valid = i < n2;
-    const double xi = valid ? tail_x[i] : 0.0;
-    const int64_t ii = valid ? tail_i[i] : 0;
-    int r = 0, p = 0;
-    for (unsigned int j0 = 0; j0 < n2; j0 += 256) {
-      __syncthreads();
-      const unsigned int j = j0 + threadIdx.x;
-      sx[threadIdx.x] = j < n2 ? tail_x[j] : INFINITY;
-      si[threadIdx.x] = j < n2 ? tail_i[j] : INT64_MAX;
-      __syncthreads();
-      const int lim = (n2 - j0) < 256 ? (int)(n2 - j0) : 256;
-      for (int q = 0; q < lim; ++q) {
-        const double xj = sx[q];
-        const int64_t ij = si[q];
-        r += (xj < xi) || (xj == xi && ij < ii);
-        p += ij < ii;
-      }
+  constexpr int per = kVBins / kSelThreads;       // 8 bins per thread
+  unsigned int loc[per], tot = 0;
+#pragma unroll
+  for (int u = 0; u < per; ++u) {
+    loc[u] = vhist[threadIdx.x * per + u];
+    tot += loc[u];
+  }
+  unsigned int incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += t;
+  }
+  if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned int v = wsum[threadIdx.x], in = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, in, o);
+      if (threadIdx.x >= o) in += t;
     }
-    if (valid) {
-      rank_of[i] = r;
-      sorted_x[r] = exp(xi) - expcut;                  // _psis.py:185-186
-      idx_sorted[p] = ii;                              // tail indices in ascending index order
-      order_rank[p] = r;                               // rank (0 = smallest tail value) of that index
+    wsum[threadIdx.x] = in - v;
+    if (threadIdx.x == 31) sc->ntail = in;
+  }
+  __syncthreads();
+  unsigned int base = wsum[threadIdx.x >> 5] + incl - tot;
+#pragma unroll
+  for (int u = 0; u < per; ++u) {
+    voff[threadIdx.x * per + u] = base;
+    base += loc[u];
+  }
+}
+
+// bin-ordered placement of the tail entries (order inside a bin is arbitrary here)
+__global__ void __launch_bounds__(256) psis_tail_place_kernel(PsisScalars* sc, const double* __restrict__ cand_x,
+                                                              const int64_t* __restrict__ cand_i,
+                                                              const unsigned int* __restrict__ voff,
+                                                              unsigned int* __restrict__ vcur, double* __restrict__ tmp_v,
+                                                              int64_t* __restrict__ tmp_i, int* __restrict__ tmp_b,
+                                                              unsigned int tail_cap) {
+  if (sc->status) return;
+  const unsigned int C = sc->ncand;
+  const double maxv = sc->maxv, cutoff = sc->cutoff, vscale = sc->vscale;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < C; i += gridDim.x * blockDim.x) {
+    const double v = cand_x[i] - maxv;
+    if (v > cutoff) {
+      const int b = vbin(v, cutoff, vscale);
+      const unsigned int pos = voff[b] + atomicAdd(&vcur[b], 1u);
+      if (pos < tail_cap) {
+        tmp_v[pos] = v;
+        tmp_i[pos] = cand_i[i];
+        tmp_b[pos] = b;
+      }
     }
   }
 }
 
-// k_j = mean_i log1p(-b_j x_i) on the quadrature grid (_psis.py:264-286); one CTA per grid point
+// exact rank by counting inside the (small) bin; output arrays are in ascending (value, index) order
+__global__ void __launch_bounds__(256) psis_tail_rank_kernel(PsisScalars* sc, const double* __restrict__ tmp_v,
+                                                             const int64_t* __restrict__ tmp_i, const int* __restrict__ tmp_b,
+                                                             const unsigned int* __restrict__ voff,
+                                                             const unsigned int* __restrict__ vhist,
+                                                             double* __restrict__ tail_v, int64_t* __restrict__ tail_i,
+                                                             double* __restrict__ sorted_x) {
+  if (sc->status) return;
+  const unsigned int n2 = sc->ntail;
+  const double expcut = sc->expcut;
+  for (unsigned int p = blockIdx.x * blockDim.x + threadIdx.x; p < n2; p += gridDim.x * blockDim.x) {
+    const double v = tmp_v[p];
+    const int64_t ii = tmp_i[p];
+    const int b = tmp_b[p];
+    const unsigned int lo = voff[b], cnt = vhist[b];
+    unsigned int r = lo;
+    for (unsigned int q = lo; q < lo + cnt; ++q) {
+      const double vq = tmp_v[q];
+      r += (vq < v) || (vq == v && tmp_i[q] < ii);
+    }
+    tail_v[r] = v;
+    tail_i[r] = ii;
+    sorted_x[r] = exp(v) - expcut;                  // _psis.py:185-186
+  }
+}
+
+// optional: tail indices in ascending index order with their value ranks (O(n2^2), API nicety / tests)
+__global__ void __launch_bounds__(256) psis_tail_index_order_kernel(PsisScalars* sc, const int64_t* __restrict__ tail_i,
+                                                                    int64_t* __restrict__ idx_sorted, int* __restrict__ order_rank) {
+  __shared__ int64_t si[256];
+  if (sc->status) return;
+  const unsigned int n2 = sc->ntail;
+  for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < n2; i0 += gridDim.x * blockDim.x) {
+    const unsigned int i = i0 + threadIdx.x;
+    const bool valid = i < n2;
+    const int64_t ii = valid ? tail_i[i] : 0;
+    int p = 0;
+    for (unsigned int j0 = 0; j0 < n2; j0 += 256) {
+      __syncthreads();
+      const unsigned int j = j0 + threadIdx.x;
+      si[threadIdx.x] = j < n2 ? tail_i[j] : INT64_MAX;
+      __syncthreads();
+      const int lim = (n2 - j0) < 256 ? (int)(n2 - j0) : 256;
+      for (int q = 0; q < lim; ++q) p += si[q] < ii;
+    }
+    if (valid) {
+      idx_sorted[p] = ii;
+      order_rank[p] = (int)i;
+    }
+  }
+}
+
+// ---- generalised Pareto fit (_psis.py:212-332), split so that no stage is a long serial loop --------
+// partial sums of log1p(-b_j x_i): grid = (m, kGpdSplit)
 __global__ void __launch_bounds__(256) psis_gpd_grid_kernel(PsisScalars* sc, const double* __restrict__ sorted_x,
-                                                            double* __restrict__ bs, double* __restrict__ ks) {
+                                                            double* __restrict__ bs, double* __restrict__ part) {
   __shared__ double red[32];
   if (sc->status) return;
   const int N = (int)sc->ntail;
   if (N <= 4) return;
   const int m = 30 + (int)sqrt((double)N);
+  const int j = blockIdx.x;
+  if (j >= m) return;
   const double xq = sorted_x[(int)(N / 4.0 + 0.5) - 1];
   const double xmax = sorted_x[N - 1];
-  for (int j = blockIdx.x; j < m; j += gridDim.x) {
-    double b = 1.0 - sqrt((double)m / ((double)(j + 1) - 0.5));
-    b /= 3.0 * xq;
-    b += 1.0 / xmax;
-    const double nb = -b;
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) acc += log1p(nb * sorted_x[i]);
-    acc = block_sum(acc, red);
-    if (threadIdx.x == 0) {
-      bs[j] = b;
-      ks[j] = acc / (double)N;
-    }
-    __syncthreads();
+  double b = 1.0 - sqrt((double)m / ((double)(j + 1) - 0.5));
+  b /= 3.0 * xq;
+  b += 1.0 / xmax;
+  const double nb = -b;
+  double acc = 0.0;
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < N; i += gridDim.y * blockDim.x) acc += log1p(nb * sorted_x[i]);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    part[j * kGpdSplit + blockIdx.y] = acc;
+    if (blockIdx.y == 0) bs[j] = b;
   }
+}
+
+// profile likelihood weights -> posterior mean of b (:288-312)
+__global__ void __launch_bounds__(kSelThreads) psis_gpd_weights_kernel(PsisScalars* sc, const double* __restrict__ bs,
+                                                                        const double* __restrict__ part, double* __restrict__ Ls) {
+  __shared__ double red[32];
+  if (sc->status) return;
+  const int N = (int)sc->ntail;
+  if (N <= 4) return;
+  const int m = 30 + (int)sqrt((double)N);
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    double ksum = 0.0;
+#pragma unroll
+    for (int u = 0; u < kGpdSplit; ++u) ksum += part[j * kGpdSplit + u];
+    const double kj = ksum / (double)N;
+    double L = bs[j] / kj;
+    L = log(-L);
+    L -= kj;
+    L -= 1.0;
+    Ls[j] = L * (double)N;
+  }
+  __syncthreads();
+  // w_j = 1 / sum_i exp(L_i - L_j)  (:295-298)  ==  exp(L_j - Lmax) / sum_i exp(L_i - Lmax): O(m) instead of
+  // O(m^2), identical up to rounding, and the reference's "benign overflow -> weight 0" becomes an underflow
+  double lmax = -INFINITY;
+  for (int j = threadIdx.x; j < m; j += blockDim.x) lmax = fmax(lmax, Ls[j]);
+  lmax = block_max(lmax, red);
+  double den = 0.0;
+  for (int j = threadIdx.x; j < m; j += blockDim.x) den += exp(Ls[j] - lmax);
+  den = block_sum(den, red);
+  double wsum = 0.0, bsum = 0.0;
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    const double w = exp(Ls[j] - lmax) / den;
+    if (w >= 10.0 * DBL_EPSILON) {
+      wsum += w;
+      bsum += bs[j] * w;
+    }
+  }
+  wsum = block_sum(wsum, red);
+  bsum = block_sum(bsum, red);
+  if (threadIdx.x == 0) sc->bhat = bsum / wsum;
+}
+
+// partial sums of log1p(-bhat x_i)
+__global__ void __launch_bounds__(256) psis_gpd_k_kernel(PsisScalars* sc, const double* __restrict__ sorted_x,
+                                                         double* __restrict__ part) {
+  __shared__ double red[32];
+  if (sc->status) return;
+  const int N = (int)sc->ntail;
+  double acc = 0.0;
+  if (N > 4) {
+    const double nb = -sc->bhat;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) acc += log1p(nb * sorted_x[i]);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = acc;
 }
 
 __device__ __forceinline__ double gpinv1(double p, double k, double sigma) {
@@ -370,85 +754,85 @@ __device__ __forceinline__ double gpinv1(double p, double k, double sigma) {
   return q * sigma;
 }
 
-// posterior weights, k-hat, sigma, smoothing decision, LSE  (_psis.py:288-324, :188-201)
-__global__ void __launch_bounds__(kSelThreads) psis_gpd_finish_kernel(PsisScalars* sc, const double* __restrict__ sorted_x,
-                                                                       const double* __restrict__ tail_x,
-                                                                       const double* __restrict__ bs, const double* __restrict__ ks,
-                                                                       double* __restrict__ Ls, double* __restrict__ result) {
+// k-hat, sigma (:313-324) and the smoothing decision (:188); then the per-rank tail values
+__global__ void __launch_bounds__(256) psis_tail_values_kernel(PsisScalars* sc, const double* __restrict__ kpart, int nkpart,
+                                                               const double* __restrict__ tail_v, double* __restrict__ tail_out,
+                                                               double* __restrict__ part3) {
   __shared__ double red[32];
+  if (sc->status) return;
+  const int N = (int)sc->ntail;
+  double k = INFINITY, sigma = 0.0;
+  if (N > 4) {
+    double s = 0.0;
+    for (int i = 0; i < nkpart; ++i) s += kpart[i];            // same order in every CTA
+    k = s / (double)N;
+    sigma = -k / sc->bhat;
+    k = k * (double)N / ((double)N + 10.0) + 5.0 / ((double)N + 10.0);
+  }
+  const bool smooth = (k >= 1.0 / 3.0) && !isinf(k);
+  const double expcut = sc->expcut;
+  double ts = 0.0, sv = 0.0, se = 0.0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x) {
+    double v;
+    if (smooth) {
+      v = log(gpinv1(((double)r + 0.5) / (double)N, k, sigma) + expcut);      // :190-197
+      v = v > 0.0 ? 0.0 : v;                                                   // :199
+    } else {
+      v = tail_v[r];
+    }
+    tail_out[r] = v;
+    ts += exp(v);
+    if (smooth) {          // moments of the smoothed tail (pass B covers everything it writes itself)
+      sv += v;
+      se += exp(2.0 * v);
+    }
+  }
+  ts = block_sum(ts, red);
+  sv = block_sum(sv, red);
+  se = block_sum(se, red);
+  if (threadIdx.x == 0) {
+    part3[3 * blockIdx.x] = ts;
+    part3[3 * blockIdx.x + 1] = sv;
+    part3[3 * blockIdx.x + 2] = se;
+    if (blockIdx.x == 0) {
+      sc->k = k;
+      sc->sigma = sigma;
+      sc->smoothed = smooth ? 1 : 0;
+    }
+  }
+}
+
+__global__ void psis_lse_kernel(PsisScalars* sc, const double* __restrict__ part3, int nparts, double* __restrict__ result) {
   if (sc->status) {
     if (threadIdx.x == 0) result[R_STATUS] = (double)sc->status;
     return;
   }
-  const int N = (int)sc->ntail;
-  double k = INFINITY, sigma = 0.0;
-  if (N > 4) {
-    const int m = 30 + (int)sqrt((double)N);
-    for (int j = threadIdx.x; j < m; j += blockDim.x) {
-      double L = bs[j] / ks[j];
-      L = log(-L);
-      L -= ks[j];
-      L -= 1.0;
-      Ls[j] = L * (double)N;
-    }
-    __syncthreads();
-    // w_j = 1 / sum_i exp(L_i - L_j); negligible weights dropped; b = sum b_j w_j / sum w_j
-    double wsum = 0.0, bsum = 0.0;
-    for (int j = threadIdx.x; j < m; j += blockDim.x) {
-      const double Lj = Ls[j];
-      double den = 0.0;
-      for (int i = 0; i < m; ++i) den += exp(Ls[i] - Lj);
-      const double w = 1.0 / den;
-      if (w >= 10.0 * DBL_EPSILON) {
-        wsum += w;
-        bsum += bs[j] * w;
-      }
-    }
-    wsum = block_sum(wsum, red);
-    bsum = block_sum(bsum, red);
-    const double b = bsum / wsum;
-    double acc = 0.0;
-    const double nb = -b;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) acc += log1p(nb * sorted_x[i]);
-    acc = block_sum(acc, red);
-    k = acc / (double)N;
-    sigma = -k / b;
-    k = k * (double)N / ((double)N + 10.0) + 5.0 / ((double)N + 10.0);
+  double ts = 0.0, sv = 0.0, se = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += 32) {
+    ts += part3[3 * i];
+    sv += part3[3 * i + 1];
+    se += part3[3 * i + 2];
   }
-  const bool smooth = (k >= 1.0 / 3.0) && !isinf(k);
-  // LSE pieces: sum over tail of exp(v), v = smoothed (clamped at 0) or raw shifted value
-  double ts = 0.0;
-  const double expcut = sc->expcut;
-  for (int r = threadIdx.x; r < N; r += blockDim.x) {
-    double v;
-    if (smooth) {
-      v = log(gpinv1(((double)r + 0.5) / (double)N, k, sigma) + expcut);
-      v = v > 0.0 ? 0.0 : v;
-    } else {
-      v = tail_x[r];                         // any order: only the sum matters
-    }
-    ts += exp(v);
-  }
-  ts = block_sum(ts, red);
-  if (threadIdx.x == 0) {
-    const double below = sc->body_below > 0.0 ? sc->body_below * exp(sc->t0 - sc->maxv) : 0.0;
-    const double total = below + sc->body_cand + ts;
-    sc->k = k;
-    sc->sigma = sigma;
-    sc->smoothed = smooth ? 1 : 0;
-    sc->tail_sum = ts;
-    sc->lse = log(total);
-    result[R_KHAT] = k;
-    result[R_SIGMA] = sigma;
-    result[R_N2] = (double)N;
-    result[R_CUTOFF] = sc->cutoff;
-    result[R_LSE] = sc->lse;
-    result[R_MAX] = sc->maxv;
-    result[R_STATUS] = 0.0;
-    result[R_M] = (double)sc->M;
-    result[R_NCAND] = (double)sc->ncand;
-    result[R_SMOOTHED] = smooth ? 1.0 : 0.0;
-  }
+  ts = warp_sum(ts);
+  sv = warp_sum(sv);
+  se = warp_sum(se);
+  if (threadIdx.x != 0) return;
+  const double below = sc->body_below > 0.0 ? sc->body_below * exp(sc->t0 - sc->maxv) : 0.0;
+  const double total = below + sc->body_cand + ts;
+  sc->tail_sum = ts;
+  sc->sumv = sv;
+  sc->sumexp2v = se;
+  sc->lse = log(total);
+  result[R_KHAT] = sc->k;
+  result[R_SIGMA] = sc->sigma;
+  result[R_N2] = (double)sc->ntail;
+  result[R_CUTOFF] = sc->cutoff;
+  result[R_LSE] = sc->lse;
+  result[R_MAX] = sc->maxv;
+  result[R_STATUS] = 0.0;
+  result[R_M] = (double)sc->M;
+  result[R_NCAND] = (double)sc->ncand;
+  result[R_SMOOTHED] = (double)sc->smoothed;
 }
 
 // pass B: out = (x - max) - lse for the body (tail entries are written by the scatter kernel when
@@ -456,47 +840,87 @@ __global__ void __launch_bounds__(kSelThreads) psis_gpd_finish_kernel(PsisScalar
 __global__ void __launch_bounds__(256) psis_pass_b_kernel(const double* __restrict__ lw, double* __restrict__ out, int64_t n,
                                                           PsisScalars* sc, double* __restrict__ blk_mom) {
   __shared__ double red[32];
+  __shared__ double etab_s[32];
+  const uint32_t etab = load_exp_table(etab_s);
   if (sc->status) return;
   const double maxv = sc->maxv, lse = sc->lse, cutoff = sc->cutoff;
   const bool smoothed = sc->smoothed != 0;
-  double sv = 0.0, se = 0.0;
+  double sv0 = 0.0, sv1 = 0.0, se0 = 0.0, se1 = 0.0;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  auto one = [&](double x, bool& skip) -> double {
-    const double v = x - maxv;
-    skip = smoothed && (v > cutoff);
-    if (!skip) {
-      sv += v;
-      se += exp(2.0 * v);
-    }
-    return v - lse;
-  };
-  const bool aligned = ((reinterpret_cast<uintptr_t>(lw) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(lw) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
   if (aligned) {
-    const int64_t n2 = n / 2;
-    for (int64_t q = tid; q < n2; q += nthreads) {
-      const double2 a = __ldcs(reinterpret_cast<const double2*>(lw) + q);
-      bool s0, s1;
-      double2 o;
-      o.x = one(a.x, s0);
-      o.y = one(a.y, s1);
-      if (!s0 && !s1) {
-        __stcs(reinterpret_cast<double2*>(out) + q, o);
+    const int64_t n4 = n / 4;
+    double2 na = make_double2(0.0, 0.0), nb = na;     // software pipeline: next iteration's loads in flight
+    if (tid < n4) {
+      na = __ldcs(reinterpret_cast<const double2*>(lw) + 2 * tid);
+      nb = __ldcs(reinterpret_cast<const double2*>(lw) + 2 * tid + 1);
+    }
+    for (int64_t q = tid; q < n4; q += nthreads) {
+      const double2 a = na, b = nb;
+      const int64_t qn = q + nthreads;
+      if (qn < n4) {
+        na = __ldcs(reinterpret_cast<const double2*>(lw) + 2 * qn);
+        nb = __ldcs(reinterpret_cast<const double2*>(lw) + 2 * qn + 1);
+      }
+      const double v0 = a.x - maxv, v1 = a.y - maxv, v2 = b.x - maxv, v3 = b.y - maxv;
+      const bool t0 = smoothed && v0 > cutoff, t1 = smoothed && v1 > cutoff, t2 = smoothed && v2 > cutoff,
+                 t3 = smoothed && v3 > cutoff;
+      sv0 += (t0 ? 0.0 : v0) + (t2 ? 0.0 : v2);
+      sv1 += (t1 ? 0.0 : v1) + (t3 ? 0.0 : v3);
+      se0 += (t0 ? 0.0 : exp_nonpos(2.0 * v0, etab)) + (t2 ? 0.0 : exp_nonpos(2.0 * v2, etab));
+      se1 += (t1 ? 0.0 : exp_nonpos(2.0 * v1, etab)) + (t3 ? 0.0 : exp_nonpos(2.0 * v3, etab));
+      if (!(t0 | t1 | t2 | t3)) {
+        __stcs(reinterpret_cast<double2*>(out) + 2 * q, make_double2(v0 - lse, v1 - lse));
+        __stcs(reinterpret_cast<double2*>(out) + 2 * q + 1, make_double2(v2 - lse, v3 - lse));
       } else {
-        if (!s0) out[2 * q] = o.x;
-        if (!s1) out[2 * q + 1] = o.y;
+        if (!t0) out[4 * q] = v0 - lse;
+        if (!t1) out[4 * q + 1] = v1 - lse;
+        if (!t2) out[4 * q + 2] = v2 - lse;
+        if (!t3) out[4 * q + 3] = v3 - lse;
       }
     }
-    if ((n & 1) && tid == 0) {
-      bool s0;
-      const double o = one(lw[n - 1], s0);
-      if (!s0) out[n - 1] = o;
+    for (int64_t i = n4 * 4 + tid; i < n; i += nthreads) {
+      const double v = lw[i] - maxv;
+      if (!(smoothed && v > cutoff)) {
+        sv0 += v;
+        se0 += exp_nonpos(2.0 * v, etab);
+        out[i] = v - lse;
+      }
     }
   } else {
     for (int64_t i = tid; i < n; i += nthreads) {
-      bool s0;
-      const double o = one(lw[i], s0);
-      if (!s0) out[i] = o;
+      const double v = lw[i] - maxv;
+      if (!(smoothed && v > cutoff)) {
+        sv0 += v;
+        se0 += exp_nonpos(2.0 * v, etab);
+        out[i] = v - lse;
+      }
+    }
+  }
+  const double sv = block_sum(sv0 + sv1, red);
+  const double se = block_sum(se0 + se1, red);
+  if (threadIdx.x == 0) {
+    blk_mom[2 * blockIdx.x] = sv;
+    blk_mom[2 * blockIdx.x + 1] = se;
+  }
+}
+
+// moments without writing an output array (k-hat / bounds only): 16 bytes per draw in total
+__global__ void __launch_bounds__(256) psis_pass_b_moments_kernel(const double* __restrict__ lw, int64_t n, PsisScalars* sc,
+                                                                  double* __restrict__ blk_mom) {
+  __shared__ double red[32];
+  __shared__ double etab_s[32];
+  const uint32_t etab = load_exp_table(etab_s);
+  if (sc->status) return;
+  const double maxv = sc->maxv, cutoff = sc->cutoff;
+  const bool smoothed = sc->smoothed != 0;
+  double sv = 0.0, se = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = lw[i] - maxv;
+    if (!(smoothed && v > cutoff)) {
+      sv += v;
+      se += exp_nonpos(2.0 * v, etab);
     }
   }
   sv = block_sum(sv, red);
@@ -510,35 +934,29 @@ __global__ void __launch_bounds__(256) psis_pass_b_kernel(const double* __restri
 // smoothed tail values into place (_psis.py:190-199) and final moment reduction
 __global__ void __launch_bounds__(256) psis_tail_scatter_kernel(double* __restrict__ out, PsisScalars* sc,
                                                                 const int64_t* __restrict__ tail_i,
-                                                                const int* __restrict__ rank_of,
+                                                                const double* __restrict__ tail_out,
                                                                 const double* __restrict__ blk_mom, int nblk,
                                                                 double* __restrict__ result) {
   __shared__ double red[32];
   if (sc->status) return;
   const int N = (int)sc->ntail;
-  const bool smoothed = sc->smoothed != 0;
-  const double k = sc->k, sigma = sc->sigma, expcut = sc->expcut, lse = sc->lse;
-  double sv = 0.0, se = 0.0;
-  if (smoothed) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-      double v = log(gpinv1(((double)rank_of[i] + 0.5) / (double)N, k, sigma) + expcut);
-      v = v > 0.0 ? 0.0 : v;
-      out[tail_i[i]] = v - lse;
-      sv += v;
-      se += exp(2.0 * v);
-    }
+  const double lse = sc->lse;
+  if (out && sc->smoothed) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x)
+      out[tail_i[r]] = tail_out[r] - lse;
   }
   if (blockIdx.x == 0) {
+    double sv = 0.0, se = 0.0;
     for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
       sv += blk_mom[2 * b];
       se += blk_mom[2 * b + 1];
     }
-  }
-  sv = block_sum(sv, red);
-  se = block_sum(se, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(&result[R_SUMV], sv);
-    atomicAdd(&result[R_SUMEXP2V], se);
+    sv = block_sum(sv, red);
+    se = block_sum(se, red);
+    if (threadIdx.x == 0) {
+      result[R_SUMV] = sv + sc->sumv;
+      result[R_SUMEXP2V] = se + sc->sumexp2v;
+    }
   }
 }
 
@@ -623,11 +1041,12 @@ __global__ void __launch_bounds__(256) dbound_sum_kernel(const double* __restric
 
 // ---------------------------------------------------------------------------------------------
 struct PsisPlan {
-  int M, m_sample, grid, tail_cap, mgrid;
+  int M, m_sample, grid, tail_cap, mgrid, kparts, vparts;
   unsigned int cap, R;
   int64_t stride;
-  size_t off_sc, off_skeys, off_candx, off_candi, off_candk, off_blk, off_tailx, off_taili, off_sorted, off_rank,
-      off_idxsorted, off_orderrank, off_bs, off_ks, off_Ls, off_mom, off_ghist, total;
+  size_t off_sc, off_candx, off_candi, off_blk, off_tmpv, off_tmpi, off_tmpb, off_tailv, off_taili, off_tailout,
+      off_sorted, off_idxsorted, off_orderrank, off_bs, off_part, off_Ls, off_kpart, off_part3, off_mom, off_ghist,
+      off_vhist, off_voff, off_gbuf, total;
 };
 
 static void psis_plan(int64_t n, double reff, PsisPlan& p) {
@@ -649,26 +1068,44 @@ static void psis_plan(int64_t n, double reff, PsisPlan& p) {
   const int64_t need = (n / 4 + 255) / 256;
   if (need < p.grid) p.grid = (int)(need < 1 ? 1 : need);
   p.mgrid = 30 + (int)sqrt((double)p.tail_cap) + 2;
+  p.kparts = 64;
+  p.vparts = 64;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   p.off_sc = take(sizeof(PsisScalars));
-  p.off_skeys = take(sizeof(unsigned long long) * p.m_sample);
   p.off_candx = take(sizeof(double) * p.cap);
   p.off_candi = take(sizeof(int64_t) * p.cap);
-  p.off_candk = take(sizeof(unsigned long long) * p.cap);
   p.off_blk = take(sizeof(double) * p.grid);
-  p.off_tailx = take(sizeof(double) * p.tail_cap);
+  p.off_tmpv = take(sizeof(double) * p.tail_cap);
+  p.off_tmpi = take(sizeof(int64_t) * p.tail_cap);
+  p.off_tmpb = take(sizeof(int) * p.tail_cap);
+  p.off_tailv = take(sizeof(double) * p.tail_cap);
   p.off_taili = take(sizeof(int64_t) * p.tail_cap);
+  p.off_tailout = take(sizeof(double) * p.tail_cap);
   p.off_sorted = take(sizeof(double) * p.tail_cap);
-  p.off_rank = take(sizeof(int) * p.tail_cap);
   p.off_idxsorted = take(sizeof(int64_t) * p.tail_cap);
   p.off_orderrank = take(sizeof(int) * p.tail_cap);
   p.off_bs = take(sizeof(double) * p.mgrid);
-  p.off_ks = take(sizeof(double) * p.mgrid);
+  p.off_part = take(sizeof(double) * p.mgrid * kGpdSplit);
   p.off_Ls = take(sizeof(double) * p.mgrid);
+  p.off_kpart = take(sizeof(double) * p.kparts);
+  p.off_part3 = take(sizeof(double) * 3 * p.vparts);
   p.off_mom = take(sizeof(double) * 2 * p.grid);
   p.off_ghist = take(sizeof(unsigned int) * kBins);
+  p.off_vhist = take(sizeof(unsigned int) * 2 * kVBins);       // tail-bin counts, then cursors
+  p.off_voff = take(sizeof(unsigned int) * kVBins);
+  p.off_gbuf = take(sizeof(unsigned long long) * kGather);
   p.total = off;
+}
+
+static bool g_tab_ready = false;
+static int ensure_exp_table() {
+  if (g_tab_ready) return VB_OK;
+  double tab[32];
+  for (int j = 0; j < 32; ++j) tab[j] = exp2((double)j / 32.0);
+  VB_CUDA(cudaMemcpyToSymbol(c_exp2_tab, tab, sizeof(tab)));
+  g_tab_ready = true;
+  return VB_OK;
 }
 
 }  // namespace vb
@@ -697,35 +1134,39 @@ extern "C" int vb_psislw_f64(const double* lw, double* out, int64_t n, double re
   PsisPlan p;
   psis_plan(n, reff, p);
   if (!workspace || workspace_bytes < p.total) return set_error(VB_ERR_WORKSPACE, "psislw: workspace too small");
+  int rc = ensure_exp_table();
+  if (rc) return rc;
   char* ws = static_cast<char*>(workspace);
   PsisScalars* sc = reinterpret_cast<PsisScalars*>(ws + p.off_sc);
-  auto skeys = reinterpret_cast<unsigned long long*>(ws + p.off_skeys);
   auto candx = reinterpret_cast<double*>(ws + p.off_candx);
   auto candi = reinterpret_cast<int64_t*>(ws + p.off_candi);
-  auto candk = reinterpret_cast<unsigned long long*>(ws + p.off_candk);
   auto blk = reinterpret_cast<double*>(ws + p.off_blk);
-  auto tailx = reinterpret_cast<double*>(ws + p.off_tailx);
+  auto tmpv = reinterpret_cast<double*>(ws + p.off_tmpv);
+  auto tmpi = reinterpret_cast<int64_t*>(ws + p.off_tmpi);
+  auto tmpb = reinterpret_cast<int*>(ws + p.off_tmpb);
+  auto tailv = reinterpret_cast<double*>(ws + p.off_tailv);
   auto taili = reinterpret_cast<int64_t*>(ws + p.off_taili);
+  auto tailout = reinterpret_cast<double*>(ws + p.off_tailout);
   auto sorted = reinterpret_cast<double*>(ws + p.off_sorted);
-  auto rankof = reinterpret_cast<int*>(ws + p.off_rank);
-  auto idxsorted = tail_idx ? tail_idx : reinterpret_cast<int64_t*>(ws + p.off_idxsorted);
-  auto orderrank = tail_rank ? tail_rank : reinterpret_cast<int*>(ws + p.off_orderrank);
   auto bs = reinterpret_cast<double*>(ws + p.off_bs);
-  auto ks = reinterpret_cast<double*>(ws + p.off_ks);
+  auto part = reinterpret_cast<double*>(ws + p.off_part);
   auto Ls = reinterpret_cast<double*>(ws + p.off_Ls);
+  auto kpart = reinterpret_cast<double*>(ws + p.off_kpart);
+  auto part3 = reinterpret_cast<double*>(ws + p.off_part3);
   auto mom = reinterpret_cast<double*>(ws + p.off_mom);
   auto ghist = reinterpret_cast<unsigned int*>(ws + p.off_ghist);
+  auto vhist = reinterpret_cast<unsigned int*>(ws + p.off_vhist);
+  auto vcur = vhist + kVBins;
+  auto voff = reinterpret_cast<unsigned int*>(ws + p.off_voff);
+  auto gbuf = reinterpret_cast<unsigned long long*>(ws + p.off_gbuf);
 
   VB_CUDA(cudaMemsetAsync(result, 0, sizeof(double) * R_COUNT, stream));
-  psis_init_kernel<<<1, 1, 0, stream>>>(sc, p.M);
+  psis_init_kernel<<<8, 1024, 0, stream>>>(sc, p.M, ghist, vhist);
   VB_CHECK_LAUNCH();
   if (!exact) {
-    psis_sample_kernel<<<(p.m_sample + 255) / 256, 256, 0, stream>>>(lw, n, p.stride, p.m_sample, skeys);
-    VB_CHECK_LAUNCH();
-    psis_sample_select_kernel<<<1, kSelThreads, 0, stream>>>(skeys, p.m_sample, p.R, sc);
+    psis_sample_select_kernel<<<1, kSelThreads, 0, stream>>>(lw, p.stride, p.m_sample, p.R, sc);
     VB_CHECK_LAUNCH();
   } else {
-    VB_CUDA(cudaMemsetAsync(ghist, 0, sizeof(unsigned int) * kBins, stream));
     psis_exact_begin_kernel<<<1, 1, 0, stream>>>(sc);
     VB_CHECK_LAUNCH();
     int shift = 64;
@@ -740,28 +1181,51 @@ extern "C" int vb_psislw_f64(const double* lw, double* out, int64_t n, double re
       mask |= (unsigned long long)((1u << bits) - 1) << shift;
     }
   }
-  psis_pass_a_kernel<<<p.grid, 256, 0, stream>>>(lw, n, sc, candx, candi, candk, p.cap, blk);
+  psis_pass_a_kernel<<<p.grid, 256, 0, stream>>>(lw, n, sc, candx, candi, p.cap, blk);
   VB_CHECK_LAUNCH();
-  psis_cutoff_kernel<<<1, kSelThreads, 0, stream>>>(sc, candk, p.cap, blk, p.grid);
+  const int cgrid = sm_count() * 2;
+  psis_cand_hist_kernel<<<cgrid, 256, 0, stream>>>(sc, candx, p.cap, ghist);
   VB_CHECK_LAUNCH();
-  psis_tail_compact_kernel<<<sm_count(), 256, 0, stream>>>(sc, candx, candi, tailx, taili, (unsigned)p.tail_cap);
+  psis_cand_gather_kernel<<<cgrid / 4 > 0 ? cgrid / 4 : 1, kSelThreads, 0, stream>>>(sc, candx, p.cap, ghist, gbuf);
+  VB_CHECK_LAUNCH();
+  psis_cutoff_kernel<<<1, kSelThreads, 0, stream>>>(sc, candx, p.cap, gbuf, blk, p.grid);
+  VB_CHECK_LAUNCH();
+  psis_tail_count_kernel<<<cgrid, 256, 0, stream>>>(sc, candx, vhist);
+  VB_CHECK_LAUNCH();
+  psis_tail_scan_kernel<<<1, kSelThreads, 0, stream>>>(sc, vhist, voff);
+  VB_CHECK_LAUNCH();
+  psis_tail_place_kernel<<<cgrid, 256, 0, stream>>>(sc, candx, candi, voff, vcur, tmpv, tmpi, tmpb, (unsigned)p.tail_cap);
   VB_CHECK_LAUNCH();
   {
     int blocks = (p.tail_cap + 255) / 256;
     if (blocks > sm_count() * 4) blocks = sm_count() * 4;
-    psis_tail_rank_kernel<<<blocks, 256, 0, stream>>>(sc, tailx, taili, sorted, rankof, idxsorted, orderrank);
+    psis_tail_rank_kernel<<<blocks, 256, 0, stream>>>(sc, tmpv, tmpi, tmpb, voff, vhist, tailv, taili, sorted);
     VB_CHECK_LAUNCH();
+    if (tail_idx && tail_rank) {
+      psis_tail_index_order_kernel<<<blocks, 256, 0, stream>>>(sc, taili, tail_idx, tail_rank);
+      VB_CHECK_LAUNCH();
+    }
   }
-  psis_gpd_grid_kernel<<<p.mgrid, 256, 0, stream>>>(sc, sorted, bs, ks);
+  psis_gpd_grid_kernel<<<dim3(p.mgrid, kGpdSplit), 256, 0, stream>>>(sc, sorted, bs, part);
   VB_CHECK_LAUNCH();
-  psis_gpd_finish_kernel<<<1, kSelThreads, 0, stream>>>(sc, sorted, tailx, bs, ks, Ls, result);
+  psis_gpd_weights_kernel<<<1, kSelThreads, 0, stream>>>(sc, bs, part, Ls);
+  VB_CHECK_LAUNCH();
+  psis_gpd_k_kernel<<<p.kparts, 256, 0, stream>>>(sc, sorted, kpart);
+  VB_CHECK_LAUNCH();
+  psis_tail_values_kernel<<<p.vparts, 256, 0, stream>>>(sc, kpart, p.kparts, tailv, tailout, part3);
+  VB_CHECK_LAUNCH();
+  psis_lse_kernel<<<1, 32, 0, stream>>>(sc, part3, p.vparts, result);
   VB_CHECK_LAUNCH();
   if (out) {
     psis_pass_b_kernel<<<p.grid, 256, 0, stream>>>(lw, out, n, sc, mom);
-    VB_CHECK_LAUNCH();
+  } else {
+    psis_pass_b_moments_kernel<<<p.grid, 256, 0, stream>>>(lw, n, sc, mom);
+  }
+  VB_CHECK_LAUNCH();
+  {
     int blocks = (p.tail_cap + 255) / 256;
     if (blocks > sm_count()) blocks = sm_count();
-    psis_tail_scatter_kernel<<<blocks, 256, 0, stream>>>(out, sc, taili, rankof, mom, p.grid, result);
+    psis_tail_scatter_kernel<<<blocks, 256, 0, stream>>>(out, sc, taili, tailout, mom, p.grid, result);
     VB_CHECK_LAUNCH();
   }
   return VB_OK;
