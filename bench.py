@@ -247,6 +247,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     import viabel_b200 as vb
+    from viabel_b200.parallel import shard_rows
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -258,7 +259,7 @@ def run_b200(args):
 
     N, d, S = args.n_obs, args.dim, args.mc
     # this rank's rows [lo, hi) of the N x d problem; rank r seeds its rows with DATA_SEED + r
-    lo, hi = rank * N // world, (rank + 1) * N // world
+    lo, hi = shard_rows(N, rank, world)
     gen = torch.Generator(device=dev)
     gen.manual_seed(DATA_SEED + 7919)
     beta = torch.randn(d, generator=gen, device=dev, dtype=torch.float64) / np.sqrt(d)
@@ -300,6 +301,15 @@ def run_b200(args):
     e1.record()
     barrier()
     elapsed = e0.elapsed_time(e1) * 1e-3
+    # nvidia-smi samples every 100 ms; a short timed region (K steps of ~1 ms) can fall between two samples,
+    # so the same step keeps running (untimed, every rank: the step contains the all-reduce) until the sampler
+    # has seen the GPU under this load
+    t_extra = time.perf_counter()
+    while elapsed < 0.6 and time.perf_counter() - t_extra < 0.6:
+        step()
+        if world > 1:
+            torch.cuda.synchronize()
+    barrier()
     clocks = sampler.stop() if sampler else None
     if world > 1:
         t = torch.tensor([elapsed], device=dev, dtype=torch.float64)

@@ -12,6 +12,7 @@ import torch
 
 from . import _lib
 from ._tensor import F64, device, is_host, like_input, to_dev
+from .parallel import allreduce_sum_
 
 __all__ = ['Model', 'GLMModel', 'LogisticRegression', 'ProbitRegression']
 
@@ -138,8 +139,8 @@ class GLMModel(Model):
         return self._ws
 
     def _allreduce(self, buf):
-        if self.sharded and torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(buf, group=self.process_group)
+        if self.sharded:
+            allreduce_sum_(buf, self.process_group)
 
     def sweep(self, theta, base=None, w=None, want_grad=True, aux=None, ll_total_only=False):
         """One pass over the observations.  Returns (ll[S], gmu[d], ge[d]); the last two are None
