@@ -301,20 +301,18 @@ def run_b200(args):
     e1.record()
     barrier()
     elapsed = e0.elapsed_time(e1) * 1e-3
-    # nvidia-smi samples every 100 ms; a short timed region (K steps of ~1 ms) can fall between two samples,
-    # so the same step keeps running (untimed, every rank: the step contains the all-reduce) until the sampler
-    # has seen the GPU under this load
-    t_extra = time.perf_counter()
-    while elapsed < 0.6 and time.perf_counter() - t_extra < 0.6:
-        step()
-        if world > 1:
-            torch.cuda.synchronize()
-    barrier()
-    clocks = sampler.stop() if sampler else None
     if world > 1:
         t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
+    # nvidia-smi samples every 100 ms; a short timed region (K steps of ~1 ms) can fall between two samples,
+    # so the same step keeps running (untimed; the same count on every rank, the step contains the all-reduce)
+    # until the sampler has seen the GPU under this load
+    n_extra = 0 if elapsed >= 0.6 else min(5000, int(0.6 / max(elapsed / args.steps, 1e-5)))
+    for _ in range(n_extra):
+        step()
+    barrier()
+    clocks = sampler.stop() if sampler else None
     ms_per_step = elapsed / args.steps * 1e3
 
     # ---- end-to-end through the public API with HOST buffers (numpy in, numpy out) -----------

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from conftest import relerr
-from _problems import logistic_problem, target_params
+from _problems import hier_problem, logistic_problem, target_params
 
 pytestmark = pytest.mark.gpu
 
@@ -75,8 +75,8 @@ def test_philox_student_and_chisquare(vb):
     assert abs(t.var() - df / (df - 2)) < 0.03
 
 
-FAMILY_TAGS = ['%s_df%s_d%d' % (k, df, d) for k, df in (('mfg', None), ('mft', 20), ('mft', 5.5))
-               for d in (1, 3, 8)]
+FAMILY_TAGS = ['%s_df%s_d%d' % (k, df, d)
+               for k, df in (('mfg', None), ('mft', 20), ('mft', 5.5), ('mvt', 100), ('mvt', 7)) for d in (1, 3, 8)]
 
 
 @pytest.mark.parametrize('tag', FAMILY_TAGS)
@@ -84,11 +84,16 @@ def test_family_golden(vb, golden, tag):
     g = golden('families')
     kind, df, d = tag.split('_')
     d = int(d[1:])
-    fam = vb.MFGaussian(d) if kind == 'mfg' else vb.MFStudentT(d, float(df[2:]))
+    if kind == 'mvt':
+        fam = vb.MultivariateT(d, float(df[2:]))
+        base = (g[tag + '/chi2'], g[tag + '/z'])
+    else:
+        fam = vb.MFGaussian(d) if kind == 'mfg' else vb.MFStudentT(d, float(df[2:]))
+        base = g[tag + '/base']
     vp, vp1 = g[tag + '/var_param'], g[tag + '/var_param1']
-    x = fam.sample(vp, 64, base=g[tag + '/base'])
+    x = fam.sample(vp, 64, base=base)
     assert isinstance(x, np.ndarray)
-    assert relerr(x, g[tag + '/sample']) < 1e-14
+    assert relerr(x, g[tag + '/sample']) < 1e-12
     assert relerr(fam.log_density(vp, x), g[tag + '/log_density']) < TOL64
     assert relerr(fam.log_density(vp, x[0]), g[tag + '/log_density_1d']) < TOL64
     assert relerr(fam.entropy(vp), g[tag + '/entropy']) < TOL64
@@ -139,6 +144,28 @@ def _torch_models(vb):
         return (c - 0.5 * (df + 1) * torch.log1p(z * z / df) - torch.log(st)).sum(dim=1)
 
     m['student_d5'] = vb.Model(student)        # gradient by torch autograd
+
+    hp = hier_problem(G=3, p=2, n_per=7, seed=15)
+    Xh = torch.as_tensor(hp['X'], device='cuda')
+    yh = torch.as_tensor(hp['y'], device='cuda')
+    grp = torch.as_tensor(hp['group'], device='cuda')
+
+    def hier(theta):
+        G, p = 3, 2
+        S = theta.shape[0]
+        beta = theta[:, :G * p].reshape(S, G, p)
+        mm = theta[:, G * p:G * p + p]
+        ltau, lsig = theta[:, -2], theta[:, -1]
+        pred = torch.einsum('np,snp->sn', Xh, beta[:, grp, :])
+        c = 0.5 * np.log(2 * np.pi)
+        res = (yh[None, :] - pred) / torch.exp(lsig)[:, None]
+        lp = (-0.5 * res ** 2).sum(dim=1) - Xh.shape[0] * (lsig + c)
+        db = (beta - mm[:, None, :]) / torch.exp(ltau)[:, None, None]
+        lp = lp + (-0.5 * db ** 2).sum(dim=(1, 2)) - G * p * (ltau + c)
+        lp = lp + (-0.5 * (mm / 10.0) ** 2).sum(dim=1) - p * (np.log(10.0) + c)
+        return lp - 0.5 * ltau ** 2 - c - 0.5 * lsig ** 2 - c
+
+    m['hier_G3p2'] = vb.Model(hier)
     return m
 
 
@@ -150,23 +177,31 @@ def test_objectives_golden(vb, golden):
     for tag in tags:
         mname, fam, point, oname = tag.split('/')
         kind, df = fam.split('_df')
-        if kind == 'mvt' or mname not in models:
+        if mname not in models:
             continue
-        vp, base = g[tag + '/var_param'], g[tag + '/base']
-        d = base.shape[1]
-        approx = vb.MFGaussian(d) if kind == 'mfg' else vb.MFStudentT(d, float(df))
-        if oname == 'ekl':
-            obj = vb.ExclusiveKL(approx, models[mname], base.shape[0])
-        elif oname == 'ekl_path':
-            obj = vb.ExclusiveKL(approx, models[mname], base.shape[0], use_path_deriv=True)
+        vp = g[tag + '/var_param']
+        if kind == 'mvt':
+            base = (g[tag + '/chi2'], g[tag + '/z'])
+            d = base[1].shape[1]
+            approx = vb.MultivariateT(d, float(df))
+            nS = base[1].shape[0]
         else:
-            obj = vb.AlphaDivergence(approx, models[mname], base.shape[0], float(oname[5:]))
+            base = g[tag + '/base']
+            d = base.shape[1]
+            approx = vb.MFGaussian(d) if kind == 'mfg' else vb.MFStudentT(d, float(df))
+            nS = base.shape[0]
+        if oname == 'ekl':
+            obj = vb.ExclusiveKL(approx, models[mname], nS)
+        elif oname == 'ekl_path':
+            obj = vb.ExclusiveKL(approx, models[mname], nS, use_path_deriv=True)
+        else:
+            obj = vb.AlphaDivergence(approx, models[mname], nS, float(oname[5:]))
         value, grad = obj(vp, base=base)
         assert isinstance(grad, np.ndarray)
         assert relerr(value, g[tag + '/value']) < TOL64, (tag, 'value')
         assert relerr(grad, g[tag + '/grad']) < TOL64, (tag, 'grad')
         checked += 1
-    assert checked >= 60
+    assert checked >= 100
 
 
 @pytest.mark.parametrize('N,d,S', [(1000, 10, 10), (1003, 13, 7), (20000, 512, 256), (4100, 130, 300),

@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from ._tensor import F64, device, is_host, like_input, to_dev
 
-__all__ = ['ApproximationFamily', 'MFGaussian', 'MFStudentT']
+__all__ = ['ApproximationFamily', 'MFGaussian', 'MFStudentT', 'MultivariateT']
 
 
 class ApproximationFamily(ABC):
@@ -228,3 +228,136 @@ class MFStudentT(_MeanField):
 
     def supports_pth_moment(self, p):
         return p in [2, 4] and p < self.df
+
+
+class MultivariateT(ApproximationFamily):
+    """A full-rank multivariate t approximation family (approximations.py:322-382,
+    _distributions.py:7-38).
+
+    var_param = [mu(d), row-major lower triangle of F] with L = tril(F,-1) + diag(exp(diag F)) and
+    Sigma = L L^T (paragami PSDSymmetricMatrixPattern, approximations.py:315-319).  Samples use the
+    SYMMETRIC square root of Sigma, as the reference does (:348).  The d x d algebra (eigh, GEMMs)
+    is replicated on every rank and runs in cuSOLVER / cuBLAS through torch; the base draws and the
+    O(n d) reductions are this package's kernels.  Entropy is sum(log L_ii) -- the reference's
+    0.5*log(det(Sigma)) (:354) overflows for large d but is the same number."""
+
+    def __init__(self, dim, df, seed=1):
+        if df <= 2:
+            raise ValueError('df must be greater than 2')
+        self._df = df
+        self._seed = int(seed)
+        self._offset = 0
+        self.last_base = None
+        self._tril = None
+        super().__init__(dim, dim + dim * (dim + 1) // 2, True, False)
+
+    @property
+    def df(self):
+        return self._df
+
+    def init_param(self):
+        # mu = 0, Sigma = 10 I  ->  F = diag(log sqrt(10))   (approximations.py:337-340)
+        d = self.dim
+        F = np.zeros((d, d))
+        F[np.diag_indices(d)] = 0.5 * np.log(10.0)
+        return np.concatenate([np.zeros(d), F[np.tril_indices(d)]])
+
+    # -- parameter unpacking on the device ---------------------------------------------------------
+    def _tril_idx(self, dev):
+        if self._tril is None or self._tril[0].device != dev:
+            r, c = np.tril_indices(self.dim)
+            self._tril = (torch.as_tensor(r, device=dev), torch.as_tensor(c, device=dev))
+        return self._tril
+
+    def unpack(self, vp):
+        """(mu[d], F[d,d], L[d,d]) as CUDA tensors."""
+        d = self.dim
+        if vp.numel() != self.var_param_dim:
+            raise ValueError('var_param has the wrong length')
+        r, c = self._tril_idx(vp.device)
+        F = torch.zeros(d, d, dtype=F64, device=vp.device)
+        F[r, c] = vp[d:]
+        L = torch.tril(F, -1) + torch.diag(torch.exp(torch.diagonal(F)))
+        return vp[:d], F, L
+
+    def pack_grad(self, gmu, Fbar):
+        r, c = self._tril_idx(Fbar.device)
+        return torch.cat([gmu, Fbar[r, c]])
+
+    @staticmethod
+    def sym_sqrt(Sigma):
+        """(A, w, V) with A = V diag(sqrt w) V^T, the PSD square root scipy.linalg.sqrtm returns."""
+        w, V = torch.linalg.eigh(Sigma)
+        return (V * torch.sqrt(torch.clamp(w, min=0.0))) @ V.T, w, V
+
+    # -- base draws: chi-square FIRST, then normals, as the reference (:345-347) -------------------
+    def base_draws(self, n_samples, seed=None):
+        n, d = int(n_samples), self.dim
+        dev = device()
+        chi2 = torch.empty(n, dtype=F64, device=dev)
+        z = torch.empty(n * d, dtype=F64, device=dev)
+        s, off = (self._seed, self._offset) if seed is None else (int(seed), 0)
+        _lib.check(_lib.lib.vb_philox_chisquare_f64(_lib.ptr(chi2), n, float(self._df), s, off, _lib.stream()))
+        off2 = off + n + (n & 1)
+        _lib.check(_lib.lib.vb_philox_normal_f64(_lib.ptr(z), n * d, s, off2, 0, _lib.stream()))
+        if seed is None:
+            self._offset = off2 + n * d + ((n * d) & 1)
+        return chi2, z.view(n, d)
+
+    def sample(self, var_param, n_samples, seed=None, base=None):
+        host = is_host(var_param)
+        vp = to_dev(var_param)
+        mu, _, L = self.unpack(vp)
+        chi2, z = self.base_draws(n_samples, seed) if base is None else (to_dev(base[0]), to_dev(base[1]))
+        self.last_base = (chi2, z)
+        A, _, _ = self.sym_sqrt(L @ L.T)
+        theta = mu + (z @ A) / torch.sqrt(chi2 / self._df)[:, None]
+        return like_input(theta, host)
+
+    def entropy(self, var_param):
+        vp = _host(var_param)
+        d = self.dim
+        F = np.zeros((d, d))
+        F[np.tril_indices(d)] = vp[d:]
+        return float(np.sum(np.diag(F)))          # = 0.5 * log det Sigma
+
+    def log_density_device(self, vp, x):
+        """multivariate_t_logpdf (_distributions.py:7-38) on CUDA tensors: eigen-decomposition of Sigma,
+        eigenvalues <= 1e-10 get a zero inverse but still enter the log pseudo-determinant."""
+        d = self.dim
+        df = float(self._df)
+        mu, _, L = self.unpack(vp)
+        w, V = torch.linalg.eigh(L @ L.T)
+        winv = torch.where(w.abs() <= 1e-10, torch.zeros_like(w), 1.0 / w)
+        U = V * torch.sqrt(winv)
+        maha = (((x - mu) @ U) ** 2).sum(dim=-1)
+        const = (torch.lgamma(torch.tensor(0.5 * (df + d), dtype=F64)) - torch.lgamma(torch.tensor(0.5 * df, dtype=F64))
+                 - 0.5 * d * np.log(np.pi * df)).item()
+        return const - 0.5 * torch.log(w).sum() - 0.5 * (df + d) * torch.log(1.0 + maha / df)
+
+    def log_density(self, var_param, x):
+        host = is_host(x)
+        xd = to_dev(x)
+        if xd.dim() == 1:
+            xd = xd[None, :]
+        return like_input(self.log_density_device(to_dev(var_param), xd), host)
+
+    def mean_and_cov(self, var_param):
+        vp = to_dev(var_param)
+        mu, _, L = self.unpack(vp)
+        df = self._df
+        return mu.cpu().numpy().copy(), (df / (df - 2.) * (L @ L.T)).cpu().numpy()
+
+    def _pth_moment(self, var_param, p):
+        df = self._df
+        if df <= p:
+            raise ValueError('df must be greater than p')
+        _, _, L = self.unpack(to_dev(var_param))
+        sq = torch.linalg.eigvalsh(L @ L.T).cpu().numpy()
+        c = df / (df - 2)
+        if p == 2:
+            return c * np.sum(sq)
+        return c ** 2 * (2 * (df - 1) / (df - 4) * np.sum(sq ** 2) + np.sum(sq) ** 2)
+
+    def supports_pth_moment(self, p):
+        return p in [2, 4] and p < self._df

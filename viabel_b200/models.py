@@ -170,6 +170,30 @@ class GLMModel(Model):
         self._allreduce(ll)
         return ll, None, None
 
+    def logp_and_grad(self, theta, chunk=65536):
+        """Per-sample log density [S] and gradient [S,d] (needed by full-rank families, whose d x d
+        cotangent uses every sample's gradient).  The S x d gradient accumulator does not fit on chip,
+        so this is X.Theta^T and R^T.X as library GEMMs (cuBLAS fp64) over row chunks; the fused
+        sweep above is the mean-field hot path."""
+        S = theta.shape[0]
+        ll = torch.zeros(S, dtype=F64, device=theta.device)
+        G = torch.zeros_like(theta)
+        for lo in range(0, self.N, chunk):
+            Xc, yc = self.X[lo:lo + chunk], self.y[lo:lo + chunk]
+            a = (Xc @ theta.T) * yc[:, None]
+            if self.link == _lib.LINK_LOGISTIC:
+                ll += torch.nn.functional.logsigmoid(a).sum(dim=0)
+                R = torch.sigmoid(-a)
+            else:
+                lc = torch.special.log_ndtr(a)
+                ll += lc.sum(dim=0)
+                R = torch.exp(-0.5 * a * a - 0.5 * np.log(2 * np.pi) - lc)
+            G += (R * yc[:, None]).T @ Xc
+        buf = torch.cat([ll, G.reshape(-1)])
+        self._allreduce(buf)
+        ll, G = buf[:S], buf[S:].view_as(theta)
+        return ll + self.log_prior(theta), G - theta / self.prior_scale ** 2
+
     def log_prior(self, theta):
         d = self.dim
         return (-0.5 * (theta * theta).sum(dim=1) / self.prior_scale ** 2

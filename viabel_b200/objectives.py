@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 from ._tensor import F64, device, is_host, like_input, to_dev
-from .approximations import _MeanField
+from .approximations import MultivariateT, _MeanField
 from .models import GLMModel, Model
 
 __all__ = ['VariationalObjective', 'StochasticVariationalObjective', 'ExclusiveKL', 'AlphaDivergence']
@@ -76,9 +76,48 @@ class StochasticVariationalObjective(VariationalObjective):
         self._update_objective_and_grad()
 
 
+def _mvt_objective(approx, model, S, objective, alpha, var_param, base=None, seed=None):
+    """ExclusiveKL (entropy branch) / AlphaDivergence for the full-rank MultivariateT family
+    (objectives.py:154-164, :443-460 with approximations.py:342-357; gradient per SURVEY.md App. A.3).
+    The d x d algebra is replicated dense linear algebra (cuSOLVER eigh + cuBLAS GEMMs via torch)."""
+    if objective == _lib.OBJ_EXCLUSIVE_KL_PATH:
+        raise NotImplementedError('path-derivative estimator is not available for MultivariateT')
+    vp = to_dev(var_param)
+    d, df = approx.dim, float(approx.df)
+    mu, F, L = approx.unpack(vp)
+    chi2, z = approx.base_draws(S, seed) if base is None else (to_dev(base[0]), to_dev(base[1]))
+    approx.last_base = (chi2, z)
+    S = z.shape[0]
+    A, w, V = approx.sym_sqrt(L @ L.T)
+    zu = z / torch.sqrt(chi2 / df)[:, None]
+    theta = (mu + zu @ A).contiguous()
+    f, G = model.logp_and_grad(theta)
+    if objective == _lib.OBJ_EXCLUSIVE_KL:
+        value = -(f.mean() + torch.diagonal(F).sum())
+        gmu = -G.mean(dim=0)
+        Abar = -(zu.T @ G) / S
+        diag_add = -1.0
+    else:
+        lw = f - approx.log_density_device(vp, theta)
+        m = lw.max()
+        sv = torch.exp(lw - m) ** alpha
+        value = torch.log(sv.mean()) / alpha + m
+        gmu = alpha / S * (sv @ G)
+        Abar = alpha / S * (zu.T @ (sv[:, None] * G))
+        diag_add = alpha / S * sv.sum()
+    rw = torch.sqrt(w)
+    M = V.T @ Abar @ V
+    Sbar = V @ (M / (rw[:, None] + rw[None, :])) @ V.T
+    Lbar = (Sbar + Sbar.T) @ L
+    Fbar = torch.tril(Lbar, -1) + torch.diag(torch.diagonal(Lbar) * torch.diagonal(L) + diag_add)
+    return value, approx.pack_grad(gmu, Fbar)
+
+
 def _mf_objective(approx, model, S, objective, alpha, var_param, base=None, seed=None, want_logp=False):
     """One fused evaluation for a mean-field family.  Returns (value, grad[, logp]) as 0-d / 1-d
     CUDA tensors (no host sync)."""
+    if isinstance(approx, MultivariateT):
+        return _mvt_objective(approx, model, S, objective, alpha, var_param, base=base, seed=seed)
     if not isinstance(approx, _MeanField):
         raise NotImplementedError('only mean-field families are supported by this objective path')
     d = approx.dim
