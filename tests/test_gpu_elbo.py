@@ -327,3 +327,34 @@ def test_bbvi_style_fit_converges(vb):
     est_mean, est_cov = approx.mean_and_cov(res['opt_param'])
     np.testing.assert_allclose(est_mean, [1., -1.], atol=0.35)
     np.testing.assert_allclose(np.sqrt(np.diag(est_cov)), [2., 5.], rtol=0.12)
+
+
+def test_builtin_target_and_hier_plugins(vb, vo):
+    rs = np.random.RandomState(4)
+    mean, sd = target_params(6, seed=30)
+    theta = rs.randn(9, 6)
+    for plug, ref in ((vb.GaussianTarget(mean, sd), lambda t: vo.gauss_target_logp_grad(t, mean, sd)),
+                      (vb.StudentTTarget(mean, sd, 10.0), lambda t: vo.student_target_logp_grad(t, mean, sd, 10.0))):
+        lp, g = plug.logp_and_grad(torch.as_tensor(theta, device='cuda'))
+        lp0, g0 = ref(theta)
+        assert relerr(lp.cpu().numpy(), lp0) < TOL64 and relerr(g.cpu().numpy(), g0) < TOL64
+        assert relerr(plug(theta), lp0) < TOL64
+    hp = hier_problem(G=5, p=3, n_per=11, seed=31)
+    model = vb.HierarchicalLinearRegression(hp['X'], hp['y'], hp['group'], 5)
+    theta = 0.3 * rs.randn(7, model.dim)
+    lp, g = model.logp_and_grad(torch.as_tensor(theta, device='cuda'))
+    lp0, g0 = vo.hier_linear_logp_grad(theta, hp['X'], hp['y'], hp['group'], 5, 3)
+    assert relerr(lp.cpu().numpy(), lp0) < TOL64 and relerr(g.cpu().numpy(), g0) < TOL64
+    # full-rank t + AlphaDivergence on it (BASELINE configs[3] at a small size) against the oracle
+    approx = vb.MultivariateT(model.dim, 100)
+    vp = approx.init_param()
+    vp[model.dim:] *= 0.0
+    vp[model.dim:] += vo.mvt_pack(np.zeros(model.dim), 0.05 * np.eye(model.dim) + 0.01)[model.dim:]
+    chi2, z = rs.chisquare(100, 16), rs.randn(16, model.dim)
+    om = lambda th: vo.hier_linear_logp_grad(th, hp['X'], hp['y'], hp['group'], 5, 3)
+    v, gr = vb.AlphaDivergence(approx, model, 16, 2.0)(vp, base=(chi2, z))
+    v0, g0, _ = vo.alpha_divergence_mvt(vp, chi2, z, om, 100.0, 2.0)
+    assert relerr(v, v0) < 1e-9 and relerr(gr, g0) < 1e-8
+    v, gr = vb.ExclusiveKL(approx, model, 16)(vp, base=(chi2, z))
+    v0, g0, _ = vo.exclusive_kl_mvt(vp, chi2, z, om, 100.0)
+    assert relerr(v, v0) < 1e-9 and relerr(gr, g0) < 1e-8

@@ -285,9 +285,21 @@ class MultivariateT(ApproximationFamily):
         return torch.cat([gmu, Fbar[r, c]])
 
     @staticmethod
-    def sym_sqrt(Sigma):
+    def _eigh(Sigma):
+        """Symmetric eigendecomposition on the device.  cuSOLVER's divide-and-conquer can refuse a large
+        matrix whose eigenvalues are all equal (e.g. the reference's init Sigma = 10 I at d = 2048); the
+        degeneracy is then broken by a relative 1e-13 ramp on the diagonal, far below the 1e-10 tolerance."""
+        try:
+            return torch.linalg.eigh(Sigma)
+        except torch.linalg.LinAlgError:
+            d = Sigma.shape[0]
+            ramp = torch.arange(d, dtype=Sigma.dtype, device=Sigma.device) / d
+            return torch.linalg.eigh(Sigma + torch.diag(1e-13 * torch.diagonal(Sigma).abs().mean() * ramp))
+
+    @classmethod
+    def sym_sqrt(cls, Sigma):
         """(A, w, V) with A = V diag(sqrt w) V^T, the PSD square root scipy.linalg.sqrtm returns."""
-        w, V = torch.linalg.eigh(Sigma)
+        w, V = cls._eigh(Sigma)
         return (V * torch.sqrt(torch.clamp(w, min=0.0))) @ V.T, w, V
 
     # -- base draws: chi-square FIRST, then normals, as the reference (:345-347) -------------------
@@ -327,7 +339,7 @@ class MultivariateT(ApproximationFamily):
         d = self.dim
         df = float(self._df)
         mu, _, L = self.unpack(vp)
-        w, V = torch.linalg.eigh(L @ L.T)
+        w, V = self._eigh(L @ L.T)
         winv = torch.where(w.abs() <= 1e-10, torch.zeros_like(w), 1.0 / w)
         U = V * torch.sqrt(winv)
         maha = (((x - mu) @ U) ** 2).sum(dim=-1)

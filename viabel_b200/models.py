@@ -14,7 +14,8 @@ from . import _lib
 from ._tensor import F64, device, is_host, like_input, to_dev
 from .parallel import allreduce_sum_
 
-__all__ = ['Model', 'GLMModel', 'LogisticRegression', 'ProbitRegression']
+__all__ = ['Model', 'GLMModel', 'LogisticRegression', 'ProbitRegression', 'HierarchicalLinearRegression',
+           'GaussianTarget', 'StudentTTarget']
 
 
 class Model(object):
@@ -212,3 +213,80 @@ class LogisticRegression(GLMModel):
 class ProbitRegression(GLMModel):
     """Bayesian probit regression, y in {-1,+1}."""
     link = _lib.LINK_PROBIT
+
+
+class HierarchicalLinearRegression(Model):
+    """GPU-resident hierarchical linear regression (BASELINE.json configs[3]):
+
+        y_i ~ N(x_i . beta_{g(i)}, sigma),  beta_g ~ N(m, tau I),  m ~ N(0, 10 I),
+        log tau ~ N(0,1),  log sigma ~ N(0,1);   theta = [beta (G*p, group-major), m (p), log tau, log sigma].
+
+    The likelihood contraction is a dense GEMM against the block-expanded design matrix
+    X_exp[N, G*p] (cuBLAS fp64 through torch); the gradient is written out analytically."""
+
+    def __init__(self, X, y, group, n_groups):
+        Xd = to_dev(X)
+        self.y = to_dev(y).reshape(-1)
+        g = torch.as_tensor(np.asarray(group), dtype=torch.int64, device=Xd.device)
+        self.N, self.p = int(Xd.shape[0]), int(Xd.shape[1])
+        self.G = int(n_groups)
+        self.dim = self.G * self.p + self.p + 2
+        Xe = torch.zeros(self.N, self.G, self.p, dtype=F64, device=Xd.device)
+        Xe[torch.arange(self.N, device=Xd.device), g] = Xd
+        self.Xe = Xe.reshape(self.N, self.G * self.p)
+        super().__init__(lambda th: self.logp_and_grad(th)[0], lambda th: self.logp_and_grad(th)[1])
+
+    def logp_and_grad(self, theta):
+        G, p, N = self.G, self.p, self.N
+        S = theta.shape[0]
+        c = 0.5 * np.log(2 * np.pi)
+        beta = theta[:, :G * p]
+        m = theta[:, G * p:G * p + p]
+        ltau, lsig = theta[:, -2], theta[:, -1]
+        inv_sig, inv_tau = torch.exp(-lsig), torch.exp(-ltau)
+        res = (self.y[None, :] - beta @ self.Xe.T) * inv_sig[:, None]              # [S, N]
+        db = (beta.reshape(S, G, p) - m[:, None, :]) * inv_tau[:, None, None]      # [S, G, p]
+        ssr, ssb = (res * res).sum(dim=1), (db * db).sum(dim=(1, 2))
+        lp = (-0.5 * ssr - N * (lsig + c) - 0.5 * ssb - G * p * (ltau + c)
+              - 0.5 * ((m / 10.0) ** 2).sum(dim=1) - p * (np.log(10.0) + c)
+              - 0.5 * ltau ** 2 - c - 0.5 * lsig ** 2 - c)
+        grad = torch.empty_like(theta)
+        grad[:, :G * p] = ((res * inv_sig[:, None]) @ self.Xe) - (db * inv_tau[:, None, None]).reshape(S, G * p)
+        grad[:, G * p:G * p + p] = db.sum(dim=1) * inv_tau[:, None] - m / 100.0
+        grad[:, -2] = ssb - G * p - ltau
+        grad[:, -1] = ssr - N - lsig
+        return lp, grad
+
+
+class GaussianTarget(Model):
+    """Independent Gaussian target sum_j N(theta_j; mean_j, sd_j) (the reference tests' target,
+    tests/test_objectives.py:18-19) with its analytic gradient."""
+
+    def __init__(self, mean, sd):
+        self.mean, self.sd = to_dev(mean).reshape(-1), to_dev(sd).reshape(-1)
+        self.dim = int(self.mean.numel())
+        self._const = float(-(torch.log(self.sd).sum() + 0.5 * self.dim * np.log(2 * np.pi)))
+        super().__init__(lambda th: self.logp_and_grad(th)[0], lambda th: self.logp_and_grad(th)[1])
+
+    def logp_and_grad(self, theta):
+        z = (theta - self.mean) / self.sd
+        return -0.5 * (z * z).sum(dim=1) + self._const, -z / self.sd
+
+
+class StudentTTarget(Model):
+    """Product Student-t target sum_j t_df(theta_j; loc_j, scale_j)."""
+
+    def __init__(self, loc, scale, df):
+        import math
+        self.loc, self.scale, self.df = to_dev(loc).reshape(-1), to_dev(scale).reshape(-1), float(df)
+        self.dim = int(self.loc.numel())
+        df = self.df
+        self._const = self.dim * (math.lgamma(0.5 * (df + 1)) - math.lgamma(0.5 * df) - 0.5 * math.log(df * math.pi)) \
+            - float(torch.log(self.scale).sum())
+        super().__init__(lambda th: self.logp_and_grad(th)[0], lambda th: self.logp_and_grad(th)[1])
+
+    def logp_and_grad(self, theta):
+        df = self.df
+        z = (theta - self.loc) / self.scale
+        lp = -0.5 * (df + 1.0) * torch.log1p(z * z / df).sum(dim=1) + self._const
+        return lp, -(df + 1.0) * z / ((df + z * z) * self.scale)

@@ -98,7 +98,12 @@ def _mvt_objective(approx, model, S, objective, alpha, var_param, base=None, see
         Abar = -(zu.T @ G) / S
         diag_add = -1.0
     else:
-        lw = f - approx.log_density_device(vp, theta)
+        # log q at the sampled points: theta - mu = (z/u) A and A Sigma^-1 A = I, so the Mahalanobis term is
+        # |z/u|^2 exactly (no second eigen-decomposition); log det Sigma = 2 sum F_ii
+        import math
+        const = math.lgamma(0.5 * (df + d)) - math.lgamma(0.5 * df) - 0.5 * d * math.log(math.pi * df)
+        logq = const - torch.diagonal(F).sum() - 0.5 * (df + d) * torch.log1p((zu * zu).sum(dim=1) / df)
+        lw = f - logq
         m = lw.max()
         sv = torch.exp(lw - m) ** alpha
         value = torch.log(sv.mean()) / alpha + m
