@@ -358,3 +358,41 @@ def test_builtin_target_and_hier_plugins(vb, vo):
     v, gr = vb.ExclusiveKL(approx, model, 16)(vp, base=(chi2, z))
     v0, g0, _ = vo.exclusive_kl_mvt(vp, chi2, z, om, 100.0)
     assert relerr(v, v0) < 1e-9 and relerr(gr, g0) < 1e-8
+
+
+def test_dis_inclusive_kl(vb):
+    """DISInclusiveKL (objectives.py:280-416): score-function gradient at the fixed samples against
+    torch autograd, ESS bisection invariants, and the reference's convergence scenario
+    (tests/test_objectives.py:82-87)."""
+    mean = torch.tensor([1., -1.], dtype=torch.float64, device='cuda')
+    sd = torch.tensor([2., 5.], dtype=torch.float64, device='cuda')
+    target = vb.GaussianTarget(mean, sd)
+    for fam in (vb.MFGaussian(2), vb.MFStudentT(2, 100)):
+        obj = vb.DISInclusiveKL(fam, target, 200, ess_target=50, temper_prior=vb.MFGaussian(2),
+                                temper_prior_params=np.array([0., 0., 1., 1.]), use_resampling=False)
+        vp = torch.tensor([0.3, -0.2, 0.5, 1.2], dtype=torch.float64, device='cuda')
+        value, grad = obj(vp)
+        xs, w = obj._state_samples, obj._state_w
+        assert 0.0 <= obj._eps <= 1.0 and bool(torch.isfinite(w).all())
+        vpt = vp.clone().requires_grad_(True)
+        z = (xs - vpt[:2]) / torch.exp(vpt[2:])
+        if isinstance(fam, vb.MFGaussian):
+            logq = (-0.5 * z * z - vpt[2:] - 0.5 * np.log(2 * np.pi)).sum(dim=1)
+        else:
+            df = 100.0
+            c = math.lgamma(0.5 * (df + 1)) - math.lgamma(0.5 * df) - 0.5 * math.log(df * math.pi)
+            logq = (c - 0.5 * (df + 1) * torch.log1p(z * z / df) - vpt[2:]).sum(dim=1)
+        ref = -(w / 200 * logq).sum()
+        (gref,) = torch.autograd.grad(ref, vpt)
+        assert relerr(float(value), float(ref)) < 1e-12
+        assert relerr(grad.cpu().numpy(), gref.cpu().numpy()) < 1e-12
+    np.random.seed(851)
+    approx = vb.MFStudentT(2, 100)
+    obj = vb.DISInclusiveKL(approx, target, 100, ess_target=50, temper_prior=vb.MFGaussian(2),
+                            temper_prior_params=np.concatenate([[0] * 2, [1] * 2]))
+    opt = vb.RMSProp(0.1)
+    opt.progress = False
+    res = opt.optimize(1000, obj, np.array([0, 0, 1, 1], dtype=np.float32))
+    est_mean, est_cov = approx.mean_and_cov(res['opt_param'])
+    np.testing.assert_allclose(est_mean, [1., -1.], atol=0.5)
+    np.testing.assert_allclose(np.sqrt(np.diag(est_cov)), [2., 5.], rtol=0.25)

@@ -15,7 +15,8 @@ from ._tensor import F64, device, is_host, like_input, to_dev
 from .approximations import MultivariateT, _MeanField
 from .models import GLMModel, Model
 
-__all__ = ['VariationalObjective', 'StochasticVariationalObjective', 'ExclusiveKL', 'AlphaDivergence']
+__all__ = ['VariationalObjective', 'StochasticVariationalObjective', 'ExclusiveKL', 'AlphaDivergence',
+           'DISInclusiveKL']
 
 
 class VariationalObjective(ABC):
@@ -236,3 +237,114 @@ class AlphaDivergence(StochasticVariationalObjective):
         if base is None:
             return self._objective_and_grad(var_param)
         return self._objective_and_grad(var_param, base=base)
+
+
+class DISInclusiveKL(StochasticVariationalObjective):
+    """Inclusive KL by distilled importance sampling (objectives.py:280-416).
+
+    Forward-only in the model (no model gradient is ever needed): every `num_resampling_batches`-th
+    call draws S samples, evaluates log q and log p, finds the tempering epsilon by bisection on the
+    effective sample size, and then each call resamples from the tempered weights and differentiates
+    -log q(lambda; x) at the FIXED samples (score terms).  Mean-field families only here."""
+
+    def __init__(self, approx, model, num_mc_samples, ess_target, temper_prior, temper_prior_params,
+                 use_resampling=True, num_resampling_batches=1, w_clip_threshold=10):
+        self._ess_target = ess_target
+        self._w_clip_threshold = w_clip_threshold
+        self._max_bisection_its = 50
+        self._max_eps = self._eps = 1
+        self._use_resampling = use_resampling
+        self._num_resampling_batches = num_resampling_batches
+        self._resampling_batch_size = max(1, self._ess_target // num_resampling_batches)
+        self._objective_step = 0
+        self._temper_prior = temper_prior
+        self._temper_prior_params = temper_prior_params
+        super().__init__(approx, model, num_mc_samples)
+
+    # -- weights / ESS / bisection (objectives.py:317-366); S-vectors on the device ------------------
+    def _get_weights(self, eps, log_prior, log_p, log_q):
+        logw = eps * log_prior + (1 - eps) * log_p - log_q
+        if bool(logw.max() == -float('inf')):
+            raise ValueError('All weights zero! ' + 'Suggests overflow in importance density.')
+        return torch.exp(logw)                     # not max-shifted, as the reference (:330)
+
+    @staticmethod
+    def _get_ess(w):
+        return float((w.sum() ** 2.0) / (w ** 2.0).sum())
+
+    def _get_eps_and_weights(self, eps_guess, log_prior, log_p, log_q):
+        lower, upper = 0., eps_guess
+        eps_guess = (lower + upper) / 2.
+        for _ in range(self._max_bisection_its):
+            w = self._get_weights(eps_guess, log_prior, log_p, log_q)
+            if self._get_ess(w) > self._ess_target:
+                upper = eps_guess
+            else:
+                lower = eps_guess
+            eps_guess = (lower + upper) / 2.
+        w = self._get_weights(eps_guess, log_prior, log_p, log_q)
+        ess = self._get_ess(w)
+        if lower == 0.:
+            eps_guess = 0.
+        if upper == self._max_eps:
+            eps_guess = self._max_eps
+        return eps_guess, ess, w
+
+    def _score_terms(self, vp, x):
+        """-log q(lambda; x) summed with weights needs d(log q)/d[mu, log sigma] at fixed x."""
+        approx = self.approx
+        d = approx.dim
+        mu, ls = vp[:d], vp[d:]
+        sig = torch.exp(ls)
+        z = (x - mu) / sig
+        if approx._family == _lib.FAMILY_MF_GAUSSIAN:
+            dmu = z / sig                       # d log q / d mu
+            dls = z * z - 1.0                   # d log q / d log sigma
+        else:
+            df = float(approx.df)
+            q = (df + 1.0) / (df + z * z)
+            dmu = q * z / sig
+            dls = q * z * z - 1.0
+        return dmu, dls
+
+    def _update_objective_and_grad(self):
+        approx = self.approx
+        if approx is not None and not isinstance(approx, _MeanField):
+            def unsupported(var_param):
+                raise NotImplementedError('DISInclusiveKL is implemented for mean-field families')
+            self._objective_and_grad = unsupported
+            return
+
+        def objective_and_grad(var_param):
+            host = is_host(var_param)
+            vp = to_dev(var_param)
+            S = self.num_mc_samples
+            if not self._use_resampling or self._objective_step % self._num_resampling_batches == 0:
+                x = approx.sample(vp, S)
+                self._state_samples = x
+                self._state_log_q = approx.log_density(vp, x)
+                self._state_log_p = self.model(x)
+                log_prior = self._temper_prior.log_density(to_dev(self._temper_prior_params), x)
+                self._eps, ess, w = self._get_eps_and_weights(self._eps, log_prior, self._state_log_p,
+                                                              self._state_log_q)
+                self._state_w = w                       # clipping (:368-386) is unreachable at threshold 10
+                self._state_w_sum = w.sum()
+                self._state_w_normalized = w / self._state_w_sum
+            self._objective_step += 1
+            if not self._use_resampling:
+                xs, wts = self._state_samples, self._state_w / S
+                value = -(wts * approx.log_density(vp, xs)).sum()
+            else:
+                p = self._state_w_normalized.cpu().numpy()
+                idx = np.random.choice(S, size=self._resampling_batch_size, p=p / p.sum())   # global RNG (:408)
+                xs = self._state_samples[torch.as_tensor(idx, device=vp.device)]
+                scale = self._state_w_sum / S / xs.shape[0]
+                wts = scale.expand(xs.shape[0])
+                value = -(wts * approx.log_density(vp, xs)).sum()
+            dmu, dls = self._score_terms(vp, xs)
+            grad = -torch.cat([(wts[:, None] * dmu).sum(dim=0), (wts[:, None] * dls).sum(dim=0)])
+            if host:
+                return float(value), grad.cpu().numpy()
+            return value, grad
+
+        self._objective_and_grad = objective_and_grad
