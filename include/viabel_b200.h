@@ -173,6 +173,36 @@ int64_t vb_psis_tail_capacity(int64_t n, double reff);
 int vb_psislw_f64(const double* lw, double* out, int64_t n, double reff, int exact, double* result,
                   int64_t* tail_idx, int32_t* tail_rank, void* workspace, size_t workspace_bytes,
                   cudaStream_t stream);
+
+/* Draw-sharded PSIS: the n_global log-weights of ONE column are split over `world`
+ * ranks, rank r holding n_local consecutive draws starting at global index idx_off.  Same
+ * algorithm and results as vb_psislw_f64 (= viabel/_psis.py:113-209), in three stream-ordered
+ * stages with ONE fixed-size exchange between the first two (host side: NCCL all-gather); no
+ * host synchronisation is needed until result[] is read.
+ *   vb_psis_dist_local : threshold + pass A over the local draws, local cutoff, then the rank's
+ *                        RECORD (device, vb_psis_dist_record_doubles doubles): [local max, c_r =
+ *                        local (M+1)-th largest, log-sum-exp of the draws not in the record,
+ *                        count], the rank's top M+1 values (local tail padded with copies of c_r)
+ *                        and their GLOBAL indices (int64 bit patterns; -1 for the padding).
+ *   vb_psis_dist_global: replicated on every rank, on the `world` records concatenated in rank
+ *                        order: global cutoff = (M+1)-th largest of the union, tail ranking, GPD
+ *                        fit, smoothed tail, log-sum-exp.  result[] as for vb_psislw_f64
+ *                        (status 1 if ANY rank's sampled threshold missed: rerun with exact=1).
+ *   vb_psis_dist_apply : pass B over the local draws + scatter of the smoothed tail entries this
+ *                        rank owns; result[7], result[8] are this rank's SHARE of the moments
+ *                        (sum over ranks = the global moments; rank 0 carries the tail's part).
+ * All three take the same workspace (vb_psis_dist_workspace_bytes), which carries the state. */
+size_t vb_psis_dist_workspace_bytes(int64_t n_local, int64_t n_global, double reff, int world);
+int64_t vb_psis_dist_record_doubles(int64_t n_global, double reff);
+int vb_psis_dist_local(const double* lw, int64_t n_local, int64_t idx_off, int64_t n_global, double reff,
+                       int world, int exact, double* record, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream);
+int vb_psis_dist_global(const double* records, int64_t n_local, int64_t n_global, double reff, int world,
+                        double* result, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int vb_psis_dist_apply(const double* lw, double* out, int64_t n_local, int64_t idx_off, int64_t n_global,
+                       double reff, int world, int rank, double* result, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream);
+
 /* out4[0] = max(lw), out4[1] = sum exp(lw - max)^alpha, out4[2] = sum lw  (out4[3] is scratch) */
 int vb_divergence_moments_f64(const double* lw, int64_t n, double alpha, double* out4,
                               cudaStream_t stream);

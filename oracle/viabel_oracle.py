@@ -554,6 +554,77 @@ def psislw_1d(lw, Reff=1.0, return_tail=False):
     return x, k
 
 
+def psis_shard_record(x_local, idx_off, M):
+    """Draw-sharded restatement of _psis.py:163-203, stage 1 (csrc/psis.cu
+    psis_export_kernel): what one rank ships.  [local max, c_r, log-sum-exp (relative to the local
+    max) of the draws not represented, count], the rank's top M+1 values -- values above its
+    (M+1)-th largest c_r, padded with copies of c_r -- and their global indices (-1 = padding)."""
+    x = np.asarray(x_local, dtype=np.float64)
+    K = M + 1
+    vals, idx = np.full(K, -np.inf), np.full(K, -1, dtype=np.int64)
+    mx = x.max()
+    if x.size < K:
+        vals[:x.size], idx[:x.size] = x, idx_off + np.arange(x.size)
+        return np.array([mx, -np.inf, -np.inf, x.size]), vals, idx
+    c = np.partition(x, x.size - K)[x.size - K]
+    tail = np.flatnonzero((x > c) & (x - mx > math.log(np.finfo(float).tiny)))
+    vals[:tail.size], idx[:tail.size] = x[tail], idx_off + tail
+    vals[tail.size:] = c
+    rest = np.ones(x.size, dtype=bool)
+    rest[tail] = False
+    body = np.exp(x[rest] - mx).sum() - (K - tail.size) * math.exp(c - mx)
+    return np.array([mx, c, math.log(body) if body > 0 else -np.inf, K]), vals, idx
+
+
+def psis_merge_records(records, M, n_global):
+    """Stage 2 of the sharded restatement: from every rank's record, the global maximum, the
+    shifted cutoff (_psis.py:170-173), the tail (global indices, shifted values) and the
+    log-sum-exp of everything that is not in the tail (relative to the global maximum)."""
+    heads = np.stack([r[0] for r in records])
+    vals = np.concatenate([r[1][:int(r[0][3])] for r in records])
+    idx = np.concatenate([r[2][:int(r[0][3])] for r in records])
+    mx = heads[:, 0].max()
+    c = np.partition(vals, vals.size - (M + 1))[vals.size - (M + 1)]          # (M+1)-th largest of the union
+    cutoff = max(c - mx, math.log(np.finfo(float).tiny))
+    v = vals - mx
+    in_tail = v > cutoff
+    body = np.exp(v[~in_tail]).sum()
+    for h in heads:
+        if h[2] > -np.inf:
+            body += math.exp(h[2] + h[0] - mx)
+    return mx, cutoff, idx[in_tail], v[in_tail], body
+
+
+def psislw_sharded(parts, Reff=1.0):
+    """_psis.py:163-203 on the concatenation of `parts`, computed the draw-sharded way; returns
+    the list of smoothed, normalised parts and k-hat.  Must equal psislw_1d(np.concatenate(parts))."""
+    sizes = [len(p) for p in parts]
+    n = sum(sizes)
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    M = psis_tail_len(n, Reff)
+    recs = [psis_shard_record(p, offs[r], M) for r, p in enumerate(parts)]
+    mx, cutoff, tidx, tv, body = psis_merge_records(recs, M, n)
+    expcut = math.exp(cutoff)
+    order = np.lexsort((tidx, tv))
+    tidx, tv = tidx[order], tv[order]
+    n2 = tv.size
+    k = np.inf
+    smoothed = None
+    if n2 > 4:
+        k, sigma = gpdfit(np.exp(tv) - expcut)
+        if k >= 1.0 / 3.0 and not np.isinf(k):
+            smoothed = np.minimum(np.log(gpinv((np.arange(n2) + 0.5) / n2, k, sigma) + expcut), 0.0)
+    tail_out = smoothed if smoothed is not None else tv
+    lse = math.log(body + np.exp(tail_out).sum())
+    outs = []
+    for r, p in enumerate(parts):
+        o = np.asarray(p, dtype=np.float64) - mx
+        mine = (tidx >= offs[r]) & (tidx < offs[r + 1])
+        o[tidx[mine] - offs[r]] = tail_out[mine]
+        outs.append(o - lse)
+    return outs, k
+
+
 def psislw(lw, Reff=1.0):
     """_psis.py:113-209 for 1-D or [n,m] input (each column separately)."""
     lw = np.asarray(lw, dtype=np.float64)

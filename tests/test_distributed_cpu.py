@@ -70,6 +70,27 @@ def _worker(rank, world, port, ret):
         expect = torch.cat([torch.arange(3 + 2 * r, dtype=torch.float64) + 100 * r for r in range(world)])
         ok = ok and torch.equal(allc, expect)
         ok = ok and parallel.world() == (rank, world) and parallel.is_distributed()
+
+        # draw-sharded PSIS exchange: fixed-size records (values + int64 indices as bit patterns)
+        # all-gathered in rank order, merged, compared with the one-column algorithm
+        from _problems import psis_case
+        lw = psis_case('t5_t7_1e5')
+        n = lw.size
+        lo, hi = parallel.shard_rows(n, rank, world)
+        Mt = vo.psis_tail_len(n, 1.0)
+        head, vals, idx = vo.psis_shard_record(lw[lo:hi], lo, Mt)
+        rec = torch.from_numpy(np.concatenate([head, vals, idx.view(np.float64)]))
+        bufs = [torch.empty_like(rec) for _ in range(world)]
+        dist.all_gather(bufs, rec)
+        recs = []
+        for b in bufs:
+            b = b.numpy()
+            recs.append((b[:4], b[4:4 + Mt + 1], b[4 + Mt + 1:].view(np.int64)))
+        mx, cutoff, tidx, tv, body = vo.psis_merge_records(recs, Mt, n)
+        x = lw - lw.max()
+        xcut = max(np.partition(x, n - Mt - 1)[n - Mt - 1], np.log(np.finfo(float).tiny))
+        ok = ok and mx == lw.max() and cutoff == xcut and np.array_equal(np.sort(tidx), np.flatnonzero(x > xcut))
+        ok = ok and abs(body - np.exp(x[x <= xcut]).sum()) < 1e-12 * body
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

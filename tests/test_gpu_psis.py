@@ -242,3 +242,79 @@ def test_bbvi_and_vi_diagnostics_scenarios(vb):
         vb.vi_diagnostics(vp, approx=approx)
     with pytest.raises(ValueError):
         vb.vi_diagnostics(vp, model=vb.Model(std_normal(1.0)), approx=approx, n_samples=0)
+
+
+# ---- draw-sharded PSIS: shards driven in one process, exchange done by hand ------------
+def _sharded(vb, lw, cuts, exact=False):
+    from viabel_b200._psis import PsisShard
+    x = torch.as_tensor(lw, dtype=torch.float64, device='cuda')
+    n, world = x.numel(), len(cuts) - 1
+    shards = [PsisShard(x[cuts[r]:cuts[r + 1]].contiguous(), cuts[r], n, 1.0, world, r) for r in range(world)]
+    recs = torch.cat([s.local(exact) for s in shards])           # what the all-gather would deliver
+    outs, res, mom = [], None, np.zeros(2)
+    for s in shards:
+        s.global_(recs)
+        o = torch.empty_like(s.lw)
+        rr = s.apply(o).cpu().numpy()
+        assert rr[6] == 0
+        mom += rr[7:9]
+        outs.append(o)
+        if res is None:
+            res = rr
+        else:
+            assert np.array_equal(rr[:7], res[:7]) and np.array_equal(rr[9:12], res[9:12])    # replicated stage
+    return torch.cat(outs).cpu().numpy(), res, mom
+
+
+@pytest.mark.parametrize('name,cuts', [('t5_t7_1e5', [0, 50000, 100000]), ('t5_t7_1e5', [0, 1000, 61234, 100000]),
+                                       ('t3_t30_2e5', [0, 66667, 200000]), ('ties_3e4', [0, 15000, 30000]),
+                                       ('small_100', [0, 40, 100]), ('small_100', [0, 10, 22, 100]),
+                                       ('underflow_5000', [0, 2500, 5000]), ('all_equal_50', [0, 20, 50]),
+                                       ('big_1e6', [0, 250000, 500000, 750000, 1000000])])
+@pytest.mark.parametrize('exact', [False, True])
+def test_psislw_sharded_matches_single(vb, name, cuts, exact):
+    lw = psis_case(name)
+    from viabel_b200._psis import psislw_device
+    x = torch.as_tensor(lw, dtype=torch.float64, device='cuda')
+    o1 = torch.empty_like(x)
+    _, r1, _, _ = psislw_device(x, o1, 1.0, exact=exact)
+    r1 = r1.cpu().numpy()
+    assert r1[6] == 0
+    out, res, mom = _sharded(vb, lw, cuts, exact)
+    assert res[0] == r1[0] and res[1] == r1[1] and res[2] == r1[2] and res[3] == r1[3]      # k-hat, sigma, n2, cutoff
+    assert abs(res[4] - r1[4]) < 1e-12 and res[5] == r1[5]
+    np.testing.assert_allclose(out, o1.cpu().numpy(), rtol=0, atol=1e-11)
+    np.testing.assert_allclose(mom, r1[7:9], rtol=1e-11)
+
+
+def test_psislw_exact_mode_all_equal(vb):
+    """Exact mode, no value strictly above the cutoff: the maximum is the cutoff itself."""
+    from viabel_b200._psis import psislw_device
+    x = torch.full((50,), -3.25, dtype=torch.float64, device='cuda')
+    o = torch.empty_like(x)
+    _, r, _, _ = psislw_device(x, o, 1.0, exact=True)
+    r = r.cpu().numpy()
+    assert r[6] == 0 and np.isinf(r[0]) and r[5] == -3.25
+    np.testing.assert_allclose(o.cpu().numpy(), -np.log(50.0), rtol=1e-14)
+
+
+def test_psislw_sharded_uneven_tail_owner(vb):
+    """All of the global tail lives on one shard; the other shard's draws are all below the cutoff."""
+    rng = np.random.default_rng(5)
+    lo = rng.standard_normal(40000) - 50.0
+    hi = rng.standard_t(3, 60000) * 2.0
+    lw = np.concatenate([lo, hi])
+    out1, k1 = vb.psislw(lw)
+    out, res, _ = _sharded(vb, lw, [0, 40000, 100000])
+    assert res[0] == k1
+    np.testing.assert_allclose(out, out1, rtol=0, atol=1e-11)
+
+
+def test_psislw_sharded_api_single_process(vb):
+    """psislw_sharded without a process group = psislw."""
+    lw = psis_case(PSIS_CASES[0])
+    lw = lw if lw.ndim == 1 else lw[:, 0].copy()
+    out1, k1 = vb.psislw(lw)
+    out, k, res = vb.psislw_sharded(torch.as_tensor(lw, device='cuda'))
+    assert k == k1
+    np.testing.assert_allclose(out.cpu().numpy(), out1, rtol=0, atol=1e-12)

@@ -231,3 +231,16 @@ def test_vi_diagnostics_pipeline(golden):
                                  q_var=vo.mfg_mean_and_cov(vp, 4)[1])
         for key in ('W1', 'W2', 'mean_error', 'std_error', 'cov_error', 'd2', 'log_norm_bound'):
             assert relerr(res[key], g['vi_%s/%s' % (name, key)]) < 1e-9, (name, key)
+
+
+@pytest.mark.parametrize('name,cuts', [('t5_t7_1e5', [0, 50000, 100000]), ('t5_t7_1e5', [0, 700, 61234, 100000]),
+                                       ('small_100', [0, 10, 22, 100]), ('ties_3e4', [0, 15000, 30000]),
+                                       ('underflow_5000', [0, 2500, 5000]), ('all_equal_50', [0, 20, 50])])
+def test_sharded_psis_rule_equals_single(name, cuts):
+    """The record rule of the draw-sharded PSIS (each rank ships its top M+1; csrc/psis.cu) gives
+    the same smoothed weights and k-hat as the one-column algorithm pinned against _psis.py."""
+    lw = psis_case(name)
+    ref, kref = vo.psislw_1d(lw)
+    outs, k = vo.psislw_sharded([lw[cuts[i]:cuts[i + 1]] for i in range(len(cuts) - 1)])
+    assert (np.isinf(k) and np.isinf(kref)) or k == kref
+    np.testing.assert_allclose(np.concatenate(outs), ref, rtol=0, atol=1e-11)

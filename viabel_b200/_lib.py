@@ -52,6 +52,11 @@ _PROTOS = {
     'vb_psis_workspace_bytes': (c_size_t, [c_int64, c_double]),
     'vb_psis_tail_capacity': (c_int64, [c_int64, c_double]),
     'vb_psislw_f64': (c_int, [P, P, c_int64, c_double, c_int, P, P, P, P, c_size_t, P]),
+    'vb_psis_dist_workspace_bytes': (c_size_t, [c_int64, c_int64, c_double, c_int]),
+    'vb_psis_dist_record_doubles': (c_int64, [c_int64, c_double]),
+    'vb_psis_dist_local': (c_int, [P, c_int64, c_int64, c_int64, c_double, c_int, c_int, P, P, c_size_t, P]),
+    'vb_psis_dist_global': (c_int, [P, c_int64, c_int64, c_double, c_int, P, P, c_size_t, P]),
+    'vb_psis_dist_apply': (c_int, [P, P, c_int64, c_int64, c_int64, c_double, c_int, c_int, P, P, c_size_t, P]),
     'vb_divergence_moments_f64': (c_int, [P, c_int64, c_double, P, P]),
 }
 

@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from ._tensor import F64, device, is_host, to_dev
 
-__all__ = ['psislw', 'psislw_device', 'gpdfitnew', 'gpinv', 'sumlogs']
+__all__ = ['psislw', 'psislw_device', 'psislw_sharded', 'PsisShard', 'gpdfitnew', 'gpinv', 'sumlogs']
 
 R_KHAT, R_SIGMA, R_N2, R_CUTOFF, R_LSE, R_MAX, R_STATUS, R_SUMV, R_SUMEXP2V, R_M, R_NCAND, R_SMOOTHED = range(12)
 
@@ -122,6 +122,94 @@ def psislw(lw, Reff=1.0, overwrite_lw=False, return_tail=False):
         lw.copy_(out)
         out = lw
     return out, kss
+
+
+class PsisShard:
+    """One rank's part of a draw-sharded PSIS: `lw` holds the n_local consecutive
+    draws starting at global index `idx_off` out of n_global.  The three stages mirror
+    vb_psis_dist_local / _global / _apply; the exchange between the first two (an all-gather of
+    the fixed-size records) is the caller's -- see `psislw_sharded`.  Kept as an object so that a
+    test can drive several shards inside one process."""
+
+    def __init__(self, lw, idx_off, n_global, Reff=1.0, world=1, rank=0):
+        if lw.dim() != 1 or lw.dtype != F64 or not lw.is_cuda or not lw.is_contiguous():
+            raise ValueError('PsisShard needs a contiguous 1-D CUDA float64 tensor')
+        if lw.numel() <= 1:
+            raise ValueError("More than one log-weight needed.")
+        self.lw, self.idx_off, self.n_global = lw, int(idx_off), int(n_global)
+        self.reff, self.world, self.rank = float(Reff), int(world), int(rank)
+        nbytes = _lib.lib.vb_psis_dist_workspace_bytes(lw.numel(), self.n_global, self.reff, self.world)
+        self.reclen = _lib.lib.vb_psis_dist_record_doubles(self.n_global, self.reff)
+        if nbytes == 0 or self.reclen == 0:
+            raise ValueError('invalid shard sizes')
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=lw.device)
+        self.record = torch.empty(self.reclen, dtype=F64, device=lw.device)
+        self.result = torch.empty(16, dtype=F64, device=lw.device)
+
+    def local(self, exact=False):
+        """Stage 1 -> this rank's record (device tensor of `reclen` doubles)."""
+        _lib.check(_lib.lib.vb_psis_dist_local(
+            _lib.ptr(self.lw), self.lw.numel(), self.idx_off, self.n_global, self.reff, self.world, int(exact),
+            _lib.ptr(self.record), _lib.ptr(self.ws), self.ws.numel(), _lib.stream()))
+        return self.record
+
+    def global_(self, records):
+        """Stage 2 on the records of all ranks ([world * reclen] doubles, rank order)."""
+        if records.numel() != self.world * self.reclen or records.dtype != F64 or not records.is_contiguous():
+            raise ValueError('records must be world x reclen contiguous float64')
+        _lib.check(_lib.lib.vb_psis_dist_global(
+            _lib.ptr(records), self.lw.numel(), self.n_global, self.reff, self.world, _lib.ptr(self.result),
+            _lib.ptr(self.ws), self.ws.numel(), _lib.stream()))
+        return self.result
+
+    def apply(self, out):
+        """Stage 3: writes this rank's smoothed, normalised log-weights (out may be None or lw);
+        result slots 7 and 8 hold this rank's share of the moments."""
+        _lib.check(_lib.lib.vb_psis_dist_apply(
+            _lib.ptr(self.lw), _lib.ptr(out), self.lw.numel(), self.idx_off, self.n_global, self.reff, self.world,
+            self.rank, _lib.ptr(self.result), _lib.ptr(self.ws), self.ws.numel(), _lib.stream()))
+        return self.result
+
+
+def psislw_sharded(lw_local, Reff=1.0, out=None, group=None, want_out=True, sizes=None):
+    """PSIS of ONE column of log-weights whose draws are sharded over the ranks of `group`
+    (rank r holds consecutive draws; sizes may differ).  Same result as `psislw` on the
+    concatenation (_psis.py:113-209): every rank runs pass A and a local cutoff on its draws, the
+    ranks all-gather their top-(M+1) records (16 (M+1) bytes each), the global cutoff / GPD fit /
+    log-sum-exp run replicated, and pass B writes each rank's part.  `sizes` (per-rank draw
+    counts) saves the one host round trip that discovers them.
+
+    Returns (out_local, khat, result) with result the 16-slot host vector of include/viabel_b200.h,
+    its moments (slots 7, 8) summed over ranks."""
+    import torch.distributed as dist
+    from . import parallel
+    rank, ws = parallel.world(group)
+    lw_local = lw_local.to(F64).contiguous()
+    if sizes is None:
+        sz = torch.zeros(ws, dtype=torch.int64, device=lw_local.device)
+        sz[rank] = lw_local.numel()
+        sizes = parallel.allreduce_sum_(sz, group).cpu().tolist()
+    if len(sizes) != ws or sizes[rank] != lw_local.numel():
+        raise ValueError('sizes does not match the process group / local shard')
+    shard = PsisShard(lw_local, sum(sizes[:rank]), sum(sizes), Reff, ws, rank)
+    if out is None and want_out:
+        out = torch.empty_like(lw_local)
+    for exact in (False, True):
+        rec = shard.local(exact)
+        if ws > 1:
+            recs = torch.empty(ws * shard.reclen, dtype=F64, device=rec.device)
+            dist.all_gather_into_tensor(recs, rec, group=group)
+        else:
+            recs = rec
+        shard.global_(recs)
+        result = shard.apply(out)
+        parallel.allreduce_sum_(result[R_SUMV:R_SUMEXP2V + 1], group)
+        res = result.cpu().numpy()               # the only host sync; status is identical on every rank
+        if res[R_STATUS] == 0:
+            return out, float(res[R_KHAT]), res
+        if res[R_STATUS] != 1:
+            break
+    raise RuntimeError('viabel_b200: PSIS failed with status %d' % int(res[R_STATUS]))
 
 
 def gpinv(p, k, sigma):

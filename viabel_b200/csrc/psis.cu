@@ -253,9 +253,10 @@ __global__ void __launch_bounds__(kSelThreads) psis_sample_select_kernel(const d
 // memory and flushed with ONE global atomic per CTA (same-address atomics with a return value
 // serialise at ~2 ns each in L2: one per candidate-bearing warp iteration cost more than the HBM pass).
 constexpr int kStage = 160;     // per-warp staging entries (>= 4 * 32)
-__global__ void __launch_bounds__(256) psis_pass_a_kernel(const double* __restrict__ lw, int64_t n, PsisScalars* sc,
-                                                          double* __restrict__ cand_x, int64_t* __restrict__ cand_i,
-                                                          unsigned int cap, double* __restrict__ blk_sum) {
+__global__ void __launch_bounds__(256) psis_pass_a_kernel(const double* __restrict__ lw, int64_t n, int64_t idx_off,
+                                                          PsisScalars* sc, double* __restrict__ cand_x,
+                                                          int64_t* __restrict__ cand_i, unsigned int cap,
+                                                          double* __restrict__ blk_sum) {
   __shared__ double red[32];
   __shared__ unsigned long long redk[32];
   __shared__ double etab_s[32];
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(256) psis_pass_a_kernel(const double* __restri
         mx = fmax(mx, x);
         const unsigned int slot = staged + __popc(ball & ((1u << lane) - 1));
         sx[w][slot] = x;
-        si[w][slot] = i;
+        si[w][slot] = i + idx_off;      // global draw index (idx_off = this rank's first draw)
       }
       staged += __popc(ball);
     }
@@ -463,7 +464,9 @@ __global__ void __launch_bounds__(kSelThreads) psis_cutoff_kernel(PsisScalars* s
   double s = 0.0;
   for (int b = threadIdx.x; b < nblk; b += blockDim.x) s += blk_sum[b];
   s = block_sum(s, red);
-  const double maxv = dkey_inv(sc->maxkey);
+  // exact mode collects only values strictly above t0: when there are none the maximum is t0 itself
+  const unsigned long long maxkey = (sc->strict && sc->maxkey < sc->t0key) ? sc->t0key : sc->maxkey;
+  const double maxv = dkey_inv(maxkey);
   unsigned long long cutkey;
   if (sc->strict) {
     cutkey = sc->t0key;                        // exact mode: t0 IS the (M+1)-th largest value
@@ -513,6 +516,7 @@ __global__ void __launch_bounds__(kSelThreads) psis_cutoff_kernel(PsisScalars* s
     const double cutraw = dkey_inv(cutkey);
     const double cutoff = fmax(cutraw - maxv, log(DBL_MIN));       // _psis.py:159, :170-173
     sc->cutkey = cutkey;
+    sc->maxkey = maxkey;
     sc->maxv = maxv;
     sc->cutoff = cutoff;
     sc->expcut = exp(cutoff);
@@ -592,7 +596,7 @@ __global__ void __launch_bounds__(256) psis_tail_place_kernel(PsisScalars* sc, c
                                                               const unsigned int* __restrict__ voff,
                                                               unsigned int* __restrict__ vcur, double* __restrict__ tmp_v,
                                                               int64_t* __restrict__ tmp_i, int* __restrict__ tmp_b,
-                                                              unsigned int tail_cap) {
+                                                              unsigned int tail_cap, int raw) {
   if (sc->status) return;
   const unsigned int C = sc->ncand;
   const double maxv = sc->maxv, cutoff = sc->cutoff, vscale = sc->vscale;
@@ -602,7 +606,7 @@ __global__ void __launch_bounds__(256) psis_tail_place_kernel(PsisScalars* sc, c
       const int b = vbin(v, cutoff, vscale);
       const unsigned int pos = voff[b] + atomicAdd(&vcur[b], 1u);
       if (pos < tail_cap) {
-        tmp_v[pos] = v;
+        tmp_v[pos] = raw ? cand_x[i] : v;          // raw: a sharded rank ships unshifted values
         tmp_i[pos] = cand_i[i];
         tmp_b[pos] = b;
       }
@@ -932,18 +936,20 @@ __global__ void __launch_bounds__(256) psis_pass_b_moments_kernel(const double* 
 }
 
 // smoothed tail values into place (_psis.py:190-199) and final moment reduction
-__global__ void __launch_bounds__(256) psis_tail_scatter_kernel(double* __restrict__ out, PsisScalars* sc,
-                                                                const int64_t* __restrict__ tail_i,
+__global__ void __launch_bounds__(256) psis_tail_scatter_kernel(double* __restrict__ out, int64_t n, int64_t idx_off,
+                                                                PsisScalars* sc, const int64_t* __restrict__ tail_i,
                                                                 const double* __restrict__ tail_out,
                                                                 const double* __restrict__ blk_mom, int nblk,
-                                                                double* __restrict__ result) {
+                                                                int add_tail, double* __restrict__ result) {
   __shared__ double red[32];
   if (sc->status) return;
   const int N = (int)sc->ntail;
   const double lse = sc->lse;
   if (out && sc->smoothed) {
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x)
-      out[tail_i[r]] = tail_out[r] - lse;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x) {
+      const int64_t li = tail_i[r] - idx_off;             // draws of other ranks are theirs to write
+      if (li >= 0 && li < n) out[li] = tail_out[r] - lse;
+    }
   }
   if (blockIdx.x == 0) {
     double sv = 0.0, se = 0.0;
@@ -954,8 +960,8 @@ __global__ void __launch_bounds__(256) psis_tail_scatter_kernel(double* __restri
     sv = block_sum(sv, red);
     se = block_sum(se, red);
     if (threadIdx.x == 0) {
-      result[R_SUMV] = sv + sc->sumv;
-      result[R_SUMEXP2V] = se + sc->sumexp2v;
+      result[R_SUMV] = sv + (add_tail ? sc->sumv : 0.0);           // sharded: rank 0 alone carries the tail's share
+      result[R_SUMEXP2V] = se + (add_tail ? sc->sumexp2v : 0.0);
     }
   }
 }
@@ -1042,27 +1048,32 @@ __global__ void __launch_bounds__(256) dbound_sum_kernel(const double* __restric
 // ---------------------------------------------------------------------------------------------
 struct PsisPlan {
   int M, m_sample, grid, tail_cap, mgrid, kparts, vparts;
-  unsigned int cap, R;
+  unsigned int cap, cap_local, R;
   int64_t stride;
   size_t off_sc, off_candx, off_candi, off_blk, off_tmpv, off_tmpi, off_tmpb, off_tailv, off_taili, off_tailout,
       off_sorted, off_idxsorted, off_orderrank, off_bs, off_part, off_Ls, off_kpart, off_part3, off_mom, off_ghist,
       off_vhist, off_voff, off_gbuf, total;
 };
 
-static void psis_plan(int64_t n, double reff, PsisPlan& p) {
-  p.M = (int)ceil(fmin(0.2 * (double)n, 3.0 * sqrt((double)n / reff)));     // _psis.py:158
+static void psis_plan(int64_t n, double reff, PsisPlan& p, int64_t n_global = 0, int world = 1) {
+  if (n_global <= 0) n_global = n;
+  // tail length from the GLOBAL number of draws (_psis.py:158); a rank may own all of the tail
+  p.M = (int)ceil(fmin(0.2 * (double)n_global, 3.0 * sqrt((double)n_global / reff)));
   if (p.M < 0) p.M = 0;
   p.m_sample = (int)(n < kSampleMax ? n : kSampleMax);
   p.stride = n / p.m_sample;
   const double f = (double)(p.M + 1) * (double)p.m_sample / (double)n;      // expected sample hits above the cutoff
   double R = ceil(f + 8.0 * sqrt(f) + 16.0);
   if (p.m_sample == n) R = p.M + 1;                                          // sample is everything: exact
+  if (R > (double)n) R = (double)n;
   p.R = (unsigned int)fmin(R, 4.0e9);
   double expect = (double)p.R * (double)n / (double)p.m_sample;
   double cap = 4.0 * expect + 65536.0;
   if (cap > (double)n) cap = (double)n;
-  if (cap < (double)(p.M + 1)) cap = (double)(p.M + 1);
-  p.cap = (unsigned int)cap;
+  if (cap < (double)(p.M + 1) && (double)(p.M + 1) <= (double)n) cap = (double)(p.M + 1);
+  p.cap_local = (unsigned int)cap;
+  // sharded: the same buffer later holds every rank's top (M+1) (see vb_psis_dist_global)
+  p.cap = (unsigned int)fmin(fmax(cap, world > 1 ? (double)world * (p.M + 1) : 0.0), 4.0e9);
   p.tail_cap = p.M + 1;
   p.grid = sm_count() * 8;
   const int64_t need = (n / 4 + 255) / 256;
@@ -1125,6 +1136,221 @@ extern "C" int64_t vb_psis_tail_capacity(int64_t n, double reff) {
   return p.tail_cap;
 }
 
+namespace vb {
+struct PsisPtrs {
+  PsisScalars* sc;
+  double *candx, *blk, *tmpv, *tailv, *tailout, *sorted, *bs, *part, *Ls, *kpart, *part3, *mom;
+  int64_t *candi, *tmpi, *taili, *idxsorted;
+  int *tmpb, *orderrank;
+  unsigned int *ghist, *vhist, *vcur, *voff;
+  unsigned long long* gbuf;
+};
+static void psis_ptrs(char* ws, const PsisPlan& p, PsisPtrs& q) {
+  q.sc = reinterpret_cast<PsisScalars*>(ws + p.off_sc);
+  q.candx = reinterpret_cast<double*>(ws + p.off_candx);
+  q.candi = reinterpret_cast<int64_t*>(ws + p.off_candi);
+  q.blk = reinterpret_cast<double*>(ws + p.off_blk);
+  q.tmpv = reinterpret_cast<double*>(ws + p.off_tmpv);
+  q.tmpi = reinterpret_cast<int64_t*>(ws + p.off_tmpi);
+  q.tmpb = reinterpret_cast<int*>(ws + p.off_tmpb);
+  q.tailv = reinterpret_cast<double*>(ws + p.off_tailv);
+  q.taili = reinterpret_cast<int64_t*>(ws + p.off_taili);
+  q.tailout = reinterpret_cast<double*>(ws + p.off_tailout);
+  q.sorted = reinterpret_cast<double*>(ws + p.off_sorted);
+  q.idxsorted = reinterpret_cast<int64_t*>(ws + p.off_idxsorted);
+  q.orderrank = reinterpret_cast<int*>(ws + p.off_orderrank);
+  q.bs = reinterpret_cast<double*>(ws + p.off_bs);
+  q.part = reinterpret_cast<double*>(ws + p.off_part);
+  q.Ls = reinterpret_cast<double*>(ws + p.off_Ls);
+  q.kpart = reinterpret_cast<double*>(ws + p.off_kpart);
+  q.part3 = reinterpret_cast<double*>(ws + p.off_part3);
+  q.mom = reinterpret_cast<double*>(ws + p.off_mom);
+  q.ghist = reinterpret_cast<unsigned int*>(ws + p.off_ghist);
+  q.vhist = reinterpret_cast<unsigned int*>(ws + p.off_vhist);
+  q.vcur = q.vhist + kVBins;
+  q.voff = reinterpret_cast<unsigned int*>(ws + p.off_voff);
+  q.gbuf = reinterpret_cast<unsigned long long*>(ws + p.off_gbuf);
+}
+
+// stage 1 (per rank): threshold, pass A over this rank's draws
+static int psis_stage_local(const double* lw, int64_t n, int64_t idx_off, int exact, const PsisPlan& p, PsisPtrs& q,
+                            cudaStream_t stream) {
+  psis_init_kernel<<<8, 1024, 0, stream>>>(q.sc, p.M, q.ghist, q.vhist);
+  VB_CHECK_LAUNCH();
+  if (!exact) {
+    psis_sample_select_kernel<<<1, kSelThreads, 0, stream>>>(lw, p.stride, p.m_sample, p.R, q.sc);
+    VB_CHECK_LAUNCH();
+  } else {
+    psis_exact_begin_kernel<<<1, 1, 0, stream>>>(q.sc);
+    VB_CHECK_LAUNCH();
+    int shift = 64;
+    unsigned long long mask = 0;
+    while (shift > 0) {
+      const int bits = shift >= kDigitBits ? kDigitBits : shift;
+      shift -= bits;
+      psis_exact_hist_kernel<<<p.grid, 256, 0, stream>>>(lw, n, q.sc, shift, bits, mask, q.ghist);
+      VB_CHECK_LAUNCH();
+      psis_exact_scan_kernel<<<1, 32, 0, stream>>>(q.sc, shift, bits, q.ghist, shift == 0);
+      VB_CHECK_LAUNCH();
+      mask |= (unsigned long long)((1u << bits) - 1) << shift;
+    }
+  }
+  psis_pass_a_kernel<<<p.grid, 256, 0, stream>>>(lw, n, idx_off, q.sc, q.candx, q.candi, p.cap, q.blk);
+  VB_CHECK_LAUNCH();
+  return VB_OK;
+}
+
+// stage 2 (replicated): cutoff, tail ranking, GPD fit, smoothed values, log-sum-exp from the candidate list
+static int psis_stage_select(const PsisPlan& p, PsisPtrs& q, int nblk, int raw, cudaStream_t stream) {
+  const int cgrid = sm_count() * 2;
+  psis_cand_hist_kernel<<<cgrid, 256, 0, stream>>>(q.sc, q.candx, p.cap, q.ghist);
+  VB_CHECK_LAUNCH();
+  psis_cand_gather_kernel<<<cgrid / 4 > 0 ? cgrid / 4 : 1, kSelThreads, 0, stream>>>(q.sc, q.candx, p.cap, q.ghist, q.gbuf);
+  VB_CHECK_LAUNCH();
+  psis_cutoff_kernel<<<1, kSelThreads, 0, stream>>>(q.sc, q.candx, p.cap, q.gbuf, q.blk, nblk);
+  VB_CHECK_LAUNCH();
+  psis_tail_count_kernel<<<cgrid, 256, 0, stream>>>(q.sc, q.candx, q.vhist);
+  VB_CHECK_LAUNCH();
+  psis_tail_scan_kernel<<<1, kSelThreads, 0, stream>>>(q.sc, q.vhist, q.voff);
+  VB_CHECK_LAUNCH();
+  psis_tail_place_kernel<<<cgrid, 256, 0, stream>>>(q.sc, q.candx, q.candi, q.voff, q.vcur, q.tmpv, q.tmpi, q.tmpb,
+                                                    (unsigned)p.tail_cap, raw);
+  VB_CHECK_LAUNCH();
+  return VB_OK;
+}
+
+static int psis_stage_global(const PsisPlan& p, PsisPtrs& q, int nblk, double* result, int64_t* tail_idx,
+                             int32_t* tail_rank, cudaStream_t stream) {
+  int rc = psis_stage_select(p, q, nblk, 0, stream);
+  if (rc) return rc;
+  int blocks = (p.tail_cap + 255) / 256;
+  if (blocks > sm_count() * 4) blocks = sm_count() * 4;
+  psis_tail_rank_kernel<<<blocks, 256, 0, stream>>>(q.sc, q.tmpv, q.tmpi, q.tmpb, q.voff, q.vhist, q.tailv, q.taili, q.sorted);
+  VB_CHECK_LAUNCH();
+  if (tail_idx && tail_rank) {
+    psis_tail_index_order_kernel<<<blocks, 256, 0, stream>>>(q.sc, q.taili, tail_idx, tail_rank);
+    VB_CHECK_LAUNCH();
+  }
+  psis_gpd_grid_kernel<<<dim3(p.mgrid, kGpdSplit), 256, 0, stream>>>(q.sc, q.sorted, q.bs, q.part);
+  VB_CHECK_LAUNCH();
+  psis_gpd_weights_kernel<<<1, kSelThreads, 0, stream>>>(q.sc, q.bs, q.part, q.Ls);
+  VB_CHECK_LAUNCH();
+  psis_gpd_k_kernel<<<p.kparts, 256, 0, stream>>>(q.sc, q.sorted, q.kpart);
+  VB_CHECK_LAUNCH();
+  psis_tail_values_kernel<<<p.vparts, 256, 0, stream>>>(q.sc, q.kpart, p.kparts, q.tailv, q.tailout, q.part3);
+  VB_CHECK_LAUNCH();
+  psis_lse_kernel<<<1, 32, 0, stream>>>(q.sc, q.part3, p.vparts, result);
+  VB_CHECK_LAUNCH();
+  return VB_OK;
+}
+
+// stage 3 (per rank): pass B over this rank's draws and the scatter of its own smoothed tail entries
+static int psis_stage_apply(const double* lw, double* out, int64_t n, int64_t idx_off, int add_tail, const PsisPlan& p,
+                            PsisPtrs& q, double* result, cudaStream_t stream) {
+  if (out) {
+    psis_pass_b_kernel<<<p.grid, 256, 0, stream>>>(lw, out, n, q.sc, q.mom);
+  } else {
+    psis_pass_b_moments_kernel<<<p.grid, 256, 0, stream>>>(lw, n, q.sc, q.mom);
+  }
+  VB_CHECK_LAUNCH();
+  int blocks = (p.tail_cap + 255) / 256;
+  if (blocks > sm_count()) blocks = sm_count();
+  psis_tail_scatter_kernel<<<blocks, 256, 0, stream>>>(out, n, idx_off, q.sc, q.taili, q.tailout, q.mom, p.grid, add_tail,
+                                                       result);
+  VB_CHECK_LAUNCH();
+  return VB_OK;
+}
+
+// ---- draw-sharded PSIS: the record a rank ships = its top (M+1) values with their global indices ------------
+// record (doubles): [0] local max, [1] c_r = local (M+1)-th largest (raw; -inf if the rank has < M+1 draws),
+// [2] log sum exp(x - max_r) over the local draws NOT represented in the record, [3] count (-status on failure),
+// then vals[M+1], then idx[M+1] (int64 bit patterns).  The local tail (values > c_r, at most M) is padded
+// with copies of c_r (index -1): a rank's top (M+1) with ties cut.  The global (M+1)-th largest is the
+// (M+1)-th largest of the union of the records, and every member of the global tail is in its rank's local tail.
+__global__ void __launch_bounds__(256) psis_export_kernel(const PsisScalars* sc, const double* __restrict__ tmp_v,
+                                                          const int64_t* __restrict__ tmp_i,
+                                                          const double* __restrict__ cand_x,
+                                                          const int64_t* __restrict__ cand_i, int small,
+                                                          double* __restrict__ rec) {
+  const int K = sc->M + 1;
+  double* vals = rec + 4;
+  int64_t* idx = reinterpret_cast<int64_t*>(rec + 4 + K);
+  const double maxv = dkey_inv(sc->maxkey);
+  if (small) {            // fewer than M+1 local draws: all of them are candidates (t0 = local minimum)
+    const int C = (int)sc->ncand;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < K; j += gridDim.x * blockDim.x) {
+      vals[j] = j < C ? cand_x[j] : -INFINITY;
+      idx[j] = j < C ? cand_i[j] : -1;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      rec[0] = maxv; rec[1] = -INFINITY; rec[2] = -INFINITY; rec[3] = (double)C;
+    }
+    return;
+  }
+  if (sc->status) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { rec[0] = maxv; rec[1] = -INFINITY; rec[2] = -INFINITY; rec[3] = -(double)sc->status; }
+    return;
+  }
+  const int nt = (int)sc->ntail;
+  const double c = dkey_inv(sc->cutkey);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < K; j += gridDim.x * blockDim.x) {
+    vals[j] = j < nt ? tmp_v[j] : c;
+    idx[j] = j < nt ? tmp_i[j] : -1;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const double below = sc->body_below > 0.0 ? sc->body_below * exp(sc->t0 - maxv) : 0.0;
+    double body = below + sc->body_cand - (double)(K - nt) * exp(c - maxv);     // the copies of c_r travel in the record
+    if (!(body > 0.0)) body = 0.0;
+    rec[0] = maxv; rec[1] = c; rec[2] = log(body); rec[3] = (double)K;
+  }
+}
+
+// merged candidate list + global scalars into the control block (replicated on every rank)
+__global__ void __launch_bounds__(256) psis_import_kernel(PsisScalars* sc, const double* __restrict__ recs, int world,
+                                                          int reclen, double* __restrict__ cand_x,
+                                                          int64_t* __restrict__ cand_i, double* __restrict__ blk, int nblk) {
+  const int K = sc->M + 1;
+  int bad = 0;
+  for (int r = 0; r < world; ++r) bad |= recs[(size_t)r * reclen + 3] < 0.0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double mx = -INFINITY, t0 = -INFINITY, below = 0.0;
+    unsigned int total = 0;
+    for (int r = 0; r < world; ++r) {
+      const double* h = recs + (size_t)r * reclen;
+      mx = fmax(mx, h[0]);
+      t0 = fmax(t0, h[1]);
+      if (h[3] > 0.0) total += (unsigned int)h[3];
+    }
+    for (int r = 0; r < world; ++r) {
+      const double* h = recs + (size_t)r * reclen;
+      if (h[2] > -INFINITY) below += exp(h[2] + h[0] - t0);          // every term is <= exp(c_r - t0) * count <= count
+    }
+    sc->maxkey = dkey(mx);
+    sc->t0 = t0;
+    sc->t0key = dkey(t0);
+    sc->ncand = bad ? 0u : total;
+    sc->strict = 0;
+    if (bad) sc->status = 1;              // some rank's sampled threshold missed: every rank reruns exact
+    blk[0] = below;
+  }
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += gridDim.x * blockDim.x)
+    if (b > 0) blk[b] = 0.0;
+  if (bad) return;
+  for (int r = blockIdx.y; r < world; r += gridDim.y) {
+    unsigned int off = 0;
+    for (int q = 0; q < r; ++q) off += (unsigned int)recs[(size_t)q * reclen + 3];
+    const double* h = recs + (size_t)r * reclen;
+    const int cnt = (int)h[3];
+    const double* vals = h + 4;
+    const int64_t* idx = reinterpret_cast<const int64_t*>(h + 4 + K);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) {
+      cand_x[off + j] = vals[j];
+      cand_i[off + j] = idx[j];
+    }
+  }
+}
+}  // namespace vb
+
 extern "C" int vb_psislw_f64(const double* lw, double* out, int64_t n, double reff, int exact, double* result,
                              int64_t* tail_idx, int32_t* tail_rank, void* workspace, size_t workspace_bytes,
                              cudaStream_t stream) {
@@ -1136,99 +1362,82 @@ extern "C" int vb_psislw_f64(const double* lw, double* out, int64_t n, double re
   if (!workspace || workspace_bytes < p.total) return set_error(VB_ERR_WORKSPACE, "psislw: workspace too small");
   int rc = ensure_exp_table();
   if (rc) return rc;
-  char* ws = static_cast<char*>(workspace);
-  PsisScalars* sc = reinterpret_cast<PsisScalars*>(ws + p.off_sc);
-  auto candx = reinterpret_cast<double*>(ws + p.off_candx);
-  auto candi = reinterpret_cast<int64_t*>(ws + p.off_candi);
-  auto blk = reinterpret_cast<double*>(ws + p.off_blk);
-  auto tmpv = reinterpret_cast<double*>(ws + p.off_tmpv);
-  auto tmpi = reinterpret_cast<int64_t*>(ws + p.off_tmpi);
-  auto tmpb = reinterpret_cast<int*>(ws + p.off_tmpb);
-  auto tailv = reinterpret_cast<double*>(ws + p.off_tailv);
-  auto taili = reinterpret_cast<int64_t*>(ws + p.off_taili);
-  auto tailout = reinterpret_cast<double*>(ws + p.off_tailout);
-  auto sorted = reinterpret_cast<double*>(ws + p.off_sorted);
-  auto bs = reinterpret_cast<double*>(ws + p.off_bs);
-  auto part = reinterpret_cast<double*>(ws + p.off_part);
-  auto Ls = reinterpret_cast<double*>(ws + p.off_Ls);
-  auto kpart = reinterpret_cast<double*>(ws + p.off_kpart);
-  auto part3 = reinterpret_cast<double*>(ws + p.off_part3);
-  auto mom = reinterpret_cast<double*>(ws + p.off_mom);
-  auto ghist = reinterpret_cast<unsigned int*>(ws + p.off_ghist);
-  auto vhist = reinterpret_cast<unsigned int*>(ws + p.off_vhist);
-  auto vcur = vhist + kVBins;
-  auto voff = reinterpret_cast<unsigned int*>(ws + p.off_voff);
-  auto gbuf = reinterpret_cast<unsigned long long*>(ws + p.off_gbuf);
-
+  PsisPtrs q;
+  psis_ptrs(static_cast<char*>(workspace), p, q);
   VB_CUDA(cudaMemsetAsync(result, 0, sizeof(double) * R_COUNT, stream));
-  psis_init_kernel<<<8, 1024, 0, stream>>>(sc, p.M, ghist, vhist);
+  if ((rc = psis_stage_local(lw, n, 0, exact, p, q, stream))) return rc;
+  if ((rc = psis_stage_global(p, q, p.grid, result, tail_idx, tail_rank, stream))) return rc;
+  return psis_stage_apply(lw, out, n, 0, 1, p, q, result, stream);
+}
+
+// ---- draw-sharded PSIS: stage 1 on each rank, one fixed-size all-gather of the records on the
+// host side (NCCL), stage 2 replicated on the merged records, stage 3 on each rank.  No host sync in between. ----
+extern "C" size_t vb_psis_dist_workspace_bytes(int64_t n_local, int64_t n_global, double reff, int world) {
+  if (n_local <= 1 || n_global < n_local || !(reff > 0) || world < 1) return 0;
+  PsisPlan p;
+  psis_plan(n_local, reff, p, n_global, world);
+  return p.total;
+}
+
+extern "C" int64_t vb_psis_dist_record_doubles(int64_t n_global, double reff) {
+  if (n_global <= 1 || !(reff > 0)) return 0;
+  PsisPlan p;
+  psis_plan(n_global, reff, p);
+  return 4 + 2 * (int64_t)(p.M + 1);
+}
+
+extern "C" int vb_psis_dist_local(const double* lw, int64_t n_local, int64_t idx_off, int64_t n_global, double reff,
+                                  int world, int exact, double* record, void* workspace, size_t workspace_bytes,
+                                  cudaStream_t stream) {
+  if (n_local <= 1 || n_global < n_local || !(reff > 0) || world < 1 || !lw || !record)
+    return set_error(VB_ERR_INVALID_ARG, "psis_dist_local: bad arguments");
+  PsisPlan p;
+  psis_plan(n_local, reff, p, n_global, world);
+  if (!workspace || workspace_bytes < p.total) return set_error(VB_ERR_WORKSPACE, "psis_dist_local: workspace too small");
+  int rc = ensure_exp_table();
+  if (rc) return rc;
+  PsisPtrs q;
+  psis_ptrs(static_cast<char*>(workspace), p, q);
+  const bool small = n_local < (int64_t)p.M + 1;         // the sample is the whole shard and everything is a candidate
+  if ((rc = psis_stage_local(lw, n_local, idx_off, small ? 0 : exact, p, q, stream))) return rc;
+  if (!small && (rc = psis_stage_select(p, q, p.grid, 1, stream))) return rc;
+  int blocks = (p.M + 1 + 255) / 256;
+  if (blocks > sm_count()) blocks = sm_count();
+  psis_export_kernel<<<blocks, 256, 0, stream>>>(q.sc, q.tmpv, q.tmpi, q.candx, q.candi, small ? 1 : 0, record);
   VB_CHECK_LAUNCH();
-  if (!exact) {
-    psis_sample_select_kernel<<<1, kSelThreads, 0, stream>>>(lw, p.stride, p.m_sample, p.R, sc);
-    VB_CHECK_LAUNCH();
-  } else {
-    psis_exact_begin_kernel<<<1, 1, 0, stream>>>(sc);
-    VB_CHECK_LAUNCH();
-    int shift = 64;
-    unsigned long long mask = 0;
-    while (shift > 0) {
-      const int bits = shift >= kDigitBits ? kDigitBits : shift;
-      shift -= bits;
-      psis_exact_hist_kernel<<<p.grid, 256, 0, stream>>>(lw, n, sc, shift, bits, mask, ghist);
-      VB_CHECK_LAUNCH();
-      psis_exact_scan_kernel<<<1, 32, 0, stream>>>(sc, shift, bits, ghist, shift == 0);
-      VB_CHECK_LAUNCH();
-      mask |= (unsigned long long)((1u << bits) - 1) << shift;
-    }
-  }
-  psis_pass_a_kernel<<<p.grid, 256, 0, stream>>>(lw, n, sc, candx, candi, p.cap, blk);
-  VB_CHECK_LAUNCH();
-  const int cgrid = sm_count() * 2;
-  psis_cand_hist_kernel<<<cgrid, 256, 0, stream>>>(sc, candx, p.cap, ghist);
-  VB_CHECK_LAUNCH();
-  psis_cand_gather_kernel<<<cgrid / 4 > 0 ? cgrid / 4 : 1, kSelThreads, 0, stream>>>(sc, candx, p.cap, ghist, gbuf);
-  VB_CHECK_LAUNCH();
-  psis_cutoff_kernel<<<1, kSelThreads, 0, stream>>>(sc, candx, p.cap, gbuf, blk, p.grid);
-  VB_CHECK_LAUNCH();
-  psis_tail_count_kernel<<<cgrid, 256, 0, stream>>>(sc, candx, vhist);
-  VB_CHECK_LAUNCH();
-  psis_tail_scan_kernel<<<1, kSelThreads, 0, stream>>>(sc, vhist, voff);
-  VB_CHECK_LAUNCH();
-  psis_tail_place_kernel<<<cgrid, 256, 0, stream>>>(sc, candx, candi, voff, vcur, tmpv, tmpi, tmpb, (unsigned)p.tail_cap);
-  VB_CHECK_LAUNCH();
-  {
-    int blocks = (p.tail_cap + 255) / 256;
-    if (blocks > sm_count() * 4) blocks = sm_count() * 4;
-    psis_tail_rank_kernel<<<blocks, 256, 0, stream>>>(sc, tmpv, tmpi, tmpb, voff, vhist, tailv, taili, sorted);
-    VB_CHECK_LAUNCH();
-    if (tail_idx && tail_rank) {
-      psis_tail_index_order_kernel<<<blocks, 256, 0, stream>>>(sc, taili, tail_idx, tail_rank);
-      VB_CHECK_LAUNCH();
-    }
-  }
-  psis_gpd_grid_kernel<<<dim3(p.mgrid, kGpdSplit), 256, 0, stream>>>(sc, sorted, bs, part);
-  VB_CHECK_LAUNCH();
-  psis_gpd_weights_kernel<<<1, kSelThreads, 0, stream>>>(sc, bs, part, Ls);
-  VB_CHECK_LAUNCH();
-  psis_gpd_k_kernel<<<p.kparts, 256, 0, stream>>>(sc, sorted, kpart);
-  VB_CHECK_LAUNCH();
-  psis_tail_values_kernel<<<p.vparts, 256, 0, stream>>>(sc, kpart, p.kparts, tailv, tailout, part3);
-  VB_CHECK_LAUNCH();
-  psis_lse_kernel<<<1, 32, 0, stream>>>(sc, part3, p.vparts, result);
-  VB_CHECK_LAUNCH();
-  if (out) {
-    psis_pass_b_kernel<<<p.grid, 256, 0, stream>>>(lw, out, n, sc, mom);
-  } else {
-    psis_pass_b_moments_kernel<<<p.grid, 256, 0, stream>>>(lw, n, sc, mom);
-  }
-  VB_CHECK_LAUNCH();
-  {
-    int blocks = (p.tail_cap + 255) / 256;
-    if (blocks > sm_count()) blocks = sm_count();
-    psis_tail_scatter_kernel<<<blocks, 256, 0, stream>>>(out, sc, taili, tailout, mom, p.grid, result);
-    VB_CHECK_LAUNCH();
-  }
   return VB_OK;
+}
+
+extern "C" int vb_psis_dist_global(const double* records, int64_t n_local, int64_t n_global, double reff, int world,
+                                   double* result, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (!records || !result || world < 1) return set_error(VB_ERR_INVALID_ARG, "psis_dist_global: bad arguments");
+  PsisPlan p;
+  psis_plan(n_local, reff, p, n_global, world);
+  if (!workspace || workspace_bytes < p.total) return set_error(VB_ERR_WORKSPACE, "psis_dist_global: workspace too small");
+  PsisPtrs q;
+  psis_ptrs(static_cast<char*>(workspace), p, q);
+  VB_CUDA(cudaMemsetAsync(result, 0, sizeof(double) * R_COUNT, stream));
+  psis_init_kernel<<<8, 1024, 0, stream>>>(q.sc, p.M, q.ghist, q.vhist);
+  VB_CHECK_LAUNCH();
+  const int reclen = 4 + 2 * (p.M + 1);
+  int bx = (p.M + 1 + 255) / 256;
+  if (bx > 64) bx = 64;
+  psis_import_kernel<<<dim3(bx, world > 64 ? 64 : world), 256, 0, stream>>>(q.sc, records, world, reclen, q.candx, q.candi,
+                                                                          q.blk, p.grid);
+  VB_CHECK_LAUNCH();
+  return psis_stage_global(p, q, p.grid, result, nullptr, nullptr, stream);
+}
+
+extern "C" int vb_psis_dist_apply(const double* lw, double* out, int64_t n_local, int64_t idx_off, int64_t n_global,
+                                  double reff, int world, int rank, double* result, void* workspace,
+                                  size_t workspace_bytes, cudaStream_t stream) {
+  if (!lw || !result || n_local <= 1) return set_error(VB_ERR_INVALID_ARG, "psis_dist_apply: bad arguments");
+  PsisPlan p;
+  psis_plan(n_local, reff, p, n_global, world);
+  if (!workspace || workspace_bytes < p.total) return set_error(VB_ERR_WORKSPACE, "psis_dist_apply: workspace too small");
+  PsisPtrs q;
+  psis_ptrs(static_cast<char*>(workspace), p, q);
+  return psis_stage_apply(lw, out, n_local, idx_off, rank == 0, p, q, result, stream);
 }
 
 extern "C" int vb_divergence_moments_f64(const double* lw, int64_t n, double alpha, double* out3, cudaStream_t stream) {
