@@ -16,15 +16,20 @@
 // Shared memory: 10 x 16 KB operand ring, 64 KB R tile, barriers.  TMEM: Z 256 cols, Tt 2 x 128 cols.
 //
 // HBM layout (chosen for the kernel, produced once by vb_glm_fast_create):
-//   Xt_h, Xt_l : fp16 [numTiles * d_pad][128]   "tile-transposed": for each 128-row tile the d_pad x 128
-//                block (column j of the tile = one 256-byte row) is contiguous, so GEMM1 reads it as an
-//                MN-major A operand and E2's column-owning threads read 128-byte rows with LDS.128.
-//   Tt_h, Tt_l : fp16 [d_pad][256]  Theta^T (MN-major B operand), rebuilt every sweep
-//   E          : fp16 [256][d_pad]  base draws (MN-major A operand of GEMM2), rebuilt every sweep
+//   Xt_h, Xt_l : fp16 [numTiles][2][d_pad][64]   "tile-transposed": for each 128-row tile and each 64-row half the
+//                d_pad x 64 block (column j = one 128-byte row) is contiguous, so GEMM1 reads it as an MN-major
+//                A operand (64-element groups, 128-byte swizzle) and E2's column-owning threads read 128-byte rows.
+//   Tt_h, Tt_l : fp16 [4][d_pad][64]  Theta^T in 64-sample groups (MN-major B operand), rebuilt every sweep
+//   E          : fp16 [d_pad/64][256][64]  base draws in 64-column groups (MN-major A operand of GEMM2)
+// Every operand group is a dense array of 128-byte rows, so ONE multi-dimensional TMA box per pipeline stage and
+// operand writes all its groups (the TMA unit is op-rate bound at 4 KB boxes).
 // All operands are MN-major with the 128-byte swizzle, so the K extent of a pipeline stage is free:
 // GEMM1 streams K = 32 per stage (16 KB for X hi+lo, 16 KB each for Theta lo / hi).
 #include <cuda.h>
 #include <cuda_fp16.h>
+
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -85,6 +90,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                                 uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar_cluster)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
+                                                 uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar_cluster)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -101,6 +126,85 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+
+// ---- cluster / CTA-pair helpers (cta_group::2) ---------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity) {      // acquire at cluster scope
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// long waits (thousands of cycles): back off so that the spinning warp leaves the issue slots to the epilogue warps
+__device__ __forceinline__ void mbar_wait_cl_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(ns);
+  }
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+// TMA load into this CTA's shared memory, completion bytes signalled on a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 
 // 32 lanes x 32 columns of 32-bit accumulators -> 32 registers per thread
@@ -151,6 +255,9 @@ struct Params {
   double* ge_part;   // [grid][d_pad]
   float* dbg;        // optional: Z of this CTA's first tile [128][256], then Tt of j-block 0 [128][128]
   long long* tim;    // optional: clock64 timestamps of CTA 0
+  int uniform_w;     // 1: every valid sample has weight 1 (w == NULL on the host side)
+  const __half* Xh;  // pair kernel: E2 reads its X rows from global memory
+  const __half* Xl;
 };
 
 struct Misc {
@@ -244,22 +351,22 @@ glm_fast_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
         return ring_u + slot * kSlotBytes;
       };
       for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
-        const int r0 = tile * p.d_pad;          // first row of this tile in the tile-transposed X arrays
+        const int r0 = tile * 2 * p.d_pad;      // first row of this tile in the [tile][half][j] x 64 view of X
         for (int kc = 0; kc < KC; ++kc, ++sc) {
           const int j0 = kc * 32;
           const uint32_t bar = smem_u32(&misc->g1_full[sc & 3]);
           mbar_expect_tx(bar, 3 * kSlotBytes);
           uint32_t dst = acquire();
           tma_load_2d(dst, &tmXh, 0, r0 + j0, bar);
-          tma_load_2d(dst + 4096, &tmXh, 64, r0 + j0, bar);
+          tma_load_2d(dst + 4096, &tmXh, 0, r0 + p.d_pad + j0, bar);
           tma_load_2d(dst + 8192, &tmXl, 0, r0 + j0, bar);
-          tma_load_2d(dst + 12288, &tmXl, 64, r0 + j0, bar);
+          tma_load_2d(dst + 12288, &tmXl, 0, r0 + p.d_pad + j0, bar);
           dst = acquire();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) tma_load_2d(dst + g * 4096, &tmTl, 64 * g, j0, bar);
+          for (int g = 0; g < 4; ++g) tma_load_2d(dst + g * 4096, &tmTl, 0, g * p.d_pad + j0, bar);
           dst = acquire();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) tma_load_2d(dst + g * 4096, &tmTh, 64 * g, j0, bar);
+          for (int g = 0; g < 4; ++g) tma_load_2d(dst + g * 4096, &tmTh, 0, g * p.d_pad + j0, bar);
         }
         if (p.want_grad) {
           for (int jb = 0; jb < JB; ++jb, ++bc) {
@@ -268,20 +375,20 @@ glm_fast_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
             mbar_expect_tx(ebar, 4 * kSlotBytes);
             for (int g = 0; g < 4; ++g) {
               const uint32_t dst = acquire();
-              tma_load_2d(dst, &tmE, j0, 64 * g, ebar);
-              tma_load_2d(dst + 8192, &tmE, j0 + 64, 64 * g, ebar);
+              tma_load_2d(dst, &tmE, 0, (j0 >> 6) * kSP + 64 * g, ebar);
+              tma_load_2d(dst + 8192, &tmE, 0, ((j0 >> 6) + 1) * kSP + 64 * g, ebar);
             }
             mbar_expect_tx(smem_u32(&misc->x_full[bc & 1][0]), 2 * kSlotBytes);
             mbar_expect_tx(smem_u32(&misc->x_full[bc & 1][1]), 2 * kSlotBytes);
             for (int a = 0; a < 2; ++a) {
               const uint32_t dst = acquire(), xbar = smem_u32(&misc->x_full[bc & 1][a]);
-              tma_load_2d(dst, &tmXh2, 64 * a, r0 + j0, xbar);
-              tma_load_2d(dst + 8192, &tmXh2, 64 * a, r0 + j0 + 64, xbar);
+              tma_load_2d(dst, &tmXh2, 0, r0 + a * p.d_pad + j0, xbar);
+              tma_load_2d(dst + 8192, &tmXh2, 0, r0 + a * p.d_pad + j0 + 64, xbar);
             }
             for (int a = 0; a < 2; ++a) {
               const uint32_t dst = acquire(), xbar = smem_u32(&misc->x_full[bc & 1][a]);
-              tma_load_2d(dst, &tmXl2, 64 * a, r0 + j0, xbar);
-              tma_load_2d(dst + 8192, &tmXl2, 64 * a, r0 + j0 + 64, xbar);
+              tma_load_2d(dst, &tmXl2, 0, r0 + a * p.d_pad + j0, xbar);
+              tma_load_2d(dst + 8192, &tmXl2, 0, r0 + a * p.d_pad + j0 + 64, xbar);
             }
           }
         }
@@ -514,7 +621,7 @@ glm_fast_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
       int64_t rows = 0;
       for (int tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x) {
         const int64_t left = p.N - (int64_t)tile * kBM;
-        rows += left < kBM ? left : kBM;
+        rows += left <= 0 ? 0 : (left < kBM ? left : kBM);
       }
       s -= (double)(kSP - p.S) * (double)rows * (double)(1.0f * 0.6931471805599453f);
       p.ll_part[(size_t)blockIdx.x * kSP + (threadIdx.x - 64)] = s / (double)p.S;
@@ -553,8 +660,494 @@ glm_fast_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
   }
 }
 
+
+// =================================================================================================
+// CTA-pair kernel (cta_group::2): two CTAs of a cluster work on a 256-row super-tile.
+//   GEMM1  M = 256 (rank r owns rows 128r..128r+127), N = 256: each CTA stages only HALF of Theta^T per K stage
+//   GEMM2  M = 256 j (rank r owns j-block r of the 256-j pair block), N = 128 tile rows (64 from each CTA's R tile),
+//          two such units (tile-row halves) per group; each CTA stages only its half of E, one 16 KB slot per
+//          64 samples, released as soon as both units have consumed it
+//   E2     reads its X rows straight from global memory / L2 (256-bit loads; a thread owns column j, whose
+//          128 tile rows are one contiguous 256-byte run in the tile-transposed layout), so the operand ring
+//          only carries tensor-core operands
+// Operand fills per 128 rows drop from 1280 KB to 896 KB (d = 512) -- the single-CTA kernel is bound by the
+// L2 -> SM rate.  GEMM2/E2 of super-tile i-1 are interleaved with GEMM1 of super-tile i (the R tile of i-1 stays
+// valid until E1 of i starts, which is after every MMA issued before Z(i) was committed), and E2 has its own
+// warps, so the tensor pipe only idles during E1.
+// Warps: 0 producer, 1 MMA (rank 0 issues for the pair), 2..17 epilogue (E2 of super-tile i-1, then E1 of i).
+constexpr int kThreadsP = 64 + 32 * 8 + 32 * 8;      // 576
+constexpr int kFullRing = 8;
+
+struct MiscP {
+  uint64_t empty[kNumSlots];
+  uint64_t g1_full[kFullRing];        // leader: bytes of both CTAs' halves of a GEMM1 stage
+  uint64_t e_full[16];                // leader: both CTAs' halves of one 64-sample slice of E (ring > slices in flight)
+  uint64_t z_full;                    // local, multicast commit
+  uint64_t r_full;                    // leader, count 2: both R tiles written, both Z read
+  uint64_t rb_full;                   // local, count 2: rb[] written by both CTAs
+  uint64_t t_full;                    // local, multicast commit: both units of a group
+  uint64_t t_empty;                   // leader, count 2
+  uint32_t tmem_base;
+  uint32_t pad;
+  alignas(16) float rbar[kBM];        // E1 column-half 1 partial row sums
+  alignas(16) float rb[2][2 * kBM];   // [iteration parity][row of the super-tile]: sum_s R[n,s]
+};
+static_assert(sizeof(MiscP) <= kMiscBytes, "misc smem overflow");
+
+__device__ __forceinline__ void epi1_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void ldg256(const void* ptr, uint32_t* r) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(ptr));
+}
+
+
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Link epilogue of 32 accumulator columns held by one thread (one tile row), staged so that the 16 independent
+// MUFU chains of a half-chunk are in flight together (the compiler keeps the order of these loops).
+//   in : v[i] = z (margin y * x.theta)
+//   out: packed = fp16 pairs of r = w * sigmoid(-z) (rows beyond N give 0), v[i] = softplus(-z) when KEEP_SP,
+//        spsum += sum_i softplus(-z_i), rsum += sum_i r_i
+// PLAIN: all rows valid and all weights 1 -> no masking.
+template <bool PLAIN, bool KEEP_SP>
+__device__ __forceinline__ void link_chunk(float (&v)[32], uint32_t (&packed)[16], float& spsum, float& rsum, float wl,
+                                           float rowvalid) {
+  float lgsum = 0.0f, mxsum = 0.0f, rs = 0.0f;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    float t[16], lg[16], ri[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = fast_exp2(-fabsf(v[16 * hh + i]) * 1.4426950408889634f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float den = 1.0f + t[i];
+      lg[i] = fast_lg2(den);
+      ri[i] = fast_rcp(den);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      float r2[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float a = v[16 * hh + i + u];
+        const float mx = fmaxf(-a, 0.0f);
+        float r = (a >= 0.0f ? t[i + u] : 1.0f) * ri[i + u];              // sigmoid(-a)
+        if (!PLAIN) r *= __shfl_sync(0xffffffffu, wl, 16 * hh + i + u) * rowvalid;
+        if (KEEP_SP) v[16 * hh + i + u] = PLAIN ? fmaf(lg[i + u], 0.6931471805599453f, mx)
+                                                : fmaf(lg[i + u], 0.6931471805599453f, mx) * rowvalid;
+        lgsum += lg[i + u];
+        mxsum += mx;
+        rs += r;
+        r2[u] = r;
+      }
+      const __half2 h2 = __floats2half2_rn(r2[0], r2[1]);
+      packed[(16 * hh + i) >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+  }
+  const float sp = fmaf(lgsum, 0.6931471805599453f, mxsum);
+  spsum += PLAIN ? sp : sp * rowvalid;
+  rsum += rs;
+}
+
+// Fill sequence of iteration i (identical in every role and in both CTAs; `fill` counts 16 KB slots):
+//   for kc in 0..KC-1:  slot A = X (hi n0 | hi n1 | lo n0 | lo n1), slot B = Theta_lo (2 groups) | Theta_hi (2 groups)
+//       after the stages with (kc & 7) == 3 (and i > 0): GEMM2 group jbp = kc >> 3 of super-tile i-1: 4 slots of E
+//   a last iteration i = nIter only carries the GEMM2 groups of the final super-tile.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP, 1)
+glm_fast_pair_kernel(const __grid_constant__ CUtensorMap tmX,      // 5-D: [hi|lo][tile][half][j][64 n]
+                     const __grid_constant__ CUtensorMap tmT,      // 4-D: [hi|lo][group][j][64 s]
+                     const __grid_constant__ CUtensorMap tmE,      // 3-D: [j group][s][64 j]
+                     Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ring = smem;
+  uint8_t* rtile = smem + kRingBytes;
+  MiscP* misc = reinterpret_cast<MiscP*>(smem + kRingBytes + kRBytes);
+  const uint32_t ring_u = smem_u32(ring), rtile_u = smem_u32(rtile);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int numSuper = (p.numTiles + 1) >> 1;
+  const int nIter = cluster_id < numSuper ? (numSuper - cluster_id + num_clusters - 1) / num_clusters : 0;
+  const int KC = p.d_pad / 32, JBP = p.d_pad / 256;      // KC = 8 JBP
+  const bool grad = p.want_grad != 0;
+  double ll_acc[2] = {0.0, 0.0};                // epilogue warps: column sums of softplus
+  double ge_acc[8], gmu_acc[8];                 // epilogue warps: gradient partials of column j per 256-column block
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ge_acc[i] = gmu_acc[i] = 0.0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kNumSlots; ++i) mbar_init(smem_u32(&misc->empty[i]), 1);
+    for (int i = 0; i < kFullRing; ++i) mbar_init(smem_u32(&misc->g1_full[i]), 1);
+    for (int i = 0; i < 16; ++i) mbar_init(smem_u32(&misc->e_full[i]), 1);
+    mbar_init(smem_u32(&misc->z_full), 1);
+    mbar_init(smem_u32(&misc->r_full), 2);
+    mbar_init(smem_u32(&misc->rb_full), 2);
+    mbar_init(smem_u32(&misc->t_full), 1);
+    mbar_init(smem_u32(&misc->t_empty), 2);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&misc->tmem_base)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // barriers of both CTAs initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem = misc->tmem_base;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    if (lane == 0) {
+      prefetch_tmap(&tmX); prefetch_tmap(&tmT); prefetch_tmap(&tmE);
+      uint32_t fill = 0, sc = 0, ec = 0;
+      auto acquire = [&]() -> uint32_t {
+        const uint32_t slot = fill % kNumSlots, par = (fill / kNumSlots) & 1;
+        mbar_wait_cl_sleep(smem_u32(&misc->empty[slot]), par ^ 1, 32);
+        ++fill;
+        return ring_u + slot * kSlotBytes;
+      };
+      auto g2_fills = [&](int jbp) {
+        const int j0 = jbp * 256 + (int)rank * 128;                 // this CTA's 128 columns of the pair block
+        for (int g = 0; g < 4; ++g, ++ec) {
+          const uint32_t ebar_l = smem_u32(&misc->e_full[ec & 15]);
+          if (leader) mbar_expect_tx(ebar_l, 2 * kSlotBytes);
+          const uint32_t ebar = mapa_u32(ebar_l, 0);
+          const uint32_t dst = acquire();
+          tma_load_3d_pair(dst, &tmE, 0, 64 * g, j0 >> 6, ebar);           // 64 samples x (2 x 64 columns): 16 KB
+        }
+      };
+      for (int it = 0; it <= nIter; ++it) {
+        const int sup = cluster_id + it * num_clusters;
+        if (it < nIter) {
+          const int tile = 2 * sup + (int)rank;                     // this CTA's 128 rows
+          for (int kc = 0; kc < KC; ++kc, ++sc) {
+            const int j0 = kc * 32;
+            const uint32_t bar_l = smem_u32(&misc->g1_full[sc % kFullRing]);
+            if (leader) mbar_expect_tx(bar_l, 4 * kSlotBytes);
+            const uint32_t bar = mapa_u32(bar_l, 0);
+            uint32_t dst = acquire();
+            tma_load_5d_pair(dst, &tmX, 0, j0, 0, tile, 0, bar);         // hi n0 | hi n1 | lo n0 | lo n1: 16 KB
+            dst = acquire();
+            tma_load_4d_pair(dst, &tmT, 0, j0, 2 * (int)rank, 0, bar);   // Theta_hi g0 | g1 | Theta_lo g0 | g1 (this CTA's half)
+            if (grad && it > 0 && (kc & 7) == 3) g2_fills(kc >> 3);
+          }
+        } else if (grad && it > 0) {
+          for (int jbp = 0; jbp < JBP; ++jbp) g2_fills(jbp);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer: rank 0 only ================================
+    if (leader) {
+      constexpr uint32_t idesc1 = make_idesc(256, 256, 1, 1);
+      constexpr uint32_t idesc2 = make_idesc(256, 128, 1, 0);
+      uint32_t fill = 0, sc = 0, ec = 0, gc = 0;
+      long long w_g1 = 0, w_e = 0, w_t = 0;
+      const bool timing = p.tim && blockIdx.x == 0;
+      auto g2_group = [&]() {
+        long long c0 = timing ? clock64() : 0;
+        mbar_wait_cl(smem_u32(&misc->t_empty), (gc & 1) ^ 1);      // both CTAs' E2 have drained the previous group
+        if (timing) w_t += clock64() - c0;
+        ++gc;
+        for (int g = 0; g < 4; ++g, ++ec) {
+          const uint32_t slot = fill % kNumSlots;
+          ++fill;
+          c0 = timing ? clock64() : 0;
+          mbar_wait_cl(smem_u32(&misc->e_full[ec & 15]), (ec >> 4) & 1);
+          if (timing) w_e += clock64() - c0;
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t es = ring_u + slot * kSlotBytes;
+#pragma unroll
+            for (int nh = 0; nh < 2; ++nh) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_pair(tmem + 256 + 128 * nh, make_desc(es + k * 2048, 8192, 1024),
+                              make_desc(rtile_u + g * 16384 + nh * 8192 + k * 32, 16, 1024), idesc2, (g | k) ? 1u : 0u);
+            }
+            umma_commit_pair(smem_u32(&misc->empty[slot]));
+            if (g == 3) umma_commit_pair(smem_u32(&misc->t_full));
+          }
+          __syncwarp();
+        }
+      };
+      for (int it = 0; it <= nIter; ++it) {
+        if (timing && it < 8 && lane == 0) p.tim[it * 16 + 0] = clock64();
+        if (it > 0) {                    // Z(it-1) read and R(it-1) written by both CTAs
+          mbar_wait_cl_sleep(smem_u32(&misc->r_full), (it - 1) & 1, 64);
+          tc_fence_after();
+        }
+        if (timing && it < 8 && lane == 0) p.tim[it * 16 + 1] = clock64();
+        if (it < nIter) {
+          for (int kc = 0; kc < KC; ++kc, ++sc) {
+            const uint32_t sa = fill % kNumSlots, sb = (fill + 1) % kNumSlots;
+            fill += 2;
+            const uint32_t ax = ring_u + sa * kSlotBytes, bh = ring_u + sb * kSlotBytes, bl = bh + 8192;
+            const long long c0 = timing ? clock64() : 0;
+            mbar_wait_cl(smem_u32(&misc->g1_full[sc % kFullRing]), (sc / kFullRing) & 1);
+            if (timing) w_g1 += clock64() - c0;
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                umma_f16_pair(tmem, make_desc(ax + k * 2048, 4096, 1024), make_desc(bl + k * 2048, 4096, 1024), idesc1,
+                              (kc | k) ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                umma_f16_pair(tmem, make_desc(ax + k * 2048, 4096, 1024), make_desc(bh + k * 2048, 4096, 1024), idesc1, 1u);
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                umma_f16_pair(tmem, make_desc(ax + 8192 + k * 2048, 4096, 1024), make_desc(bh + k * 2048, 4096, 1024), idesc1, 1u);
+              umma_commit_pair(smem_u32(&misc->empty[sa]));
+              umma_commit_pair(smem_u32(&misc->empty[sb]));
+              if (kc == KC - 1) umma_commit_pair(smem_u32(&misc->z_full));
+            }
+            __syncwarp();
+            if (grad && it > 0 && (kc & 7) == 3) g2_group();
+          }
+        } else if (grad && it > 0) {
+          for (int jbp = 0; jbp < JBP; ++jbp) g2_group();
+        }
+        if (timing && it < 8 && lane == 0) {
+          p.tim[it * 16 + 2] = clock64();
+          p.tim[it * 16 + 3] = w_g1;
+          p.tim[it * 16 + 4] = w_e;
+          p.tim[it * 16 + 5] = w_t;
+        }
+        w_g1 = w_e = w_t = 0;
+      }
+    }
+  } else {
+    // ================================ epilogue warps (16): E2 of super-tile it-1, then E1 of super-tile it ==========
+    // The two jobs never overlap in time for long (E2 groups arrive while GEMM1 streams, E1 starts when Z is
+    // complete and the tensor pipe idles until E1 is done), so one pool of warps does both at full width.
+    const int ew = warp - 2;
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int k = ew >> 2;             // E1: sample-column quarter;  E2: (tile t, tile-row half nh)
+    const int row = 32 * q + lane;     // TMEM lane = row of this CTA's tile (E1) / column j of its block (E2)
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+    const uint32_t r_full_leader = mapa_u32(smem_u32(&misc->r_full), 0);
+    const uint32_t t_empty_leader = mapa_u32(smem_u32(&misc->t_empty), 0);
+    const uint32_t rbf_own = mapa_u32(smem_u32(&misc->rb_full), rank), rbf_peer = mapa_u32(smem_u32(&misc->rb_full), rank ^ 1);
+    const bool tthread = p.tim && blockIdx.x == 0 && threadIdx.x == 64;
+    const int t2 = k & 1, nh2 = k >> 1;
+    const size_t tstride = (size_t)p.d_pad * kBM;
+    uint32_t gc = 0;
+    long long w_tf = 0, busy = 0;
+
+    auto e2_group = [&](int itp, int jbp) {      // GEMM2 group jbp of iteration itp: this warp's 64 tile rows
+      const int sup = cluster_id + itp * num_clusters;
+      const int j = jbp * 256 + 128 * (int)rank + row;
+      // this thread's X values: column j, the 64 rows of half nh2 of tile t2 (128 contiguous bytes), hi and lo
+      const __half* xhp = p.Xh + ((size_t)((2 * sup + t2) * 2 + nh2) * p.d_pad + j) * 64;
+      const __half* xlp = p.Xl + ((size_t)((2 * sup + t2) * 2 + nh2) * p.d_pad + j) * 64;
+      uint32_t xa[32], xb[32];                   // [0,16): hi, [16,32): lo of a 32-row step
+      ldg256(xhp, xa);                           // X does not depend on the MMA: in flight while waiting
+      ldg256(xhp + 16, xa + 8);
+      ldg256(xlp, xa + 16);
+      ldg256(xlp + 16, xa + 24);
+      ldg256(xhp + 32, xb);
+      ldg256(xhp + 48, xb + 8);
+      ldg256(xlp + 32, xb + 16);
+      ldg256(xlp + 48, xb + 24);
+      float ge = 0.0f, gm = 0.0f;
+      auto compute = [&](const uint32_t* x, int part) {
+        const float* rbp = &misc->rb[itp & 1][128 * t2 + 64 * nh2 + 32 * part];
+        float tv[32];
+        tmem_ld32(lane_addr + 256 + 128 * nh2 + 64 * t2 + 32 * part, tv);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float2 fh2 = __half22float2(*reinterpret_cast<const __half2*>(&x[e]));
+          const float2 fl2 = __half22float2(*reinterpret_cast<const __half2*>(&x[16 + e]));
+          const float x0 = fh2.x + fl2.x, x1 = fh2.y + fl2.y;
+          const float2 rb2 = *reinterpret_cast<const float2*>(rbp + 2 * e);
+          ge = fmaf(x0, tv[2 * e], ge);
+          ge = fmaf(x1, tv[2 * e + 1], ge);
+          gm = fmaf(x0, rb2.x, gm);
+          gm = fmaf(x1, rb2.y, gm);
+        }
+      };
+      const long long c1 = tthread ? clock64() : 0;
+      mbar_wait_cl_sleep(smem_u32(&misc->t_full), gc & 1, 64);
+      ++gc;
+      const long long c2 = tthread ? clock64() : 0;
+      w_tf += c2 - c1;
+      tc_fence_after();
+      if (tthread && itp < 8 && jbp == 0) p.tim[itp * 16 + 10] = c2;
+      compute(xa, 0);
+      compute(xb, 1);
+      tc_fence_before();
+      epi1_barrier();
+      if (tthread) busy += clock64() - c2;
+      if (threadIdx.x == 64) mbar_arrive_cluster(t_empty_leader);
+      ge_acc[jbp & 7] += (double)ge;
+      gmu_acc[jbp & 7] += (double)gm;
+    };
+
+    for (int it = 0; it <= nIter; ++it) {
+      // ---------------- E2 of the previous super-tile ----------------
+      if (grad && it > 0) {
+        mbar_wait_cl_sleep(smem_u32(&misc->rb_full), (it - 1) & 1, 64);      // rb[(it-1)&1] complete (both CTAs)
+        for (int jbp = 0; jbp < JBP; ++jbp) e2_group(it - 1, jbp);
+        if (tthread && it < 8) {
+          p.tim[it * 16 + 12] = w_tf;
+          p.tim[it * 16 + 13] = busy;
+        }
+        w_tf = busy = 0;
+      }
+      if (it == nIter) break;
+      // ---------------- E1: link epilogue on Z ----------------
+      const int sup = cluster_id + it * num_clusters;
+      const int64_t n = ((int64_t)2 * sup + rank) * kBM + row;
+      const float rowvalid = n < p.N ? 1.0f : 0.0f;
+      mbar_wait_cl_sleep(smem_u32(&misc->z_full), it & 1, 32);
+      tc_fence_after();
+      if (tthread && it < 8) p.tim[it * 16 + 8] = clock64();
+      float rsum = 0.0f, lls0 = 0.0f, lls1 = 0.0f;
+      // plain: every row of the tile is a real observation and every sample of this column quarter has weight 1
+      // (the common case: ExclusiveKL away from the last tile) -> no per-element masking / weighting
+      const bool plain = p.uniform_w && (64 * k + 64 <= p.S) && (((int64_t)2 * sup + rank) * kBM + kBM <= p.N);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = 64 * k + 32 * c;
+        float v[32];
+        tmem_ld32(lane_addr + col0, v);
+        uint32_t packed[16];
+        float spsum = 0.0f;
+        if (plain) {
+          if (p.ll_total_only) link_chunk<true, false>(v, packed, spsum, rsum, 1.0f, 1.0f);
+          else link_chunk<true, true>(v, packed, spsum, rsum, 1.0f, 1.0f);
+        } else {
+          const float wl = __ldg(p.w + col0 + lane);                       // lane i holds the weight of column col0 + i
+          if (p.ll_total_only) link_chunk<false, false>(v, packed, spsum, rsum, wl, rowvalid);
+          else link_chunk<false, true>(v, packed, spsum, rsum, wl, rowvalid);
+        }
+        {   // R tile: K-group k (64 samples, 16 KB), row-major 128-byte rows, 128-byte swizzle
+          uint8_t* rowp = rtile + k * 16384 + row * 128;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int chunk = (4 * c + u) ^ (row & 7);
+            *reinterpret_cast<uint4*>(rowp + chunk * 16) =
+                make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
+          }
+        }
+        if (p.ll_total_only) {
+          lls0 += spsum;
+        } else {
+          // column sums of softplus over this warp's 32 rows (transpose-reduce): lane l ends with column l
+#pragma unroll
+          for (int o = 16, cnt = 16; o >= 1; o >>= 1, cnt >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < cnt; ++i) {
+              const float send = up ? v[i] : v[i + cnt];
+              const float keep = up ? v[i + cnt] : v[i];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          lls0 += c == 0 ? v[0] : 0.0f;            // static registers: a dynamically indexed array would live in local memory
+          lls1 += c == 1 ? v[0] : 0.0f;
+        }
+      }
+      ll_acc[0] += (double)lls0;
+      ll_acc[1] += (double)lls1;
+      if (tthread && it < 8) p.tim[it * 16 + 6] = clock64();
+      float* rbl = &misc->rb[it & 1][128 * rank + row];
+      if (grad && k == 0) *rbl = rsum;             // row sums of R: quarter 0 stores, the others add
+      fence_proxy_async();       // R tile writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      epi1_barrier();
+      // Z has been read and R written by this CTA: the leader may start the next GEMM1 (critical path) ...
+      if (threadIdx.x == 64) mbar_arrive_cluster(r_full_leader);
+      if (tthread && it < 8) p.tim[it * 16 + 7] = clock64();
+      // ... while the row sums go into BOTH CTAs' rb (E2 of either CTA sweeps all 256 rows; needed later)
+      if (grad) {
+        if (k != 0) atomicAdd(rbl, rsum);
+        epi1_barrier();
+        if (k == 0) st_cluster_f32(mapa_u32(smem_u32(rbl), rank ^ 1), *rbl);
+        epi1_barrier();          // CTA-scope ordering of the stores before the (cumulative) cluster-scope release below
+        if (threadIdx.x == 64) {
+          mbar_arrive_cluster(rbf_own);
+          mbar_arrive_cluster(rbf_peer);
+        }
+      }
+      if (tthread && it < 8) p.tim[it * 16 + 9] = clock64();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp >= 2) {
+    // -------- per-CTA partials (every MMA has completed: the R tile is free scratch) --------
+    const int ew = warp - 2, q = warp & 3, k = ew >> 2;
+    const int row = 32 * q + lane;
+    double (*red)[kBM] = reinterpret_cast<double (*)[kBM]>(rtile);       // [4][128] doubles
+    if (p.ll_total_only) {
+      double tot = ll_acc[0];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      if (lane == 0) red[0][ew] = tot;
+      epi1_barrier();
+      double sum = 0.0;
+      for (int i = 0; i < 16; ++i) sum += red[0][i];
+      // padded sample columns (theta = 0) each contributed softplus(0) = ln2 (as computed in fp32) per valid row
+      int64_t rows = 0;
+      for (int it = 0; it < nIter; ++it) {
+        const int64_t left = p.N - ((int64_t)2 * (cluster_id + it * num_clusters) + rank) * kBM;
+        rows += left <= 0 ? 0 : (left < kBM ? left : kBM);
+      }
+      sum -= (double)(kSP - p.S) * (double)rows * (double)(1.0f * 0.6931471805599453f);
+      if (threadIdx.x - 64 < kSP) p.ll_part[(size_t)blockIdx.x * kSP + (threadIdx.x - 64)] = sum / (double)p.S;
+    } else {
+      // lane l of (q,k) holds column 64k + 32c + l summed over the rows of quarter q -> sum the 4 quarters
+      for (int c = 0; c < 2; ++c) {
+        epi1_barrier();
+        if (q != 0) red[k][(q - 1) * 32 + lane] = ll_acc[c];
+        epi1_barrier();
+        if (q == 0) {
+          const double sum = ll_acc[c] + red[k][lane] + red[k][32 + lane] + red[k][64 + lane];
+          p.ll_part[(size_t)blockIdx.x * kSP + 64 * k + 32 * c + lane] = sum;
+        }
+      }
+    }
+    if (grad) {
+      // the four warps that share a lane quarter swept different tile rows of the same columns j
+      for (int jbp = 0; jbp < JBP; ++jbp) {
+        for (int which = 0; which < 2; ++which) {
+          epi1_barrier();
+          if (k != 0) red[k][row] = which ? gmu_acc[jbp & 7] : ge_acc[jbp & 7];
+          epi1_barrier();
+          if (k == 0) {
+            const double sum = (which ? gmu_acc[jbp & 7] : ge_acc[jbp & 7]) + red[1][row] + red[2][row] + red[3][row];
+            const size_t o = (size_t)cluster_id * p.d_pad + jbp * 256 + 128 * rank + row;
+            (which ? p.gmu_part : p.ge_part)[o] = sum;
+          }
+        }
+      }
+    }
+  }
+  cluster_sync_all();                      // no CTA leaves while its pair may still touch its shared memory / TMEM
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+}
+
 // ---- operand preparation ------------------------------------------------------------------------
-// Xy = y*X split into fp16 hi + lo, written tile-transposed: Xt[(tile*d_pad + j)*128 + (n % 128)]
+// Xy = y*X split into fp16 hi + lo, written tile-transposed: Xt[((tile*2 + half)*d_pad + j)*64 + (n % 64)]
 __global__ void fast_prepare_x_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ y, int64_t N,
                                       int d, int64_t numTiles, int d_pad, __half* __restrict__ Xh, __half* __restrict__ Xl,
                                       float* __restrict__ absmax) {
@@ -582,7 +1175,7 @@ __global__ void fast_prepare_x_kernel(const double* __restrict__ X, int64_t ldx,
       const int j = jblk * 32 + r;
       const float v = tile[tx][r];
       const __half hi = __float2half_rn(v);
-      const size_t o = ((size_t)t * d_pad + j) * 128 + nblk * 32 + tx;
+      const size_t o = (((size_t)t * 2 + (nblk >> 1)) * d_pad + j) * 64 + (nblk & 1) * 32 + tx;
       Xh[o] = hi;
       Xl[o] = __float2half_rn(v - __half2float(hi));
     }
@@ -592,7 +1185,7 @@ __global__ void fast_prepare_x_kernel(const double* __restrict__ X, int64_t ldx,
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(absmax), __float_as_int(mx));
 }
 
-// Theta^T hi/lo [d_pad][256], E [256][d_pad] (fp16) and weights, zero padded
+// Theta^T hi/lo [4][d_pad][64], E [d_pad/64][256][64] (fp16) and weights, zero padded
 __global__ void fast_prepare_theta_kernel(const double* __restrict__ theta, const double* __restrict__ base,
                                           const double* __restrict__ w, int64_t S, int d, int d_pad,
                                           __half* __restrict__ Th, __half* __restrict__ Tl, __half* __restrict__ E,
@@ -604,7 +1197,7 @@ __global__ void fast_prepare_theta_kernel(const double* __restrict__ theta, cons
       const int j = (int)(i - s * d_pad);
       float e = 0.0f;
       if (base && s < S && j < d) e = (float)base[s * d + j];
-      E[i] = __float2half_rn(e);
+      E[((size_t)(j >> 6) * kSP + s) * 64 + (j & 63)] = __float2half_rn(e);
     }
     {   // Theta^T: [j][s]
       const int j = (int)(i / kSP);
@@ -612,8 +1205,9 @@ __global__ void fast_prepare_theta_kernel(const double* __restrict__ theta, cons
       float t = 0.0f;
       if (s < S && j < d) t = (float)theta[s * d + j];
       const __half hi = __float2half_rn(t);
-      Th[i] = hi;
-      Tl[i] = __float2half_rn(t - __half2float(hi));
+      const size_t o = ((size_t)(s >> 6) * d_pad + j) * 64 + (s & 63);
+      Th[o] = hi;
+      Tl[o] = __float2half_rn(t - __half2float(hi));
     }
   }
   for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < kSP; s += (int64_t)gridDim.x * blockDim.x)
@@ -646,18 +1240,30 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D fp16 row-major [rows][cols] tensor, box = [box_rows][64 cols] (128-byte rows), 128-byte swizzle
-static bool encode_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// fp16 tensor of 128-byte rows (innermost dimension 64), 128-byte swizzle.  dims/box are innermost first;
+// strides (bytes) are those of dims[1..rank-1].
+static bool encode_nd(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                      const uint32_t* box) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {64, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) gs[i] = strides[i];
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+// 2-D view [rows][64] with a [box_rows][64] box (the one-CTA kernel)
+static bool encode_2d(CUtensorMap* map, const void* base, uint64_t rows, uint32_t box_rows) {
+  const uint64_t dims[2] = {64, rows}, strides[1] = {128};
+  const uint32_t box[2] = {64, box_rows};
+  return encode_nd(map, base, 2, dims, strides, box);
 }
 
 struct FastModel {
@@ -665,7 +1271,8 @@ struct FastModel {
   int d, d_pad;
   const __half* Xh;
   const __half* Xl;
-  CUtensorMap tmXh, tmXl, tmXh2, tmXl2;
+  CUtensorMap tmXh, tmXl, tmXh2, tmXl2;      // one-CTA kernel: 2-D views
+  CUtensorMap tmXP;                          // pair kernel: 5-D [hi|lo][tile][half][j][64]
 };
 
 struct FastLayout {
@@ -676,7 +1283,8 @@ struct FastLayout {
 static void fast_layout(int64_t N, int d_pad, FastLayout& L) {
   const int64_t tiles = ceil_div(N, kBM);
   int sms = sm_count();
-  L.grid = (int)(tiles < sms ? (tiles > 0 ? tiles : 1) : sms);
+  const int64_t ctas = ceil_div(tiles, 2) * 2;                  // the pair kernel runs two CTAs per 256-row super-tile
+  L.grid = (int)(ctas < sms ? (ctas > 1 ? ctas : 2) : sms);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
   L.off_Th = take((size_t)kSP * d_pad * 2);
@@ -697,15 +1305,15 @@ using namespace vb::fast;
 
 extern "C" size_t vb_glm_fast_model_bytes(int64_t N, int d) {
   if (N <= 0 || d <= 0) return 0;
-  const int64_t N_pad = ceil_div(N, kBM) * kBM;
-  const int64_t d_pad = ceil_div(d, 128) * 128;
+  const int64_t N_pad = ceil_div(N, 2 * kBM) * 2 * kBM;        // whole 256-row super-tiles (CTA pairs)
+  const int64_t d_pad = ceil_div(d, 256) * 256;
   return (size_t)(2 * N_pad * d_pad * 2) + 1024;
 }
 
 extern "C" size_t vb_glm_fast_workspace_bytes(int64_t N, int d, int64_t S) {
   if (N <= 0 || d <= 0 || S <= 0 || S > kSP) return 0;
   FastLayout L;
-  fast_layout(N, (int)(ceil_div(d, 128) * 128), L);
+  fast_layout(N, (int)(ceil_div(d, 256) * 256), L);
   return L.total;
 }
 
@@ -722,8 +1330,8 @@ extern "C" int vb_glm_fast_create(void** handle, const double* X, int64_t ldx, c
   FastModel* m = new FastModel();
   m->N = N;
   m->d = d;
-  m->numTiles = ceil_div(N, kBM);
-  m->d_pad = (int)(ceil_div(d, 128) * 128);
+  m->numTiles = ceil_div(N, 2 * kBM) * 2;                       // even: the pair kernel works on super-tiles
+  m->d_pad = (int)(ceil_div(d, 256) * 256);
   const size_t elems = (size_t)m->numTiles * kBM * m->d_pad;
   __half* Xh = static_cast<__half*>(model_mem);
   __half* Xl = Xh + elems;
@@ -744,9 +1352,12 @@ extern "C" int vb_glm_fast_create(void** handle, const double* X, int64_t ldx, c
       return set_error(VB_ERR_UNSUPPORTED, "glm_fast: |y*X| exceeds the fp16 operand range; use the float64 path");
     }
   }
-  const uint64_t rows = (uint64_t)m->numTiles * m->d_pad;
-  if (!encode_2d(&m->tmXh, Xh, rows, 128, 32) || !encode_2d(&m->tmXl, Xl, rows, 128, 32) ||
-      !encode_2d(&m->tmXh2, Xh, rows, 128, 64) || !encode_2d(&m->tmXl2, Xl, rows, 128, 64)) {
+  const uint64_t rows = (uint64_t)m->numTiles * 2 * m->d_pad;
+  const uint64_t xd[5] = {64, (uint64_t)m->d_pad, 2, (uint64_t)m->numTiles, 2};
+  const uint64_t xs[4] = {128, (uint64_t)m->d_pad * 128, (uint64_t)m->d_pad * 256, (uint64_t)elems * 2};
+  const uint32_t xb[5] = {64, 32, 2, 1, 2};
+  if (!encode_2d(&m->tmXh, Xh, rows, 32) || !encode_2d(&m->tmXl, Xl, rows, 32) || !encode_2d(&m->tmXh2, Xh, rows, 64) ||
+      !encode_2d(&m->tmXl2, Xl, rows, 64) || !encode_nd(&m->tmXP, Xh, 5, xd, xs, xb)) {
     delete m;
     return set_error(VB_ERR_CUDA, "glm_fast_create: cuTensorMapEncodeTiled failed");
   }
@@ -783,10 +1394,17 @@ extern "C" int vb_glm_fast_sweep(void* handle, const double* theta, const double
 
   static thread_local const void* cached_ws = nullptr;
   static thread_local int cached_dpad = 0;
-  static thread_local CUtensorMap tmTh, tmTl, tmE;
+  static thread_local CUtensorMap tmTh, tmTl, tmE, tmTP, tmEP;
   if (cached_ws != workspace || cached_dpad != m->d_pad) {
-    if (!encode_2d(&tmTh, Th, m->d_pad, kSP, 32) || !encode_2d(&tmTl, Tl, m->d_pad, kSP, 32) ||
-        !encode_2d(&tmE, E, kSP, m->d_pad, 64))
+    const uint64_t dp = (uint64_t)m->d_pad;
+    const uint64_t td[4] = {64, dp, 4, 2}, ts[3] = {128, dp * 128, dp * 512};      // Tl follows Th
+    const uint32_t tb[4] = {64, 32, 2, 2};
+    const uint64_t ed[3] = {64, (uint64_t)kSP, dp / 64}, es[2] = {128, (uint64_t)kSP * 128};
+    const uint32_t eb[3] = {64, 64, 2};
+    if (reinterpret_cast<char*>(Tl) - reinterpret_cast<char*>(Th) != (ptrdiff_t)(dp * 512))
+      return set_error(VB_ERR_CUDA, "glm_fast_sweep: Theta hi/lo are not adjacent");
+    if (!encode_2d(&tmTh, Th, 4 * dp, 32) || !encode_2d(&tmTl, Tl, 4 * dp, 32) || !encode_2d(&tmE, E, (dp / 64) * kSP, 64) ||
+        !encode_nd(&tmTP, Th, 4, td, ts, tb) || !encode_nd(&tmEP, E, 3, ed, es, eb))
       return set_error(VB_ERR_CUDA, "glm_fast_sweep: cuTensorMapEncodeTiled failed");
     cached_ws = workspace;
     cached_dpad = m->d_pad;
@@ -808,20 +1426,68 @@ extern "C" int vb_glm_fast_sweep(void* handle, const double* theta, const double
   p.ge_part = reinterpret_cast<double*>(ws + L.off_ge);
   p.dbg = debug;
   p.tim = debug ? reinterpret_cast<long long*>(debug + (size_t)49152 * L.grid) : nullptr;
-  static bool attr_set = false;
-  if (!attr_set) {
+  p.Xh = m->Xh;
+  p.Xl = m->Xl;
+  p.uniform_w = w ? 0 : 1;
+  // kernel choice: the CTA-pair kernel unless the device cannot co-schedule clusters of two such CTAs
+  // (VB_FAST_KERNEL=single forces the one-CTA kernel, for A/B measurements)
+  static int pair_clusters = -1;
+  if (pair_clusters < 0) {
     VB_CUDA(cudaFuncSetAttribute(glm_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
+    VB_CUDA(cudaFuncSetAttribute(glm_fast_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    const char* env = getenv("VB_FAST_KERNEL");
+    int nc = 0;
+    if (!(env && strcmp(env, "single") == 0)) {
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(sm_count() & ~1);
+      qc.blockDim = dim3(kThreadsP);
+      qc.dynamicSmemBytes = kSmemBytes;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa;
+      qc.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&nc, glm_fast_pair_kernel, &qc) != cudaSuccess) {
+        cudaGetLastError();
+        nc = 0;
+      }
+    }
+    pair_clusters = nc;
   }
-  glm_fast_kernel<<<L.grid, kThreads, kSmemBytes, stream>>>(m->tmXh, m->tmXl, m->tmXh2, m->tmXl2, tmTh, tmTl, tmE, p);
-  VB_CHECK_LAUNCH();
+  int nblk_ll = L.grid, nblk_g = L.grid;
+  if (pair_clusters > 0) {
+    const int64_t numSuper = m->numTiles / 2;
+    int clusters = pair_clusters < L.grid / 2 ? pair_clusters : L.grid / 2;
+    if (clusters < 1) clusters = 1;
+    if (numSuper < clusters) clusters = (int)numSuper;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreadsP);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    VB_CUDA(cudaLaunchKernelEx(&cfg, glm_fast_pair_kernel, m->tmXP, tmTP, tmEP, p));
+    nblk_ll = 2 * clusters;
+    nblk_g = clusters;              // one row of gradient partials per pair (a CTA owns half of the columns)
+  } else {
+    glm_fast_kernel<<<L.grid, kThreads, kSmemBytes, stream>>>(m->tmXh, m->tmXl, m->tmXh2, m->tmXl2, tmTh, tmTl, tmE, p);
+    VB_CHECK_LAUNCH();
+  }
   // ll = -sum softplus
-  reduce_partials_kernel<<<1, 256, 0, stream>>>(p.ll_part, L.grid, kSP, S, -1.0, out_ll);
+  reduce_partials_kernel<<<1, 256, 0, stream>>>(p.ll_part, nblk_ll, kSP, S, -1.0, out_ll);
   VB_CHECK_LAUNCH();
   if (want_grad) {
-    reduce_partials_kernel<<<(m->d + 255) / 256, 256, 0, stream>>>(p.gmu_part, L.grid, m->d_pad, m->d, 1.0, out_gmu);
+    reduce_partials_kernel<<<(m->d + 255) / 256, 256, 0, stream>>>(p.gmu_part, nblk_g, m->d_pad, m->d, 1.0, out_gmu);
     VB_CHECK_LAUNCH();
-    reduce_partials_kernel<<<(m->d + 255) / 256, 256, 0, stream>>>(p.ge_part, L.grid, m->d_pad, m->d, 1.0, out_ge);
+    reduce_partials_kernel<<<(m->d + 255) / 256, 256, 0, stream>>>(p.ge_part, nblk_g, m->d_pad, m->d, 1.0, out_ge);
     VB_CHECK_LAUNCH();
   }
   return VB_OK;
