@@ -696,7 +696,7 @@ static_assert(sizeof(MiscP) <= kMiscBytes, "misc smem overflow");
 
 __device__ __forceinline__ void epi1_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ void ldg256(const void* ptr, uint32_t* r) {
-  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "l"(ptr));
 }
@@ -760,7 +760,8 @@ __device__ __forceinline__ void link_chunk(float (&v)[32], uint32_t (&packed)[16
 
 // Fill sequence of iteration i (identical in every role and in both CTAs; `fill` counts 16 KB slots):
 //   for kc in 0..KC-1:  slot A = X (hi n0 | hi n1 | lo n0 | lo n1), slot B = Theta_lo (2 groups) | Theta_hi (2 groups)
-//       after the stages with (kc & 7) == 3 (and i > 0): GEMM2 group jbp = kc >> 3 of super-tile i-1: 4 slots of E
+//       after the stages with (kc & 7) == 1 (and i > 0): the 4 E slots of GEMM2 group jbp = kc >> 3 of super-tile i-1,
+//       consumed after stage (kc & 7) == 3
 //   a last iteration i = nIter only carries the GEMM2 groups of the final super-tile.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP, 1)
 glm_fast_pair_kernel(const __grid_constant__ CUtensorMap tmX,      // 5-D: [hi|lo][tile][half][j][64 n]
@@ -843,7 +844,7 @@ glm_fast_pair_kernel(const __grid_constant__ CUtensorMap tmX,      // 5-D: [hi|l
             tma_load_5d_pair(dst, &tmX, 0, j0, 0, tile, 0, bar);         // hi n0 | hi n1 | lo n0 | lo n1: 16 KB
             dst = acquire();
             tma_load_4d_pair(dst, &tmT, 0, j0, 2 * (int)rank, 0, bar);   // Theta_hi g0 | g1 | Theta_lo g0 | g1 (this CTA's half)
-            if (grad && it > 0 && (kc & 7) == 3) g2_fills(kc >> 3);
+            if (grad && it > 0 && (kc & 7) == 1) g2_fills(kc >> 3);     // two stages ahead of the group that consumes them
           }
         } else if (grad && it > 0) {
           for (int jbp = 0; jbp < JBP; ++jbp) g2_fills(jbp);
@@ -858,14 +859,14 @@ glm_fast_pair_kernel(const __grid_constant__ CUtensorMap tmX,      // 5-D: [hi|l
       uint32_t fill = 0, sc = 0, ec = 0, gc = 0;
       long long w_g1 = 0, w_e = 0, w_t = 0;
       const bool timing = p.tim && blockIdx.x == 0;
+      uint32_t e_base = 0;                  // first of the 4 ring slots holding the E slices of the pending group
       auto g2_group = [&]() {
         long long c0 = timing ? clock64() : 0;
         mbar_wait_cl(smem_u32(&misc->t_empty), (gc & 1) ^ 1);      // both CTAs' E2 have drained the previous group
         if (timing) w_t += clock64() - c0;
         ++gc;
         for (int g = 0; g < 4; ++g, ++ec) {
-          const uint32_t slot = fill % kNumSlots;
-          ++fill;
+          const uint32_t slot = (e_base + g) % kNumSlots;
           c0 = timing ? clock64() : 0;
           mbar_wait_cl(smem_u32(&misc->e_full[ec & 15]), (ec >> 4) & 1);
           if (timing) w_e += clock64() - c0;
@@ -917,10 +918,18 @@ glm_fast_pair_kernel(const __grid_constant__ CUtensorMap tmX,      // 5-D: [hi|l
               if (kc == KC - 1) umma_commit_pair(smem_u32(&misc->z_full));
             }
             __syncwarp();
+            if (grad && it > 0 && (kc & 7) == 1) {      // the E slices were filled here, two stages ahead
+              e_base = fill;
+              fill += 4;
+            }
             if (grad && it > 0 && (kc & 7) == 3) g2_group();
           }
         } else if (grad && it > 0) {
-          for (int jbp = 0; jbp < JBP; ++jbp) g2_group();
+          for (int jbp = 0; jbp < JBP; ++jbp) {
+            e_base = fill;
+            fill += 4;
+            g2_group();
+          }
         }
         if (timing && it < 8 && lane == 0) {
           p.tim[it * 16 + 2] = clock64();
