@@ -380,7 +380,7 @@ def run_b200(args):
         'metric': 'elbo_grad_iters_per_sec', 'value': 1e3 / ms_per_step, 'unit': 'iter/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-        'dtype': 'f64' if path == 'f64' else 'bf16x2-split/f32',
+        'dtype': 'f64' if path == 'f64' else 'f16x2-split/f32',
         'data': 'synthetic',
         'config': {'workload': 'bayes-logistic N=%d d=%d S=%d MFGaussian+RMSProp (BASELINE configs[1])' % (N, d, S),
                    'path': path, 'rows_per_rank': hi - lo, 'l2': 'inputs larger than L2 (X = %.2f GB per rank)'

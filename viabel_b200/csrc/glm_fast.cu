@@ -1223,12 +1223,35 @@ __global__ void fast_prepare_theta_kernel(const double* __restrict__ theta, cons
     wf[s] = s < S ? (w ? (float)w[s] : 1.0f) : 0.0f;
 }
 
-__global__ void reduce_partials_kernel(const double* __restrict__ part, int nblk, int64_t stride, int64_t n,
-                                       double sign, double* __restrict__ out) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double s = 0.0;
-    for (int b = 0; b < nblk; ++b) s += part[(size_t)b * stride + i];
-    out[i] = sign * s;
+// out[i] = sign * sum_b part[b][i] for up to three arrays in one launch (blockIdx.y selects the array):
+// 32 columns x 8 row groups per block, coalesced 256-byte row reads, shared-memory reduction over the groups
+struct Reduce3 {
+  const double* part[3];
+  double* out[3];
+  int nblk[3];
+  int64_t stride[3], n[3];
+  double sign[3];
+};
+__global__ void __launch_bounds__(256) reduce_partials3_kernel(Reduce3 a) {
+  __shared__ double sm[8][33];
+  const int which = blockIdx.y;
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + x;
+  const int64_t n = a.n[which];
+  if ((int64_t)blockIdx.x * 32 >= n) return;
+  double acc = 0.0;
+  if (i < n) {
+    const double* p = a.part[which] + i;
+    const int64_t stride = a.stride[which];
+    for (int b = y; b < a.nblk[which]; b += 8) acc += p[(size_t)b * stride];
+  }
+  sm[y][x] = acc;
+  __syncthreads();
+  if (y == 0 && i < n) {
+    double t = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += sm[r][x];
+    a.out[which][i] = a.sign[which] * t;
   }
 }
 
@@ -1490,14 +1513,13 @@ extern "C" int vb_glm_fast_sweep(void* handle, const double* theta, const double
     glm_fast_kernel<<<L.grid, kThreads, kSmemBytes, stream>>>(m->tmXh, m->tmXl, m->tmXh2, m->tmXl2, tmTh, tmTl, tmE, p);
     VB_CHECK_LAUNCH();
   }
-  // ll = -sum softplus
-  reduce_partials_kernel<<<1, 256, 0, stream>>>(p.ll_part, nblk_ll, kSP, S, -1.0, out_ll);
+  // ll = -sum softplus; gradient partials summed over the pairs -- one launch for the three arrays
+  Reduce3 r;
+  r.part[0] = p.ll_part;  r.out[0] = out_ll;  r.nblk[0] = nblk_ll; r.stride[0] = kSP;      r.n[0] = S;                    r.sign[0] = -1.0;
+  r.part[1] = p.gmu_part; r.out[1] = out_gmu; r.nblk[1] = nblk_g;  r.stride[1] = m->d_pad; r.n[1] = want_grad ? m->d : 0; r.sign[1] = 1.0;
+  r.part[2] = p.ge_part;  r.out[2] = out_ge;  r.nblk[2] = nblk_g;  r.stride[2] = m->d_pad; r.n[2] = want_grad ? m->d : 0; r.sign[2] = 1.0;
+  const int64_t nmax = want_grad && m->d > S ? m->d : S;
+  reduce_partials3_kernel<<<dim3((unsigned)((nmax + 31) / 32), want_grad ? 3 : 1), 256, 0, stream>>>(r);
   VB_CHECK_LAUNCH();
-  if (want_grad) {
-    reduce_partials_kernel<<<(m->d + 255) / 256, 256, 0, stream>>>(p.gmu_part, nblk_g, m->d_pad, m->d, 1.0, out_gmu);
-    VB_CHECK_LAUNCH();
-    reduce_partials_kernel<<<(m->d + 255) / 256, 256, 0, stream>>>(p.ge_part, nblk_g, m->d_pad, m->d, 1.0, out_ge);
-    VB_CHECK_LAUNCH();
-  }
   return VB_OK;
 }

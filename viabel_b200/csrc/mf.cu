@@ -98,60 +98,73 @@ __global__ void alpha_weights_kernel(const double* __restrict__ lw, int64_t S, d
 }
 
 // value for ExclusiveKL (entropy or path-derivative form) + per-sample model log density
-__global__ void mf_value_kernel(const double* __restrict__ vp, const double* __restrict__ theta,
-                                const double* __restrict__ base, const double* __restrict__ ll, int64_t S,
-                                int d, int family, double df, double tconst, double inv_tau2,
-                                double prior_const, int objective, double* __restrict__ value,
-                                double* __restrict__ logp) {
+__global__ void __launch_bounds__(256) mf_value_kernel(const double* __restrict__ vp, const double* __restrict__ theta,
+                                                       const double* __restrict__ base, const double* __restrict__ ll,
+                                                       int64_t S, int d, int family, double df, double tconst,
+                                                       double inv_tau2, double prior_const, int objective,
+                                                       double* __restrict__ value, double* __restrict__ logp) {
+  // one warp per sample, 8 samples per block; value[0] (zeroed by the caller) receives every block's share
   __shared__ double red[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool path = objective == VB_OBJ_EXCLUSIVE_KL_PATH;
   double acc = 0.0;
-  for (int64_t s = warp; s < S; s += nw) {
+  const int64_t s = (int64_t)blockIdx.x * 8 + warp;
+  if (s < S) {
     double prior, logq;
     sample_terms(vp, theta, base, s, d, family, df, tconst, inv_tau2, prior_const, path, lane, prior, logq);
     const double f = ll[s] + prior;
     if (lane == 0) {
       if (logp) logp[s] = f;
-      acc += path ? (f - logq) : f;
+      acc = path ? (f - logq) : f;
     }
   }
-  acc = block_sum(acc, red);
   if (objective == VB_OBJ_ALPHA) return;    // value comes from alpha_weights_kernel
+  acc = block_sum(acc, red);
   double H = 0.0;
-  if (!path) {
+  if (blockIdx.x == 0 && !path) {
     for (int j = threadIdx.x; j < d; j += blockDim.x) H += vp[d + j];
     H = block_sum(H, red);
     if (family == VB_FAMILY_MF_GAUSSIAN) H += 0.5 * d * (1.0 + kLog2Pi);   // approximations.py:218-220
   }
-  if (threadIdx.x == 0) value[0] = -(acc / (double)S + H);
+  if (threadIdx.x == 0) atomicAdd(value, -(acc / (double)S + H));
 }
 
-// gradient wrt [mu, log_sigma]; one thread per coordinate j  
-__global__ void mf_grad_kernel(const double* __restrict__ vp, const double* __restrict__ theta,
-                               const double* __restrict__ base, const double* __restrict__ gmu,
-                               const double* __restrict__ ge, const double* __restrict__ w, int64_t S, int d,
-                               int family, double df, double inv_tau2, int objective, double alpha,
-                               double* __restrict__ grad) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= d) return;
+// gradient wrt [mu, log_sigma]  (SURVEY.md App. A.1): block = 32 coordinates x 8 sample groups
+__global__ void __launch_bounds__(256) mf_grad_kernel(const double* __restrict__ vp, const double* __restrict__ theta,
+                                                      const double* __restrict__ base, const double* __restrict__ gmu,
+                                                      const double* __restrict__ ge, const double* __restrict__ w,
+                                                      int64_t S, int d, int family, double df, double inv_tau2,
+                                                      int objective, double alpha, double* __restrict__ grad) {
+  __shared__ double sm[5][8][33];
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + x;
   double p1 = 0.0, p2 = 0.0, pa = 0.0, pb = 0.0, sw = 0.0;
-  for (int64_t s = 0; s < S; ++s) {
-    const double ws = w ? w[s] : 1.0;
-    const double th = theta[s * d + j], e = base[s * d + j];
-    p1 += ws * th;
-    p2 += ws * th * e;
-    sw += ws;
-    if (objective == VB_OBJ_EXCLUSIVE_KL_PATH) {
-      if (family == VB_FAMILY_MF_GAUSSIAN) {
-        pa += e;
-        pb += e * e;
-      } else {
-        const double q = (df + 1.0) / (df + e * e);
-        pa += q * e;
-        pb += q * e * e;
+  if (j < d) {
+    for (int64_t s = y; s < S; s += 8) {
+      const double ws = w ? w[s] : 1.0;
+      const double th = theta[s * d + j], e = base[s * d + j];
+      p1 += ws * th;
+      p2 += ws * th * e;
+      sw += ws;
+      if (objective == VB_OBJ_EXCLUSIVE_KL_PATH) {
+        if (family == VB_FAMILY_MF_GAUSSIAN) {
+          pa += e;
+          pb += e * e;
+        } else {
+          const double q = (df + 1.0) / (df + e * e);
+          pa += q * e;
+          pb += q * e * e;
+        }
       }
     }
+  }
+  sm[0][y][x] = p1; sm[1][y][x] = p2; sm[2][y][x] = pa; sm[3][y][x] = pb; sm[4][y][x] = sw;
+  __syncthreads();
+  if (y != 0 || j >= d) return;
+  p1 = p2 = pa = pb = sw = 0.0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {            // fixed order: deterministic
+    p1 += sm[0][r][x]; p2 += sm[1][r][x]; pa += sm[2][r][x]; pb += sm[3][r][x]; sw += sm[4][r][x];
   }
   const double sig = exp(vp[d + j]);
   const double a = gmu[j] - p1 * inv_tau2;          // sum_s w_s g_s[j]
@@ -258,12 +271,13 @@ extern "C" int vb_mf_objective_finish_f64(const double* var_param, const double*
   if (value || logp) {
     if (objective != VB_OBJ_ALPHA && !value)
       return set_error(VB_ERR_INVALID_ARG, "mf_objective_finish: value is required");
-    mf_value_kernel<<<1, 1024, 0, stream>>>(var_param, theta, base, ll, S, d, family, df, tc, inv_tau2, pc,
-                                            objective, value, logp);
+    if (objective != VB_OBJ_ALPHA) VB_CUDA(cudaMemsetAsync(value, 0, sizeof(double), stream));
+    mf_value_kernel<<<(unsigned)((S + 7) / 8), 256, 0, stream>>>(var_param, theta, base, ll, S, d, family, df, tc, inv_tau2,
+                                                                 pc, objective, value, logp);
     VB_CHECK_LAUNCH();
   }
   if (grad) {
-    mf_grad_kernel<<<(d + 127) / 128, 128, 0, stream>>>(var_param, theta, base, gmu, ge,
+    mf_grad_kernel<<<(d + 31) / 32, 256, 0, stream>>>(var_param, theta, base, gmu, ge,
                                                          objective == VB_OBJ_ALPHA ? w : nullptr, S, d, family,
                                                          df, inv_tau2, objective, alpha, grad);
     VB_CHECK_LAUNCH();
