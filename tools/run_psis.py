@@ -21,3 +21,14 @@ for _ in range(reps):
     _, res, _, _ = vb.psislw_device(lw, out)
 torch.cuda.synchronize()
 print(res.cpu().numpy())
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ts = []
+for _ in range(10):
+    e0.record()
+    vb.psislw_device(lw, out)
+    e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1))
+ts.sort()
+print('psislw n=%d: median %.4f ms  min %.4f ms  -> %.3e draws/s, %.1f%% of 6543.7 GB/s at 24 B/draw'
+      % (n, ts[len(ts) // 2], ts[0], n / ts[len(ts) // 2] * 1e3, 100 * 24.0 * n / ts[len(ts) // 2] * 1e3 / 6543.7e9))

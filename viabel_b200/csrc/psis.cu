@@ -33,6 +33,30 @@ constexpr int kGpdSplit = 8;             // CTAs per quadrature point
 enum { R_KHAT = 0, R_SIGMA, R_N2, R_CUTOFF, R_LSE, R_MAX, R_STATUS, R_SUMV, R_SUMEXP2V, R_M, R_NCAND, R_SMOOTHED,
        R_COUNT = 16 };
 
+// Programmatic dependent launch: every kernel of the short chain between the two streaming passes starts with
+// PDL_SYNC() (wait until the kernels before it in the stream have completed and flushed) followed by a trigger
+// that lets the NEXT kernel's blocks be scheduled while this one runs, so the launch ramps overlap.
+#define PDL_SYNC()                                               \
+  do {                                                           \
+    asm volatile("griddepcontrol.wait;" ::: "memory");           \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  } while (0)
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 struct PsisScalars {           // device-resident control block
   unsigned long long maxkey;   // order-preserving key of the global max
   unsigned long long t0key;    // candidate threshold (key)
@@ -58,6 +82,7 @@ struct PsisScalars {           // device-resident control block
   unsigned int gcount;         // keys gathered from it
   unsigned long long prefix;   // exact-mode radix state
   unsigned long long kth;
+  unsigned int gpd_done;       // blocks of the GPD grid kernel that have finished
 };
 
 __device__ __forceinline__ unsigned long long dkey(double x) {
@@ -69,18 +94,22 @@ __device__ __forceinline__ double dkey_inv(unsigned long long k) {
   return __longlong_as_double((long long)b);
 }
 
-// exp(x) for x <= 0 (to ~1 ulp): x = (32 k + j) ln2/32 + r, exp = 2^k * 2^(j/32) * e^r, |r| <= ln2/64
-__constant__ double c_exp2_tab[32];
+// exp(x) for x <= 0: x = (1024 k + j) ln2/1024 + r, exp = 2^k * 2^(j/1024) * e^r, |r| <= ln2/2048, so a degree-3
+// polynomial is enough (r^4/24 < 5.5e-16 relative, far inside the 1e-10 budget of the log-sum-exp).  The two
+// streaming passes are bound by the FP64 pipe, not by HBM, at ~14 double-precision operations per draw with the
+// textbook 32-entry table: the larger table removes three of them.
+constexpr int kExpTab = 256;
+__device__ double g_exp2_tab[kExpTab];
 // polynomial / reduction constants live in the constant bank so every DFMA takes them as a direct
 // operand (no per-call re-materialisation of 64-bit immediates)
-__constant__ double c_expk[10] = {46.166241308446828384 /* 32/ln2 */, 6755399441055744.0 /* 1.5 * 2^52 */,
-                                  -2.16608493865351192653e-02 /* -ln2_hi/32 */, -5.96317165397058656257e-12 /* -ln2_lo/32 */,
-                                  1.3888888888888889e-03, 8.3333333333333332e-03, 4.1666666666666664e-02,
-                                  1.6666666666666666e-01, 0.5, 8.6736173798840355e-19 /* 2^-60 */};
-// `tab` is the 32-bit shared-memory address of a per-CTA copy of c_exp2_tab (per-lane indices would
-// serialise on the constant cache)
+__constant__ double c_expk[8] = {369.3299304675746322841407 /* 256/ln2 */, 6755399441055744.0 /* 1.5 * 2^52 */,
+                                 -2.7076061733168899081640625e-03 /* -ln2_hi/256 */,
+                                 -7.453964567463233203203125e-13 /* -ln2_lo/256 */,
+                                 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 0.0};
+// `tab` is the 32-bit shared-memory address of a per-CTA copy of the table (per-lane indices would serialise on the
+// constant cache; shared memory serves them at full rate)
 __device__ __forceinline__ uint32_t load_exp_table(double* tab) {
-  if (threadIdx.x < 32) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+  for (int i = threadIdx.x; i < kExpTab; i += blockDim.x) tab[i] = g_exp2_tab[i];
   __syncthreads();
   return (uint32_t)__cvta_generic_to_shared(tab);
 }
@@ -93,14 +122,12 @@ __device__ __forceinline__ double exp_nonpos(double x, uint32_t tab) {
   double p = c_expk[4];
   p = fma(p, r, c_expk[5]);
   p = fma(p, r, c_expk[6]);
-  p = fma(p, r, c_expk[7]);
-  p = fma(p, r, c_expk[8]);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-  const int k = n >> 5;
+  const int k = n >> 8;
   double tj;
-  asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab + ((uint32_t)(n & 31) << 3)));
-  const double v = p * tj;                           // in [1, 2.05)
+  asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab + ((uint32_t)(n & (kExpTab - 1)) << 3)));
+  const double v = p * tj;                           // in [1, 2.001)
   const double res = __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
   // x <= -707.75 (incl. -inf): the result would be subnormal (< 2^-1021).  Every sum these terms enter is
   // >= 1 (it contains exp(0) for the maximum), so they are below half an ulp of it: flushed to zero.
@@ -180,6 +207,7 @@ __device__ unsigned long long cta_select_kth_largest(const unsigned long long* k
 __global__ void psis_init_kernel(PsisScalars* sc, int M, unsigned int* hist, unsigned int* vhist) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     sc->maxkey = 0; sc->t0key = 0; sc->cutkey = 0; sc->ncand = 0; sc->ntail = 0; sc->status = 0; sc->strict = 0;
+    sc->gpd_done = 0;
     sc->t0 = -INFINITY; sc->maxv = 0; sc->cutoff = 0; sc->expcut = 0; sc->body_below = 0; sc->body_cand = 0;
     sc->tail_sum = 0; sc->k = INFINITY; sc->sigma = 0; sc->lse = 0; sc->bhat = 0; sc->sumv = 0; sc->sumexp2v = 0;
     sc->vscale = 0; sc->smoothed = 0; sc->M = M; sc->shift = 0; sc->bstar = 0; sc->need = 0; sc->members = 0; sc->gcount = 0; sc->prefix = 0; sc->kth = 0;
@@ -252,14 +280,14 @@ __global__ void __launch_bounds__(kSelThreads) psis_sample_select_kernel(const d
 // sum exp(x - t0) over everything below the threshold.  Candidates are staged per warp in shared
 // memory and flushed with ONE global atomic per CTA (same-address atomics with a return value
 // serialise at ~2 ns each in L2: one per candidate-bearing warp iteration cost more than the HBM pass).
-constexpr int kStage = 160;     // per-warp staging entries (>= 4 * 32)
+constexpr int kStage = 64;      // per-warp staging entries (>= 2 * 32: every push of up to 32 candidates checks for room)
 __global__ void __launch_bounds__(256) psis_pass_a_kernel(const double* __restrict__ lw, int64_t n, int64_t idx_off,
                                                           PsisScalars* sc, double* __restrict__ cand_x,
                                                           int64_t* __restrict__ cand_i, unsigned int cap,
                                                           double* __restrict__ blk_sum) {
   __shared__ double red[32];
   __shared__ unsigned long long redk[32];
-  __shared__ double etab_s[32];
+  __shared__ double etab_s[kExpTab];
   __shared__ double sx[8][kStage];
   __shared__ long long si[8][kStage];
   __shared__ unsigned int wcnt[8], cta_base;
@@ -326,10 +354,13 @@ __global__ void __launch_bounds__(256) psis_pass_a_kernel(const double* __restri
       acc0 += (c0 ? 0.0 : e0) + (c2 ? 0.0 : e2);
       acc1 += (c1 ? 0.0 : e1) + (c3 ? 0.0 : e3);
       if (__any_sync(0xffffffffu, c0 | c1 | c2 | c3)) {
-        if (staged + 128 > kStage) flush_warp();
+        if (staged + 32 > kStage) flush_warp();
         push(a.x, 4 * q, c0);
+        if (staged + 32 > kStage) flush_warp();
         push(a.y, 4 * q + 1, c1);
+        if (staged + 32 > kStage) flush_warp();
         push(b.x, 4 * q + 2, c2);
+        if (staged + 32 > kStage) flush_warp();
         push(b.y, 4 * q + 3, c3);
       }
     }
@@ -401,6 +432,7 @@ __device__ __forceinline__ double cand_scale(const PsisScalars* sc, double& lo) 
 
 __global__ void __launch_bounds__(256) psis_cand_hist_kernel(PsisScalars* sc, const double* __restrict__ cand_x,
                                                              unsigned int cap, unsigned int* __restrict__ ghist) {
+  PDL_SYNC();
   __shared__ unsigned int hist[kBins];
   const unsigned int C = sc->ncand;
   if (sc->strict || C > cap || C < (unsigned)(sc->M + 1)) return;
@@ -425,6 +457,7 @@ __global__ void __launch_bounds__(256) psis_cand_hist_kernel(PsisScalars* sc, co
 __global__ void __launch_bounds__(kSelThreads) psis_cand_gather_kernel(PsisScalars* sc, const double* __restrict__ cand_x,
                                                                         unsigned int cap, const unsigned int* __restrict__ ghist,
                                                                         unsigned long long* __restrict__ gbuf) {
+  PDL_SYNC();
   __shared__ unsigned int hist[kBins];
   __shared__ unsigned long long sh[2];
   __shared__ unsigned int wtot[32];
@@ -455,6 +488,7 @@ __global__ void __launch_bounds__(kSelThreads) psis_cand_gather_kernel(PsisScala
 __global__ void __launch_bounds__(kSelThreads) psis_cutoff_kernel(PsisScalars* sc, const double* __restrict__ cand_x,
                                                                    unsigned int cap, const unsigned long long* __restrict__ gbuf,
                                                                    const double* __restrict__ blk_sum, int nblk) {
+  PDL_SYNC();
   __shared__ unsigned int hist[kBins];
   __shared__ unsigned long long sh[2];
   __shared__ unsigned int wtot[32];
@@ -534,6 +568,7 @@ __device__ __forceinline__ int vbin(double v, double cutoff, double vscale) {
 // tail membership (shifted value > cutoff), per-bin tail counts, LSE contribution of the other candidates
 __global__ void __launch_bounds__(256) psis_tail_count_kernel(PsisScalars* sc, const double* __restrict__ cand_x,
                                                               unsigned int* __restrict__ vhist) {
+  PDL_SYNC();
   __shared__ double red[32];
   if (sc->status) return;
   const unsigned int C = sc->ncand;
@@ -554,6 +589,7 @@ __global__ void __launch_bounds__(256) psis_tail_count_kernel(PsisScalars* sc, c
 // exclusive scan of the tail bins (ascending value) -> bin offsets; n2
 __global__ void __launch_bounds__(kSelThreads) psis_tail_scan_kernel(PsisScalars* sc, const unsigned int* __restrict__ vhist,
                                                                       unsigned int* __restrict__ voff) {
+  PDL_SYNC();
   __shared__ unsigned int wsum[32];
   if (sc->status) return;
   constexpr int per = kVBins / kSelThreads;       // 8 bins per thread
@@ -597,6 +633,7 @@ __global__ void __launch_bounds__(256) psis_tail_place_kernel(PsisScalars* sc, c
                                                               unsigned int* __restrict__ vcur, double* __restrict__ tmp_v,
                                                               int64_t* __restrict__ tmp_i, int* __restrict__ tmp_b,
                                                               unsigned int tail_cap, int raw) {
+  PDL_SYNC();
   if (sc->status) return;
   const unsigned int C = sc->ncand;
   const double maxv = sc->maxv, cutoff = sc->cutoff, vscale = sc->vscale;
@@ -621,6 +658,7 @@ __global__ void __launch_bounds__(256) psis_tail_rank_kernel(PsisScalars* sc, co
                                                              const unsigned int* __restrict__ vhist,
                                                              double* __restrict__ tail_v, int64_t* __restrict__ tail_i,
                                                              double* __restrict__ sorted_x) {
+  PDL_SYNC();
   if (sc->status) return;
   const unsigned int n2 = sc->ntail;
   const double expcut = sc->expcut;
@@ -643,6 +681,7 @@ __global__ void __launch_bounds__(256) psis_tail_rank_kernel(PsisScalars* sc, co
 // optional: tail indices in ascending index order with their value ranks (O(n2^2), API nicety / tests)
 __global__ void __launch_bounds__(256) psis_tail_index_order_kernel(PsisScalars* sc, const int64_t* __restrict__ tail_i,
                                                                     int64_t* __restrict__ idx_sorted, int* __restrict__ order_rank) {
+  PDL_SYNC();
   __shared__ int64_t si[256];
   if (sc->status) return;
   const unsigned int n2 = sc->ntail;
@@ -666,46 +705,15 @@ __global__ void __launch_bounds__(256) psis_tail_index_order_kernel(PsisScalars*
   }
 }
 
-// ---- generalised Pareto fit (_psis.py:212-332), split so that no stage is a long serial loop --------
-// partial sums of log1p(-b_j x_i): grid = (m, kGpdSplit)
-__global__ void __launch_bounds__(256) psis_gpd_grid_kernel(PsisScalars* sc, const double* __restrict__ sorted_x,
-                                                            double* __restrict__ bs, double* __restrict__ part) {
-  __shared__ double red[32];
-  if (sc->status) return;
-  const int N = (int)sc->ntail;
-  if (N <= 4) return;
-  const int m = 30 + (int)sqrt((double)N);
-  const int j = blockIdx.x;
-  if (j >= m) return;
-  const double xq = sorted_x[(int)(N / 4.0 + 0.5) - 1];
-  const double xmax = sorted_x[N - 1];
-  double b = 1.0 - sqrt((double)m / ((double)(j + 1) - 0.5));
-  b /= 3.0 * xq;
-  b += 1.0 / xmax;
-  const double nb = -b;
-  double acc = 0.0;
-  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < N; i += gridDim.y * blockDim.x) acc += log1p(nb * sorted_x[i]);
-  acc = block_sum(acc, red);
-  if (threadIdx.x == 0) {
-    part[j * kGpdSplit + blockIdx.y] = acc;
-    if (blockIdx.y == 0) bs[j] = b;
-  }
-}
-
 // profile likelihood weights -> posterior mean of b (:288-312)
-__global__ void __launch_bounds__(kSelThreads) psis_gpd_weights_kernel(PsisScalars* sc, const double* __restrict__ bs,
-                                                                        const double* __restrict__ part, double* __restrict__ Ls) {
-  __shared__ double red[32];
-  if (sc->status) return;
-  const int N = (int)sc->ntail;
-  if (N <= 4) return;
-  const int m = 30 + (int)sqrt((double)N);
+__device__ __forceinline__ void gpd_weights(PsisScalars* sc, const double* bs, const double* part, double* Ls, int N, int m,
+                                            double* red) {
   for (int j = threadIdx.x; j < m; j += blockDim.x) {
     double ksum = 0.0;
 #pragma unroll
-    for (int u = 0; u < kGpdSplit; ++u) ksum += part[j * kGpdSplit + u];
+    for (int u = 0; u < kGpdSplit; ++u) ksum += __ldcg(part + j * kGpdSplit + u);     // written by other blocks
     const double kj = ksum / (double)N;
-    double L = bs[j] / kj;
+    double L = __ldcg(bs + j) / kj;
     L = log(-L);
     L -= kj;
     L -= 1.0;
@@ -725,7 +733,7 @@ __global__ void __launch_bounds__(kSelThreads) psis_gpd_weights_kernel(PsisScala
     const double w = exp(Ls[j] - lmax) / den;
     if (w >= 10.0 * DBL_EPSILON) {
       wsum += w;
-      bsum += bs[j] * w;
+      bsum += __ldcg(bs + j) * w;
     }
   }
   wsum = block_sum(wsum, red);
@@ -733,9 +741,47 @@ __global__ void __launch_bounds__(kSelThreads) psis_gpd_weights_kernel(PsisScala
   if (threadIdx.x == 0) sc->bhat = bsum / wsum;
 }
 
+
+// ---- generalised Pareto fit (_psis.py:212-332), split so that no stage is a long serial loop --------
+// partial sums of log1p(-b_j x_i): grid = (m, kGpdSplit)
+__global__ void __launch_bounds__(256) psis_gpd_grid_kernel(PsisScalars* sc, const double* __restrict__ sorted_x,
+                                                            double* __restrict__ bs, double* __restrict__ part,
+                                                            double* __restrict__ Ls) {
+  PDL_SYNC();
+  __shared__ double red[32];
+  if (sc->status) return;
+  const int N = (int)sc->ntail;
+  if (N <= 4) return;
+  const int m = 30 + (int)sqrt((double)N);
+  const int j = blockIdx.x;
+  if (j >= m) return;
+  const double xq = sorted_x[(int)(N / 4.0 + 0.5) - 1];
+  const double xmax = sorted_x[N - 1];
+  double b = 1.0 - sqrt((double)m / ((double)(j + 1) - 0.5));
+  b /= 3.0 * xq;
+  b += 1.0 / xmax;
+  const double nb = -b;
+  double acc = 0.0;
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < N; i += gridDim.y * blockDim.x) acc += log1p(nb * sorted_x[i]);
+  acc = block_sum(acc, red);
+  __shared__ unsigned int last;
+  if (threadIdx.x == 0) {
+    part[j * kGpdSplit + blockIdx.y] = acc;
+    if (blockIdx.y == 0) bs[j] = b;
+    __threadfence();
+    last = atomicAdd(&sc->gpd_done, 1u) == (unsigned)(m * kGpdSplit) - 1u;
+  }
+  __syncthreads();
+  if (last) {              // every partial sum is visible: the last block turns them into the posterior mean of b
+    __threadfence();
+    gpd_weights(sc, bs, part, Ls, N, m, red);
+  }
+}
+
 // partial sums of log1p(-bhat x_i)
 __global__ void __launch_bounds__(256) psis_gpd_k_kernel(PsisScalars* sc, const double* __restrict__ sorted_x,
                                                          double* __restrict__ part) {
+  PDL_SYNC();
   __shared__ double red[32];
   if (sc->status) return;
   const int N = (int)sc->ntail;
@@ -762,6 +808,7 @@ __device__ __forceinline__ double gpinv1(double p, double k, double sigma) {
 __global__ void __launch_bounds__(256) psis_tail_values_kernel(PsisScalars* sc, const double* __restrict__ kpart, int nkpart,
                                                                const double* __restrict__ tail_v, double* __restrict__ tail_out,
                                                                double* __restrict__ part3) {
+  PDL_SYNC();
   __shared__ double red[32];
   if (sc->status) return;
   const int N = (int)sc->ntail;
@@ -807,6 +854,7 @@ __global__ void __launch_bounds__(256) psis_tail_values_kernel(PsisScalars* sc, 
 }
 
 __global__ void psis_lse_kernel(PsisScalars* sc, const double* __restrict__ part3, int nparts, double* __restrict__ result) {
+  PDL_SYNC();
   if (sc->status) {
     if (threadIdx.x == 0) result[R_STATUS] = (double)sc->status;
     return;
@@ -843,8 +891,9 @@ __global__ void psis_lse_kernel(PsisScalars* sc, const double* __restrict__ part
 // smoothing is on); moments of v = out + lse for the divergence bounds
 __global__ void __launch_bounds__(256) psis_pass_b_kernel(const double* __restrict__ lw, double* __restrict__ out, int64_t n,
                                                           PsisScalars* sc, double* __restrict__ blk_mom) {
+  PDL_SYNC();
   __shared__ double red[32];
-  __shared__ double etab_s[32];
+  __shared__ double etab_s[kExpTab];
   const uint32_t etab = load_exp_table(etab_s);
   if (sc->status) return;
   const double maxv = sc->maxv, lse = sc->lse, cutoff = sc->cutoff;
@@ -913,8 +962,9 @@ __global__ void __launch_bounds__(256) psis_pass_b_kernel(const double* __restri
 // moments without writing an output array (k-hat / bounds only): 16 bytes per draw in total
 __global__ void __launch_bounds__(256) psis_pass_b_moments_kernel(const double* __restrict__ lw, int64_t n, PsisScalars* sc,
                                                                   double* __restrict__ blk_mom) {
+  PDL_SYNC();
   __shared__ double red[32];
-  __shared__ double etab_s[32];
+  __shared__ double etab_s[kExpTab];
   const uint32_t etab = load_exp_table(etab_s);
   if (sc->status) return;
   const double maxv = sc->maxv, cutoff = sc->cutoff;
@@ -941,6 +991,7 @@ __global__ void __launch_bounds__(256) psis_tail_scatter_kernel(double* __restri
                                                                 const double* __restrict__ tail_out,
                                                                 const double* __restrict__ blk_mom, int nblk,
                                                                 int add_tail, double* __restrict__ result) {
+  PDL_SYNC();
   __shared__ double red[32];
   if (sc->status) return;
   const int N = (int)sc->ntail;
@@ -1112,9 +1163,9 @@ static void psis_plan(int64_t n, double reff, PsisPlan& p, int64_t n_global = 0,
 static bool g_tab_ready = false;
 static int ensure_exp_table() {
   if (g_tab_ready) return VB_OK;
-  double tab[32];
-  for (int j = 0; j < 32; ++j) tab[j] = exp2((double)j / 32.0);
-  VB_CUDA(cudaMemcpyToSymbol(c_exp2_tab, tab, sizeof(tab)));
+  double tab[kExpTab];
+  for (int j = 0; j < kExpTab; ++j) tab[j] = exp2((double)j / (double)kExpTab);
+  VB_CUDA(cudaMemcpyToSymbol(g_exp2_tab, tab, sizeof(tab)));
   g_tab_ready = true;
   return VB_OK;
 }
@@ -1203,19 +1254,13 @@ static int psis_stage_local(const double* lw, int64_t n, int64_t idx_off, int ex
 // stage 2 (replicated): cutoff, tail ranking, GPD fit, smoothed values, log-sum-exp from the candidate list
 static int psis_stage_select(const PsisPlan& p, PsisPtrs& q, int nblk, int raw, cudaStream_t stream) {
   const int cgrid = sm_count() * 2;
-  psis_cand_hist_kernel<<<cgrid, 256, 0, stream>>>(q.sc, q.candx, p.cap, q.ghist);
-  VB_CHECK_LAUNCH();
-  psis_cand_gather_kernel<<<cgrid / 4 > 0 ? cgrid / 4 : 1, kSelThreads, 0, stream>>>(q.sc, q.candx, p.cap, q.ghist, q.gbuf);
-  VB_CHECK_LAUNCH();
-  psis_cutoff_kernel<<<1, kSelThreads, 0, stream>>>(q.sc, q.candx, p.cap, q.gbuf, q.blk, nblk);
-  VB_CHECK_LAUNCH();
-  psis_tail_count_kernel<<<cgrid, 256, 0, stream>>>(q.sc, q.candx, q.vhist);
-  VB_CHECK_LAUNCH();
-  psis_tail_scan_kernel<<<1, kSelThreads, 0, stream>>>(q.sc, q.vhist, q.voff);
-  VB_CHECK_LAUNCH();
-  psis_tail_place_kernel<<<cgrid, 256, 0, stream>>>(q.sc, q.candx, q.candi, q.voff, q.vcur, q.tmpv, q.tmpi, q.tmpb,
-                                                    (unsigned)p.tail_cap, raw);
-  VB_CHECK_LAUNCH();
+  VB_CUDA(launch_pdl(psis_cand_hist_kernel, dim3(cgrid), dim3(256), stream, q.sc, q.candx, p.cap, q.ghist));
+  VB_CUDA(launch_pdl(psis_cand_gather_kernel, dim3(cgrid / 4 > 0 ? cgrid / 4 : 1), dim3(kSelThreads), stream, q.sc, q.candx, p.cap, q.ghist, q.gbuf));
+  VB_CUDA(launch_pdl(psis_cutoff_kernel, dim3(1), dim3(kSelThreads), stream, q.sc, q.candx, p.cap, q.gbuf, q.blk, nblk));
+  VB_CUDA(launch_pdl(psis_tail_count_kernel, dim3(cgrid), dim3(256), stream, q.sc, q.candx, q.vhist));
+  VB_CUDA(launch_pdl(psis_tail_scan_kernel, dim3(1), dim3(kSelThreads), stream, q.sc, q.vhist, q.voff));
+  VB_CUDA(launch_pdl(psis_tail_place_kernel, dim3(cgrid), dim3(256), stream, q.sc, q.candx, q.candi, q.voff, q.vcur, q.tmpv, q.tmpi, q.tmpb,
+                                                    (unsigned)p.tail_cap, raw));
   return VB_OK;
 }
 
@@ -1225,22 +1270,14 @@ static int psis_stage_global(const PsisPlan& p, PsisPtrs& q, int nblk, double* r
   if (rc) return rc;
   int blocks = (p.tail_cap + 255) / 256;
   if (blocks > sm_count() * 4) blocks = sm_count() * 4;
-  psis_tail_rank_kernel<<<blocks, 256, 0, stream>>>(q.sc, q.tmpv, q.tmpi, q.tmpb, q.voff, q.vhist, q.tailv, q.taili, q.sorted);
-  VB_CHECK_LAUNCH();
+  VB_CUDA(launch_pdl(psis_tail_rank_kernel, dim3(blocks), dim3(256), stream, q.sc, q.tmpv, q.tmpi, q.tmpb, q.voff, q.vhist, q.tailv, q.taili, q.sorted));
   if (tail_idx && tail_rank) {
-    psis_tail_index_order_kernel<<<blocks, 256, 0, stream>>>(q.sc, q.taili, tail_idx, tail_rank);
-    VB_CHECK_LAUNCH();
+    VB_CUDA(launch_pdl(psis_tail_index_order_kernel, dim3(blocks), dim3(256), stream, q.sc, q.taili, tail_idx, tail_rank));
   }
-  psis_gpd_grid_kernel<<<dim3(p.mgrid, kGpdSplit), 256, 0, stream>>>(q.sc, q.sorted, q.bs, q.part);
-  VB_CHECK_LAUNCH();
-  psis_gpd_weights_kernel<<<1, kSelThreads, 0, stream>>>(q.sc, q.bs, q.part, q.Ls);
-  VB_CHECK_LAUNCH();
-  psis_gpd_k_kernel<<<p.kparts, 256, 0, stream>>>(q.sc, q.sorted, q.kpart);
-  VB_CHECK_LAUNCH();
-  psis_tail_values_kernel<<<p.vparts, 256, 0, stream>>>(q.sc, q.kpart, p.kparts, q.tailv, q.tailout, q.part3);
-  VB_CHECK_LAUNCH();
-  psis_lse_kernel<<<1, 32, 0, stream>>>(q.sc, q.part3, p.vparts, result);
-  VB_CHECK_LAUNCH();
+  VB_CUDA(launch_pdl(psis_gpd_grid_kernel, dim3(p.mgrid, kGpdSplit), dim3(256), stream, q.sc, q.sorted, q.bs, q.part, q.Ls));
+  VB_CUDA(launch_pdl(psis_gpd_k_kernel, dim3(p.kparts), dim3(256), stream, q.sc, q.sorted, q.kpart));
+  VB_CUDA(launch_pdl(psis_tail_values_kernel, dim3(p.vparts), dim3(256), stream, q.sc, q.kpart, p.kparts, q.tailv, q.tailout, q.part3));
+  VB_CUDA(launch_pdl(psis_lse_kernel, dim3(1), dim3(32), stream, q.sc, q.part3, p.vparts, result));
   return VB_OK;
 }
 
@@ -1248,16 +1285,14 @@ static int psis_stage_global(const PsisPlan& p, PsisPtrs& q, int nblk, double* r
 static int psis_stage_apply(const double* lw, double* out, int64_t n, int64_t idx_off, int add_tail, const PsisPlan& p,
                             PsisPtrs& q, double* result, cudaStream_t stream) {
   if (out) {
-    psis_pass_b_kernel<<<p.grid, 256, 0, stream>>>(lw, out, n, q.sc, q.mom);
+    VB_CUDA(launch_pdl(psis_pass_b_kernel, dim3(p.grid), dim3(256), stream, lw, out, n, q.sc, q.mom));
   } else {
-    psis_pass_b_moments_kernel<<<p.grid, 256, 0, stream>>>(lw, n, q.sc, q.mom);
+    VB_CUDA(launch_pdl(psis_pass_b_moments_kernel, dim3(p.grid), dim3(256), stream, lw, n, q.sc, q.mom));
   }
-  VB_CHECK_LAUNCH();
   int blocks = (p.tail_cap + 255) / 256;
   if (blocks > sm_count()) blocks = sm_count();
-  psis_tail_scatter_kernel<<<blocks, 256, 0, stream>>>(out, n, idx_off, q.sc, q.taili, q.tailout, q.mom, p.grid, add_tail,
-                                                       result);
-  VB_CHECK_LAUNCH();
+  VB_CUDA(launch_pdl(psis_tail_scatter_kernel, dim3(blocks), dim3(256), stream, out, n, idx_off, q.sc, q.taili, q.tailout, q.mom, p.grid, add_tail,
+                                                       result));
   return VB_OK;
 }
 
