@@ -156,6 +156,17 @@ class ClockSampler(object):
         return out
 
 
+def profiled_traffic(*kernels):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernels, from the committed
+    ncu --set full captures (profiles/traffic_r01.json); None when a kernel has not been captured."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'traffic_r01.json')) as f:
+            t = json.load(f)
+        return float(sum(t[k] for k in kernels))
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def measured_peak(name, fallback):
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -237,7 +248,9 @@ def bench_psis(torch, vb, args):
     return {'metric': 'psis_draws_per_sec', 'value': n / sec, 'unit': 'draws/s', 'n_draws': n, 'ms': sec * 1e3,
             'khat': float(r[0]), 'n_tail': int(r[2]), 'status': int(r[6]),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s', 'frac': achieved / hbm,
-                         'traffic': None, 'peak_source': how, 'algorithmic_bytes_per_draw': 24},
+                         'traffic': profiled_traffic('psis_pass_a_kernel', 'psis_pass_b_kernel') if n == 100000000 else None,
+                         'traffic_note': 'the two streaming passes (the short kernels between them touch < 10 MB)',
+                         'peak_source': how, 'algorithmic_bytes_per_draw': 24},
             'e2e': {'value': e2e, 'unit': 'draws/s', 'n_draws': host.numel(), 'h2d_bytes': host.numel() * 8,
                     'd2h_bytes': host.numel() * 8 + 8, 'khat': k2},
             'cpu_baseline': cpu}
@@ -361,8 +374,11 @@ def run_b200(args):
         peak_note = 'cuBLAS tf32 matmul 8192^3 measured in this run'
     achieved = flops / sweep_sec / 1e12
     bf16_peak, how = measured_peak('bf16_tflops', 1590.0)
+    traffic = None
+    if path == 'fast' and world == 1 and (N, d, S) == (1000000, 512, 256):
+        traffic = profiled_traffic('glm_fast_pair_kernel')       # ncu --set full capture of this very launch shape
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                'frac': achieved / peak, 'traffic': None, 'kernel': 'glm_sweep_%s' % path,
+                'frac': achieved / peak, 'traffic': traffic, 'kernel': 'glm_sweep_%s' % path,
                 'kernel_ms': sweep_sec * 1e3, 'peak_note': peak_note,
                 'bf16_peak_tflops': bf16_peak, 'bf16_peak_source': how,
                 'algorithmic_flops_per_launch': flops, 'algorithmic_bytes_per_launch': (hi - lo) * d * 8.0}
