@@ -29,7 +29,8 @@ def _f16_exact(a):
 
 
 @pytest.mark.parametrize('N,d,S', [(1000, 512, 256), (20000, 512, 256), (1003, 13, 7), (4100, 130, 100),
-                                   (128, 128, 64), (257, 1024, 256), (5, 2048, 3), (40000, 64, 256)])
+                                   (128, 128, 64), (257, 1024, 256), (5, 2048, 3), (40000, 64, 256),
+                                   (60000, 1024, 256), (45000, 2048, 64)])
 def test_fast_sweep_vs_oracle(vb, vo, N, d, S):
     X, y, beta = logistic_problem(N, d, seed=N + d)
     rs = np.random.RandomState(S)

@@ -119,6 +119,16 @@ def _mvt_objective(approx, model, S, objective, alpha, var_param, base=None, see
     return value, approx.pack_grad(gmu, Fbar)
 
 
+def _to_host(value, grad):
+    """(value, grad) -> (float, numpy) with ONE device-to-host copy when both are views of the same
+    [1 + len(grad)] buffer (the layout _mf_objective produces), else one copy each."""
+    base = grad._base
+    if base is not None and base is value._base and base.dim() == 1 and base.numel() == grad.numel() + 1:
+        h = base.cpu().numpy()
+        return float(h[0]), h[1:].copy()
+    return float(value), grad.cpu().numpy()
+
+
 def _mf_objective(approx, model, S, objective, alpha, var_param, base=None, seed=None, want_logp=False):
     """One fused evaluation for a mean-field family.  Returns (value, grad[, logp]) as 0-d / 1-d
     CUDA tensors (no host sync)."""
@@ -196,7 +206,7 @@ class ExclusiveKL(StochasticVariationalObjective):
             value, grad = _mf_objective(self.approx, self.model, self.num_mc_samples, obj, 0.0,
                                         var_param, base=base)
             if host:
-                return float(value), grad.cpu().numpy()
+                return _to_host(value, grad)
             return value, grad
 
         self._objective_and_grad = objective_and_grad
@@ -228,7 +238,7 @@ class AlphaDivergence(StochasticVariationalObjective):
             value, grad = _mf_objective(self.approx, self.model, self.num_mc_samples, _lib.OBJ_ALPHA,
                                         self.alpha, var_param, base=base, seed=seed)
             if host:
-                return float(value), grad.cpu().numpy()
+                return _to_host(value, grad)
             return value, grad
 
         self._objective_and_grad = objective_grad_and_log_norm
@@ -344,7 +354,7 @@ class DISInclusiveKL(StochasticVariationalObjective):
             dmu, dls = self._score_terms(vp, xs)
             grad = -torch.cat([(wts[:, None] * dmu).sum(dim=0), (wts[:, None] * dls).sum(dim=0)])
             if host:
-                return float(value), grad.cpu().numpy()
+                return _to_host(value, grad)
             return value, grad
 
         self._objective_and_grad = objective_and_grad
