@@ -83,6 +83,7 @@ struct PsisScalars {           // device-resident control block
   unsigned long long prefix;   // exact-mode radix state
   unsigned long long kth;
   unsigned int gpd_done;       // blocks of the GPD grid kernel that have finished
+  unsigned int gather_done, count_done, values_done;      // same for the kernels whose last block runs the next (single-CTA) step
 };
 
 __device__ __forceinline__ unsigned long long dkey(double x) {
@@ -207,7 +208,7 @@ __device__ unsigned long long cta_select_kth_largest(const unsigned long long* k
 __global__ void psis_init_kernel(PsisScalars* sc, int M, unsigned int* hist, unsigned int* vhist) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     sc->maxkey = 0; sc->t0key = 0; sc->cutkey = 0; sc->ncand = 0; sc->ntail = 0; sc->status = 0; sc->strict = 0;
-    sc->gpd_done = 0;
+    sc->gpd_done = 0; sc->gather_done = 0; sc->count_done = 0; sc->values_done = 0;
     sc->t0 = -INFINITY; sc->maxv = 0; sc->cutoff = 0; sc->expcut = 0; sc->body_below = 0; sc->body_cand = 0;
     sc->tail_sum = 0; sc->k = INFINITY; sc->sigma = 0; sc->lse = 0; sc->bhat = 0; sc->sumv = 0; sc->sumexp2v = 0;
     sc->vscale = 0; sc->smoothed = 0; sc->M = M; sc->shift = 0; sc->bstar = 0; sc->need = 0; sc->members = 0; sc->gcount = 0; sc->prefix = 0; sc->kth = 0;
@@ -454,45 +455,10 @@ __global__ void __launch_bounds__(256) psis_cand_hist_kernel(PsisScalars* sc, co
 
 // every CTA locates the boundary bin from the global histogram, then gathers the keys of its slice of
 // that bin into a small global buffer
-__global__ void __launch_bounds__(kSelThreads) psis_cand_gather_kernel(PsisScalars* sc, const double* __restrict__ cand_x,
-                                                                        unsigned int cap, const unsigned int* __restrict__ ghist,
-                                                                        unsigned long long* __restrict__ gbuf) {
-  PDL_SYNC();
-  __shared__ unsigned int hist[kBins];
-  __shared__ unsigned long long sh[2];
-  __shared__ unsigned int wtot[32];
-  const unsigned int C = sc->ncand;
-  if (sc->strict || C > cap || C < (unsigned)(sc->M + 1)) return;
-  for (unsigned int b = threadIdx.x; b < kBins; b += blockDim.x) hist[b] = ghist[b];
-  __syncthreads();
-  cta_find_bin(hist, kBins, (unsigned long long)(sc->M + 1), sh, wtot);
-  const unsigned int bstar = (unsigned int)sh[0];
-  const unsigned int members = hist[bstar];
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    sc->bstar = bstar;
-    sc->need = (unsigned int)sh[1];
-    sc->members = members;
-  }
-  if (members > kGather) return;             // the cutoff kernel falls back to radix passes
-  double lo;
-  const double scale = cand_scale(sc, lo);
-  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < C; i += gridDim.x * blockDim.x) {
-    const double x = cand_x[i];
-    if ((scale > 0.0 ? cbin(x, lo, scale) : 0u) == bstar) {
-      const unsigned int slot = atomicAdd(&sc->gcount, 1u);
-      if (slot < kGather) gbuf[slot] = dkey(x);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(kSelThreads) psis_cutoff_kernel(PsisScalars* sc, const double* __restrict__ cand_x,
-                                                                   unsigned int cap, const unsigned long long* __restrict__ gbuf,
-                                                                   const double* __restrict__ blk_sum, int nblk) {
-  PDL_SYNC();
-  __shared__ unsigned int hist[kBins];
-  __shared__ unsigned long long sh[2];
-  __shared__ unsigned int wtot[32];
-  __shared__ double red[32];
+// cutoff = (M+1)-th largest candidate (one CTA of kSelThreads threads; run by the last block of the gather kernel)
+__device__ __forceinline__ void cutoff_block(PsisScalars* sc, const double* cand_x, unsigned int cap,
+                                             const unsigned long long* gbuf, const double* blk_sum, int nblk,
+                                             unsigned int* hist, unsigned long long* sh, unsigned int* wtot, double* red) {
   const unsigned int C = sc->ncand;
   const int M = sc->M;
   double s = 0.0;
@@ -559,6 +525,50 @@ __global__ void __launch_bounds__(kSelThreads) psis_cutoff_kernel(PsisScalars* s
   }
 }
 
+__global__ void __launch_bounds__(kSelThreads) psis_cand_gather_kernel(PsisScalars* sc, const double* __restrict__ cand_x,
+                                                                        unsigned int cap, const unsigned int* __restrict__ ghist,
+                                                                        unsigned long long* gbuf, const double* blk_sum, int nblk) {
+  PDL_SYNC();
+  __shared__ unsigned int hist[kBins];
+  __shared__ unsigned long long sh[2];
+  __shared__ unsigned int wtot[32];
+  __shared__ double red[32];
+  __shared__ unsigned int last;
+  const unsigned int C = sc->ncand;
+  if (!(sc->strict || C > cap || C < (unsigned)(sc->M + 1))) {
+    for (unsigned int b = threadIdx.x; b < kBins; b += blockDim.x) hist[b] = ghist[b];
+    __syncthreads();
+    cta_find_bin(hist, kBins, (unsigned long long)(sc->M + 1), sh, wtot);
+    const unsigned int bstar = (unsigned int)sh[0];
+    const unsigned int members = hist[bstar];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      sc->bstar = bstar;
+      sc->need = (unsigned int)sh[1];
+      sc->members = members;
+    }
+    if (members <= kGather) {                  // else the cutoff step falls back to radix passes
+      double lo;
+      const double scale = cand_scale(sc, lo);
+      for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < C; i += gridDim.x * blockDim.x) {
+        const double x = cand_x[i];
+        if ((scale > 0.0 ? cbin(x, lo, scale) : 0u) == bstar) {
+          const unsigned int slot = atomicAdd(&sc->gcount, 1u);
+          if (slot < kGather) gbuf[slot] = dkey(x);
+        }
+      }
+    }
+  }
+  // the last block to finish selects the cutoff among the gathered keys (saves a single-CTA launch)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&sc->gather_done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    cutoff_block(sc, cand_x, cap, gbuf, blk_sum, nblk, hist, sh, wtot, red);
+  }
+}
+
 __device__ __forceinline__ int vbin(double v, double cutoff, double vscale) {
   const double f = (v - cutoff) * vscale;
   int b = (int)f;
@@ -566,32 +576,9 @@ __device__ __forceinline__ int vbin(double v, double cutoff, double vscale) {
 }
 
 // tail membership (shifted value > cutoff), per-bin tail counts, LSE contribution of the other candidates
-__global__ void __launch_bounds__(256) psis_tail_count_kernel(PsisScalars* sc, const double* __restrict__ cand_x,
-                                                              unsigned int* __restrict__ vhist) {
-  PDL_SYNC();
-  __shared__ double red[32];
-  if (sc->status) return;
-  const unsigned int C = sc->ncand;
-  const double maxv = sc->maxv, cutoff = sc->cutoff, vscale = sc->vscale;
-  double acc = 0.0;
-  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < C; i += gridDim.x * blockDim.x) {
-    const double v = cand_x[i] - maxv;
-    if (v > cutoff) {
-      atomicAdd(&vhist[vbin(v, cutoff, vscale)], 1u);
-    } else {
-      acc += exp(v);
-    }
-  }
-  acc = block_sum(acc, red);
-  if (threadIdx.x == 0 && acc != 0.0) atomicAdd(&sc->body_cand, acc);
-}
-
 // exclusive scan of the tail bins (ascending value) -> bin offsets; n2
-__global__ void __launch_bounds__(kSelThreads) psis_tail_scan_kernel(PsisScalars* sc, const unsigned int* __restrict__ vhist,
-                                                                      unsigned int* __restrict__ voff) {
-  PDL_SYNC();
-  __shared__ unsigned int wsum[32];
-  if (sc->status) return;
+__device__ __forceinline__ void tail_scan_block(PsisScalars* sc, const unsigned int* vhist, unsigned int* voff,
+                                                unsigned int* wsum) {
   constexpr int per = kVBins / kSelThreads;       // 8 bins per thread
   unsigned int loc[per], tot = 0;
 #pragma unroll
@@ -623,6 +610,37 @@ __global__ void __launch_bounds__(kSelThreads) psis_tail_scan_kernel(PsisScalars
   for (int u = 0; u < per; ++u) {
     voff[threadIdx.x * per + u] = base;
     base += loc[u];
+  }
+}
+
+__global__ void __launch_bounds__(kSelThreads) psis_tail_count_kernel(PsisScalars* sc, const double* __restrict__ cand_x,
+                                                                       unsigned int* vhist, unsigned int* __restrict__ voff) {
+  PDL_SYNC();
+  __shared__ double red[32];
+  __shared__ unsigned int wsum[32];
+  __shared__ unsigned int last;
+  if (sc->status) return;
+  const unsigned int C = sc->ncand;
+  const double maxv = sc->maxv, cutoff = sc->cutoff, vscale = sc->vscale;
+  double acc = 0.0;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < C; i += gridDim.x * blockDim.x) {
+    const double v = cand_x[i] - maxv;
+    if (v > cutoff) {
+      atomicAdd(&vhist[vbin(v, cutoff, vscale)], 1u);
+    } else {
+      acc += exp(v);
+    }
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0 && acc != 0.0) atomicAdd(&sc->body_cand, acc);
+  // the last block to finish scans the bin counts into offsets (saves a single-CTA launch)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&sc->count_done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    tail_scan_block(sc, vhist, voff, wsum);
   }
 }
 
@@ -804,13 +822,51 @@ __device__ __forceinline__ double gpinv1(double p, double k, double sigma) {
   return q * sigma;
 }
 
+// log-sum-exp of everything and the result vector (first warp of the last block of the tail-values kernel)
+__device__ __forceinline__ void lse_warp(PsisScalars* sc, const double* part3, int nparts, double* result) {
+  if (sc->status) {
+    if (threadIdx.x == 0) result[R_STATUS] = (double)sc->status;
+    return;
+  }
+  double ts = 0.0, sv = 0.0, se = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += 32) {
+    ts += part3[3 * i];
+    sv += part3[3 * i + 1];
+    se += part3[3 * i + 2];
+  }
+  ts = warp_sum(ts);
+  sv = warp_sum(sv);
+  se = warp_sum(se);
+  if (threadIdx.x != 0) return;
+  const double below = sc->body_below > 0.0 ? sc->body_below * exp(sc->t0 - sc->maxv) : 0.0;
+  const double total = below + sc->body_cand + ts;
+  sc->tail_sum = ts;
+  sc->sumv = sv;
+  sc->sumexp2v = se;
+  sc->lse = log(total);
+  result[R_KHAT] = sc->k;
+  result[R_SIGMA] = sc->sigma;
+  result[R_N2] = (double)sc->ntail;
+  result[R_CUTOFF] = sc->cutoff;
+  result[R_LSE] = sc->lse;
+  result[R_MAX] = sc->maxv;
+  result[R_STATUS] = 0.0;
+  result[R_M] = (double)sc->M;
+  result[R_NCAND] = (double)sc->ncand;
+  result[R_SMOOTHED] = (double)sc->smoothed;
+}
+
 // k-hat, sigma (:313-324) and the smoothing decision (:188); then the per-rank tail values
 __global__ void __launch_bounds__(256) psis_tail_values_kernel(PsisScalars* sc, const double* __restrict__ kpart, int nkpart,
                                                                const double* __restrict__ tail_v, double* __restrict__ tail_out,
-                                                               double* __restrict__ part3) {
+                                                               double* part3, double* __restrict__ result) {
   PDL_SYNC();
   __shared__ double red[32];
-  if (sc->status) return;
+  __shared__ unsigned int last;
+  if (sc->status) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) result[R_STATUS] = (double)sc->status;
+    return;
+  }
   const int N = (int)sc->ntail;
   double k = INFINITY, sigma = 0.0;
   if (N > 4) {
@@ -851,40 +907,15 @@ __global__ void __launch_bounds__(256) psis_tail_values_kernel(PsisScalars* sc, 
       sc->smoothed = smooth ? 1 : 0;
     }
   }
-}
-
-__global__ void psis_lse_kernel(PsisScalars* sc, const double* __restrict__ part3, int nparts, double* __restrict__ result) {
-  PDL_SYNC();
-  if (sc->status) {
-    if (threadIdx.x == 0) result[R_STATUS] = (double)sc->status;
-    return;
+  // the last block to finish folds the partial sums into the log-sum-exp (saves a one-warp launch)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&sc->values_done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && threadIdx.x < 32) {
+    __threadfence();
+    lse_warp(sc, part3, gridDim.x, result);
   }
-  double ts = 0.0, sv = 0.0, se = 0.0;
-  for (int i = threadIdx.x; i < nparts; i += 32) {
-    ts += part3[3 * i];
-    sv += part3[3 * i + 1];
-    se += part3[3 * i + 2];
-  }
-  ts = warp_sum(ts);
-  sv = warp_sum(sv);
-  se = warp_sum(se);
-  if (threadIdx.x != 0) return;
-  const double below = sc->body_below > 0.0 ? sc->body_below * exp(sc->t0 - sc->maxv) : 0.0;
-  const double total = below + sc->body_cand + ts;
-  sc->tail_sum = ts;
-  sc->sumv = sv;
-  sc->sumexp2v = se;
-  sc->lse = log(total);
-  result[R_KHAT] = sc->k;
-  result[R_SIGMA] = sc->sigma;
-  result[R_N2] = (double)sc->ntail;
-  result[R_CUTOFF] = sc->cutoff;
-  result[R_LSE] = sc->lse;
-  result[R_MAX] = sc->maxv;
-  result[R_STATUS] = 0.0;
-  result[R_M] = (double)sc->M;
-  result[R_NCAND] = (double)sc->ncand;
-  result[R_SMOOTHED] = (double)sc->smoothed;
 }
 
 // pass B: out = (x - max) - lse for the body (tail entries are written by the scatter kernel when
@@ -1255,10 +1286,9 @@ static int psis_stage_local(const double* lw, int64_t n, int64_t idx_off, int ex
 static int psis_stage_select(const PsisPlan& p, PsisPtrs& q, int nblk, int raw, cudaStream_t stream) {
   const int cgrid = sm_count() * 2;
   VB_CUDA(launch_pdl(psis_cand_hist_kernel, dim3(cgrid), dim3(256), stream, q.sc, q.candx, p.cap, q.ghist));
-  VB_CUDA(launch_pdl(psis_cand_gather_kernel, dim3(cgrid / 4 > 0 ? cgrid / 4 : 1), dim3(kSelThreads), stream, q.sc, q.candx, p.cap, q.ghist, q.gbuf));
-  VB_CUDA(launch_pdl(psis_cutoff_kernel, dim3(1), dim3(kSelThreads), stream, q.sc, q.candx, p.cap, q.gbuf, q.blk, nblk));
-  VB_CUDA(launch_pdl(psis_tail_count_kernel, dim3(cgrid), dim3(256), stream, q.sc, q.candx, q.vhist));
-  VB_CUDA(launch_pdl(psis_tail_scan_kernel, dim3(1), dim3(kSelThreads), stream, q.sc, q.vhist, q.voff));
+  VB_CUDA(launch_pdl(psis_cand_gather_kernel, dim3(cgrid / 4 > 0 ? cgrid / 4 : 1), dim3(kSelThreads), stream, q.sc, q.candx, p.cap, q.ghist, q.gbuf,
+                     q.blk, nblk));
+  VB_CUDA(launch_pdl(psis_tail_count_kernel, dim3(cgrid / 4 > 0 ? cgrid / 4 : 1), dim3(kSelThreads), stream, q.sc, q.candx, q.vhist, q.voff));
   VB_CUDA(launch_pdl(psis_tail_place_kernel, dim3(cgrid), dim3(256), stream, q.sc, q.candx, q.candi, q.voff, q.vcur, q.tmpv, q.tmpi, q.tmpb,
                                                     (unsigned)p.tail_cap, raw));
   return VB_OK;
@@ -1276,8 +1306,7 @@ static int psis_stage_global(const PsisPlan& p, PsisPtrs& q, int nblk, double* r
   }
   VB_CUDA(launch_pdl(psis_gpd_grid_kernel, dim3(p.mgrid, kGpdSplit), dim3(256), stream, q.sc, q.sorted, q.bs, q.part, q.Ls));
   VB_CUDA(launch_pdl(psis_gpd_k_kernel, dim3(p.kparts), dim3(256), stream, q.sc, q.sorted, q.kpart));
-  VB_CUDA(launch_pdl(psis_tail_values_kernel, dim3(p.vparts), dim3(256), stream, q.sc, q.kpart, p.kparts, q.tailv, q.tailout, q.part3));
-  VB_CUDA(launch_pdl(psis_lse_kernel, dim3(1), dim3(32), stream, q.sc, q.part3, p.vparts, result));
+  VB_CUDA(launch_pdl(psis_tail_values_kernel, dim3(p.vparts), dim3(256), stream, q.sc, q.kpart, p.kparts, q.tailv, q.tailout, q.part3, result));
   return VB_OK;
 }
 
