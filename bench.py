@@ -97,7 +97,7 @@ def run_reference(args):
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': scaled * 1e3,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
-        'config': {'workload': 'bayes-logistic N=%d d=%d S=%d MFGaussian+RMSProp' % (args.n_obs, args.dim, args.mc)},
+        'config': {'workload': 'bayes-logistic N=%d d=%d S=%d MFGaussian+RMSProp (BASELINE configs[1])' % (args.n_obs, args.dim, args.mc)},
         'cpu_baseline': {'value': value, 'unit': 'iter/s', 'cores': cpu_threads(), 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'iter/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
