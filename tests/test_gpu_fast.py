@@ -92,3 +92,42 @@ def test_fast_path_rejections(vb):
     approx = vb.MFGaussian(8)
     v, g = vb.ExclusiveKL(approx, model, 300)(approx.init_param())
     assert np.isfinite(v) and np.all(np.isfinite(g))
+
+
+def test_c2_full_size_properties(vb):
+    """BASELINE configs[1] at full size (N=1e6, d=512, S=256), where the numpy oracle would need minutes:
+    size-independent properties instead.  (1) The fast path agrees with the exact FP64 path on the same inputs
+    to the stated 1e-4; (2) the sweep is additive over row shards -- exactly what the multi-GPU all-reduce
+    relies on -- to 1e-12 (FP64 path) and 2e-5 (fast path: fp32 accumulation inside a tile)."""
+    N, d, S = 1000000, 512, 256
+    g = torch.Generator(device='cuda')
+    g.manual_seed(20260117)
+    beta = torch.randn(d, generator=g, device='cuda', dtype=torch.float64) / np.sqrt(d)
+    X = torch.randn(N, d, generator=g, device='cuda', dtype=torch.float64)
+    y = torch.where(torch.rand(N, generator=g, device='cuda', dtype=torch.float64) < torch.sigmoid(X @ beta), 1.0, -1.0)
+    base = torch.randn(S, d, generator=g, device='cuda', dtype=torch.float64).to(torch.float16).to(torch.float64)
+    theta = beta + 0.05 * base                       # near the mode: residuals of every size
+
+    def rel(a, b):
+        return float((a - b).norm() / b.norm())
+
+    cut = 437123                                     # not a multiple of the tile size
+    full = vb.LogisticRegression(X, y)
+    parts = [vb.LogisticRegression(X[:cut], y[:cut]), vb.LogisticRegression(X[cut:], y[cut:])]
+    ref = torch.cat(full.sweep(theta, base, None, True))
+    ref_parts = sum(torch.cat(m.sweep(theta, base, None, True)) for m in parts)
+    assert rel(ref_parts, ref) < 1e-12
+
+    full.enable_fast_path()
+    fast = torch.cat(full.sweep(theta, base, None, True))
+    for lo, hi in ((0, S), (S, S + d), (S + d, S + 2 * d)):            # ll, gmu, ge
+        assert rel(fast[lo:hi], ref[lo:hi]) < TOL_FAST
+    del full
+    for m in parts:
+        m.enable_fast_path()
+    fast_parts = sum(torch.cat(m.sweep(theta, base, None, True)) for m in parts)
+    for lo, hi in ((0, S), (S, S + d), (S + d, S + 2 * d)):
+        assert rel(fast_parts[lo:hi], fast[lo:hi]) < 2e-5
+    # the summed-likelihood shortcut used by plain ExclusiveKL returns the mean in every slot
+    tot = parts[0].sweep(theta, base, None, True, ll_total_only=True)[0] + parts[1].sweep(theta, base, None, True, ll_total_only=True)[0]
+    assert abs(float(tot[0]) * S - float(ref[:S].sum())) < TOL_FAST * abs(float(ref[:S].sum()))
