@@ -130,3 +130,27 @@ __device__ __forceinline__ void link_probit(double a, double& ll, double& dl) {
 }
 
 }  // namespace vb
+
+// Programmatic dependent launch: a kernel launched with launch_pdl() starts with PDL_SYNC() (wait until the kernels before it in the stream have completed and flushed) followed by a trigger
+// that lets the NEXT kernel's blocks be scheduled while this one runs, so the launch ramps overlap.
+#define PDL_SYNC()                                               \
+  do {                                                           \
+    asm volatile("griddepcontrol.wait;" ::: "memory");           \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  } while (0)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+

@@ -809,6 +809,7 @@ glm_fast_pair_kernel(const __grid_constant__ CUtensorMap tmX,      // 5-D: [hi|l
   cluster_sync_all();                      // barriers of both CTAs initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem = misc->tmem_base;
+  PDL_SYNC();                              // everything above overlapped the previous kernel; global memory from here on
 
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ================================
@@ -1199,6 +1200,7 @@ __global__ void fast_prepare_theta_kernel(const double* __restrict__ theta, cons
                                           const double* __restrict__ w, int64_t S, int d, int d_pad,
                                           __half* __restrict__ Th, __half* __restrict__ Tl, __half* __restrict__ E,
                                           float* __restrict__ wf) {
+  PDL_SYNC();
   const int64_t total = (int64_t)kSP * d_pad;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     {   // E: [s][j]
@@ -1233,6 +1235,7 @@ struct Reduce3 {
   double sign[3];
 };
 __global__ void __launch_bounds__(256) reduce_partials3_kernel(Reduce3 a) {
+  PDL_SYNC();
   __shared__ double sm[8][33];
   const int which = blockIdx.y;
   const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
@@ -1442,8 +1445,8 @@ extern "C" int vb_glm_fast_sweep(void* handle, const double* theta, const double
     cached_dpad = m->d_pad;
   }
 
-  fast_prepare_theta_kernel<<<128, 256, 0, stream>>>(theta, want_grad ? base : nullptr, w, S, m->d, m->d_pad, Th, Tl, E, wf);
-  VB_CHECK_LAUNCH();
+  VB_CUDA(launch_pdl(fast_prepare_theta_kernel, dim3(128), dim3(256), stream, theta, want_grad ? base : nullptr, w, S, m->d, m->d_pad,
+                     Th, Tl, E, wf));
 
   Params p;
   p.N = m->N;
@@ -1499,13 +1502,15 @@ extern "C" int vb_glm_fast_sweep(void* handle, const double* theta, const double
     cfg.blockDim = dim3(kThreadsP);
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     VB_CUDA(cudaLaunchKernelEx(&cfg, glm_fast_pair_kernel, m->tmXP, tmTP, tmEP, p));
     nblk_ll = 2 * clusters;
     nblk_g = clusters;              // one row of gradient partials per pair (a CTA owns half of the columns)
@@ -1519,7 +1524,6 @@ extern "C" int vb_glm_fast_sweep(void* handle, const double* theta, const double
   r.part[1] = p.gmu_part; r.out[1] = out_gmu; r.nblk[1] = nblk_g;  r.stride[1] = m->d_pad; r.n[1] = want_grad ? m->d : 0; r.sign[1] = 1.0;
   r.part[2] = p.ge_part;  r.out[2] = out_ge;  r.nblk[2] = nblk_g;  r.stride[2] = m->d_pad; r.n[2] = want_grad ? m->d : 0; r.sign[2] = 1.0;
   const int64_t nmax = want_grad && m->d > S ? m->d : S;
-  reduce_partials3_kernel<<<dim3((unsigned)((nmax + 31) / 32), want_grad ? 3 : 1), 256, 0, stream>>>(r);
-  VB_CHECK_LAUNCH();
+  VB_CUDA(launch_pdl(reduce_partials3_kernel, dim3((unsigned)((nmax + 31) / 32), want_grad ? 3 : 1), dim3(256), stream, r));
   return VB_OK;
 }

@@ -11,6 +11,7 @@ static inline double student_const(double df) {
 // theta = mu + exp(log_sigma) * base   (approximations.py:212-216, :270-274)
 __global__ void mf_sample_kernel(const double* __restrict__ vp, const double* __restrict__ base,
                                  double* __restrict__ theta, int64_t S, int d) {
+  PDL_SYNC();
   const int64_t total = S * d;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(256) mf_value_kernel(const double* __restrict_
                                                        int64_t S, int d, int family, double df, double tconst,
                                                        double inv_tau2, double prior_const, int objective,
                                                        double* __restrict__ value, double* __restrict__ logp) {
+  PDL_SYNC();
   // one warp per sample, 8 samples per block; value[0] (zeroed by the caller) receives every block's share
   __shared__ double red[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(256) mf_grad_kernel(const double* __restrict__
                                                       const double* __restrict__ ge, const double* __restrict__ w,
                                                       int64_t S, int d, int family, double df, double inv_tau2,
                                                       int objective, double alpha, double* __restrict__ grad) {
+  PDL_SYNC();
   __shared__ double sm[5][8][33];
   const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + x;
@@ -214,8 +217,7 @@ extern "C" int vb_mf_sample_f64(const double* var_param, const double* base, dou
   if (S < 0 || d <= 0 || !var_param || (S > 0 && (!base || !theta)))
     return set_error(VB_ERR_INVALID_ARG, "mf_sample: bad arguments");
   if (S == 0) return VB_OK;
-  mf_sample_kernel<<<grid_for(S * d, 256), 256, 0, stream>>>(var_param, base, theta, S, d);
-  VB_CHECK_LAUNCH();
+  VB_CUDA(launch_pdl(mf_sample_kernel, dim3(grid_for(S * d, 256)), dim3(256), stream, var_param, base, theta, S, d));
   return VB_OK;
 }
 
@@ -272,15 +274,13 @@ extern "C" int vb_mf_objective_finish_f64(const double* var_param, const double*
     if (objective != VB_OBJ_ALPHA && !value)
       return set_error(VB_ERR_INVALID_ARG, "mf_objective_finish: value is required");
     if (objective != VB_OBJ_ALPHA) VB_CUDA(cudaMemsetAsync(value, 0, sizeof(double), stream));
-    mf_value_kernel<<<(unsigned)((S + 7) / 8), 256, 0, stream>>>(var_param, theta, base, ll, S, d, family, df, tc, inv_tau2,
-                                                                 pc, objective, value, logp);
-    VB_CHECK_LAUNCH();
+    VB_CUDA(launch_pdl(mf_value_kernel, dim3((unsigned)((S + 7) / 8)), dim3(256), stream, var_param, theta, base, ll, S, d, family,
+                       df, tc, inv_tau2, pc, objective, value, logp));
   }
   if (grad) {
-    mf_grad_kernel<<<(d + 31) / 32, 256, 0, stream>>>(var_param, theta, base, gmu, ge,
+    VB_CUDA(launch_pdl(mf_grad_kernel, dim3((d + 31) / 32), dim3(256), stream, var_param, theta, base, gmu, ge,
                                                          objective == VB_OBJ_ALPHA ? w : nullptr, S, d, family,
-                                                         df, inv_tau2, objective, alpha, grad);
-    VB_CHECK_LAUNCH();
+                                                         df, inv_tau2, objective, alpha, grad));
   }
   return VB_OK;
 }

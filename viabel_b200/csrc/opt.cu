@@ -7,6 +7,7 @@ namespace vb {
 __global__ void rmsprop_step_kernel(double* __restrict__ vp, const double* __restrict__ grad,
                                     double* __restrict__ nu, double* __restrict__ dir, int64_t P, double lr,
                                     double beta, double jitter, int first) {
+  PDL_SYNC();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P;
        i += (int64_t)gridDim.x * blockDim.x) {
     const double g = grad[i], g2 = g * g;
@@ -23,6 +24,7 @@ __global__ void rmsprop_step_kernel(double* __restrict__ vp, const double* __res
 __global__ void adam_step_kernel(double* __restrict__ vp, const double* __restrict__ grad,
                                  double* __restrict__ m, double* __restrict__ nu, double* __restrict__ dir,
                                  int64_t P, double lr, double beta1, double beta2, double jitter, int first) {
+  PDL_SYNC();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P;
        i += (int64_t)gridDim.x * blockDim.x) {
     const double g = grad[i];
@@ -58,8 +60,7 @@ extern "C" int vb_rmsprop_step_f64(double* var_param, const double* grad, double
   if (P <= 0 || !var_param || !grad || !nu) return set_error(VB_ERR_INVALID_ARG, "rmsprop_step: bad arguments");
   int blocks = (int)((P + 255) / 256);
   if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
-  rmsprop_step_kernel<<<blocks, 256, 0, stream>>>(var_param, grad, nu, direction, P, lr, beta, jitter, first);
-  VB_CHECK_LAUNCH();
+  VB_CUDA(launch_pdl(rmsprop_step_kernel, dim3(blocks), dim3(256), stream, var_param, grad, nu, direction, P, lr, beta, jitter, first));
   return VB_OK;
 }
 
@@ -69,7 +70,6 @@ extern "C" int vb_adam_step_f64(double* var_param, const double* grad, double* m
   if (P <= 0 || !var_param || !grad || !m || !nu) return set_error(VB_ERR_INVALID_ARG, "adam_step: bad arguments");
   int blocks = (int)((P + 255) / 256);
   if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
-  adam_step_kernel<<<blocks, 256, 0, stream>>>(var_param, grad, m, nu, direction, P, lr, beta1, beta2, jitter, first);
-  VB_CHECK_LAUNCH();
+  VB_CUDA(launch_pdl(adam_step_kernel, dim3(blocks), dim3(256), stream, var_param, grad, m, nu, direction, P, lr, beta1, beta2, jitter, first));
   return VB_OK;
 }

@@ -33,30 +33,6 @@ constexpr int kGpdSplit = 8;             // CTAs per quadrature point
 enum { R_KHAT = 0, R_SIGMA, R_N2, R_CUTOFF, R_LSE, R_MAX, R_STATUS, R_SUMV, R_SUMEXP2V, R_M, R_NCAND, R_SMOOTHED,
        R_COUNT = 16 };
 
-// Programmatic dependent launch: every kernel of the short chain between the two streaming passes starts with
-// PDL_SYNC() (wait until the kernels before it in the stream have completed and flushed) followed by a trigger
-// that lets the NEXT kernel's blocks be scheduled while this one runs, so the launch ramps overlap.
-#define PDL_SYNC()                                               \
-  do {                                                           \
-    asm volatile("griddepcontrol.wait;" ::: "memory");           \
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
-  } while (0)
-
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
 struct PsisScalars {           // device-resident control block
   unsigned long long maxkey;   // order-preserving key of the global max
   unsigned long long t0key;    // candidate threshold (key)

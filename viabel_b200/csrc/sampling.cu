@@ -31,6 +31,7 @@ __device__ __forceinline__ void normal_pair(const Philox& ph, uint64_t ctr, uint
 template <typename T>
 __global__ void philox_normal_kernel(T* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset,
                                      int quantize) {
+  PDL_SYNC();
   const Philox ph(seed);
   const int64_t pairs = (n + 1) / 2;
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pairs;
@@ -114,8 +115,7 @@ extern "C" int vb_philox_normal_f64(double* out, int64_t n, uint64_t seed, uint6
                                     cudaStream_t stream) {
   if (n < 0 || (n > 0 && !out)) return set_error(VB_ERR_INVALID_ARG, "philox_normal: bad arguments");
   if (n == 0) return VB_OK;
-  philox_normal_kernel<double><<<grid_for((n + 1) / 2, 256), 256, 0, stream>>>(out, n, seed, offset, quantize);
-  VB_CHECK_LAUNCH();
+  VB_CUDA(launch_pdl(philox_normal_kernel<double>, dim3(grid_for((n + 1) / 2, 256)), dim3(256), stream, out, n, seed, offset, quantize));
   return VB_OK;
 }
 
@@ -123,8 +123,7 @@ extern "C" int vb_philox_normal_f32(float* out, int64_t n, uint64_t seed, uint64
                                     cudaStream_t stream) {
   if (n < 0 || (n > 0 && !out)) return set_error(VB_ERR_INVALID_ARG, "philox_normal: bad arguments");
   if (n == 0) return VB_OK;
-  philox_normal_kernel<float><<<grid_for((n + 1) / 2, 256), 256, 0, stream>>>(out, n, seed, offset, quantize);
-  VB_CHECK_LAUNCH();
+  VB_CUDA(launch_pdl(philox_normal_kernel<float>, dim3(grid_for((n + 1) / 2, 256)), dim3(256), stream, out, n, seed, offset, quantize));
   return VB_OK;
 }
 
