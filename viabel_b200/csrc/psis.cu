@@ -59,7 +59,7 @@ struct PsisScalars {           // device-resident control block
   unsigned long long prefix;   // exact-mode radix state
   unsigned long long kth;
   unsigned int gpd_done;       // blocks of the GPD grid kernel that have finished
-  unsigned int gather_done, count_done, values_done;      // same for the kernels whose last block runs the next (single-CTA) step
+  unsigned int gather_done, count_done, values_done, select_done;      // same for the kernels whose last block runs the next (single-CTA) step
 };
 
 __device__ __forceinline__ unsigned long long dkey(double x) {
@@ -184,7 +184,7 @@ __device__ unsigned long long cta_select_kth_largest(const unsigned long long* k
 __global__ void psis_init_kernel(PsisScalars* sc, int M, unsigned int* hist, unsigned int* vhist) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     sc->maxkey = 0; sc->t0key = 0; sc->cutkey = 0; sc->ncand = 0; sc->ntail = 0; sc->status = 0; sc->strict = 0;
-    sc->gpd_done = 0; sc->gather_done = 0; sc->count_done = 0; sc->values_done = 0;
+    sc->gpd_done = 0; sc->gather_done = 0; sc->count_done = 0; sc->values_done = 0; sc->select_done = 0;
     sc->t0 = -INFINITY; sc->maxv = 0; sc->cutoff = 0; sc->expcut = 0; sc->body_below = 0; sc->body_cand = 0;
     sc->tail_sum = 0; sc->k = INFINITY; sc->sigma = 0; sc->lse = 0; sc->bhat = 0; sc->sumv = 0; sc->sumexp2v = 0;
     sc->vscale = 0; sc->smoothed = 0; sc->M = M; sc->shift = 0; sc->bstar = 0; sc->need = 0; sc->members = 0; sc->gcount = 0; sc->prefix = 0; sc->kth = 0;
@@ -227,28 +227,51 @@ __device__ unsigned long long reg_select_kth_largest(const unsigned long long (&
 // sample (a subset's order statistic), i.e. errs on the side of a few more candidates and needs one key
 // per thread; larger R (only for n of a few 1e5 or less): the exact R-th largest of the sample.
 __global__ void __launch_bounds__(kSelThreads) psis_sample_select_kernel(const double* __restrict__ lw, int64_t stride,
-                                                                          int m, unsigned int R, PsisScalars* sc) {
+                                                                          int m, unsigned int R, PsisScalars* sc,
+                                                                          unsigned long long* gmax) {
   __shared__ unsigned int hist[kBins];
   __shared__ unsigned long long sh[2];
   __shared__ unsigned int wtot[32];
+  __shared__ unsigned int last;
   if (R >= (unsigned)m) {
-    if (threadIdx.x == 0) { sc->t0key = 0; sc->t0 = -INFINITY; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sc->t0key = 0; sc->t0 = -INFINITY; }
     return;
   }
-  unsigned long long kreg[16];
-#pragma unroll
-  for (int u = 0; u < 16; ++u) {
-    const int i = u * kSelThreads + threadIdx.x;
-    kreg[u] = i < m ? dkey(lw[(int64_t)i * stride]) : 0ull;          // key 0 = below everything
-  }
   unsigned long long key;
-  if (R <= 256) {
-    unsigned long long kmax[1] = {0ull};
+  if (gridDim.x > 1) {
+    // R <= 256 and a full sample: 16 CTAs load one key per thread (a single SM cannot keep 16384 scattered DRAM
+    // reads in flight), groups of 16 threads keep their maximum, the last CTA to finish selects among the 1024 maxima
+    const unsigned int g = blockIdx.x * kSelThreads + threadIdx.x;
+    unsigned long long k = dkey(lw[(int64_t)g * stride]);
 #pragma unroll
-    for (int u = 0; u < 16; ++u) kmax[0] = kreg[u] > kmax[0] ? kreg[u] : kmax[0];
+    for (int o = 8; o > 0; o >>= 1) {
+      const unsigned long long v = __shfl_xor_sync(0xffffffffu, k, o);
+      k = v > k ? v : k;
+    }
+    if ((threadIdx.x & 15) == 0) gmax[g >> 4] = k;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&sc->select_done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    unsigned long long kmax[1] = {__ldcg(gmax + threadIdx.x)};
     key = reg_select_kth_largest<1>(kmax, R, hist, sh, wtot);
   } else {
-    key = reg_select_kth_largest<16>(kreg, R, hist, sh, wtot);
+    unsigned long long kreg[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int i = u * kSelThreads + threadIdx.x;
+      kreg[u] = i < m ? dkey(lw[(int64_t)i * stride]) : 0ull;          // key 0 = below everything
+    }
+    if (R <= 256) {
+      unsigned long long kmax[1] = {0ull};
+#pragma unroll
+      for (int u = 0; u < 16; ++u) kmax[0] = kreg[u] > kmax[0] ? kreg[u] : kmax[0];
+      key = reg_select_kth_largest<1>(kmax, R, hist, sh, wtot);
+    } else {
+      key = reg_select_kth_largest<16>(kreg, R, hist, sh, wtot);
+    }
   }
   if (threadIdx.x == 0) { sc->t0key = key; sc->t0 = dkey_inv(key); }
 }
@@ -1236,7 +1259,8 @@ static int psis_stage_local(const double* lw, int64_t n, int64_t idx_off, int ex
   psis_init_kernel<<<8, 1024, 0, stream>>>(q.sc, p.M, q.ghist, q.vhist);
   VB_CHECK_LAUNCH();
   if (!exact) {
-    psis_sample_select_kernel<<<1, kSelThreads, 0, stream>>>(lw, p.stride, p.m_sample, p.R, q.sc);
+    psis_sample_select_kernel<<<(p.R <= 256 && p.m_sample == kSampleMax) ? kSampleMax / kSelThreads : 1, kSelThreads, 0, stream>>>(
+        lw, p.stride, p.m_sample, p.R, q.sc, q.gbuf);
     VB_CHECK_LAUNCH();
   } else {
     psis_exact_begin_kernel<<<1, 1, 0, stream>>>(q.sc);
