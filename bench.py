@@ -218,6 +218,15 @@ def bench_psis(torch, vb, args):
     torch.cuda.synchronize()
     sec = e0.elapsed_time(e1) * 1e-3 / reps
     r = res.cpu().numpy()
+    # diagnostics-only mode (k-hat and the CUBO / ELBO moments, no smoothed output): 16 algorithmic bytes per draw
+    for _ in range(2):
+        vb.psislw_device(lw, None)
+    e0.record()
+    for _ in range(reps):
+        vb.psislw_device(lw, None)
+    e1.record()
+    torch.cuda.synchronize()
+    sec_diag = e0.elapsed_time(e1) * 1e-3 / reps
     hbm, how = measured_peak('hbm_gbs', 6650.0)
     achieved = 24.0 * n / sec / 1e9
     # end to end from HOST memory: H2D of the weights, PSIS, D2H of k-hat and the smoothed weights
@@ -251,6 +260,9 @@ def bench_psis(torch, vb, args):
                          'traffic': profiled_traffic('psis_pass_a_kernel', 'psis_pass_b_kernel') if n == 100000000 else None,
                          'traffic_note': 'the two streaming passes (the short kernels between them touch < 10 MB)',
                          'peak_source': how, 'algorithmic_bytes_per_draw': 24},
+            'diagnostics_only': {'value': n / sec_diag, 'unit': 'draws/s', 'ms': sec_diag * 1e3,
+                                 'algorithmic_bytes_per_draw': 16, 'achieved_gbs': 16.0 * n / sec_diag / 1e9,
+                                 'frac': 16.0 * n / sec_diag / 1e9 / hbm},
             'e2e': {'value': e2e, 'unit': 'draws/s', 'n_draws': host.numel(), 'h2d_bytes': host.numel() * 8,
                     'd2h_bytes': host.numel() * 8 + 8, 'khat': k2},
             'cpu_baseline': cpu}
@@ -398,7 +410,8 @@ def run_b200(args):
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f64' if path == 'f64' else 'f16x2-split/f32',
         'data': 'synthetic',
-        'config': {'workload': 'bayes-logistic N=%d d=%d S=%d MFGaussian+RMSProp (BASELINE configs[1])' % (N, d, S),
+        'config': {'workload': 'bayes-logistic N=%d d=%d S=%d MFGaussian+RMSProp (BASELINE configs[%d])'
+                   % (N, d, S, 2 if (N, d) == (10000000, 1024) else 1),
                    'path': path, 'rows_per_rank': hi - lo, 'l2': 'inputs larger than L2 (X = %.2f GB per rank)'
                    % ((hi - lo) * d * 8 / 1e9)},
         'clocks': clocks,
