@@ -108,8 +108,12 @@ int vb_glm_sweep_f64(const double* X, int64_t ldx, const double* y, int64_t N, i
  *   alive for the lifetime of the handle): y*X split into fp16 hi and lo, zero padded.
  *   absmax_host (optional, HOST pointer) receives max|y*X|; values above 3e4 do not fit the
  *   fp16 operand range and are rejected with VB_ERR_UNSUPPORTED (use the float64 path).
- * vb_glm_fast_sweep: S <= 256 samples per call.  `debug` (optional, device, 49152 floats per
- *   CTA) receives the raw accumulators of each CTA's first tile for testing.
+ * vb_glm_fast_sweep: S <= 256 samples per call.  want_grad bit 0: gradients wanted; bit 1: only
+ *   sum_s ll[s] is needed (every out_ll[s] then receives the mean, plain ExclusiveKL).  `debug`
+ *   (optional, device, 49152 floats per CTA + 128 int64) receives per-phase clock64 timestamps of
+ *   CTA 0 (and, with the one-CTA kernel, the raw accumulators of each CTA's first tile).
+ *   The default kernel runs CTA pairs (tcgen05 cta_group::2, clusters of 2); the environment
+ *   variable VB_FAST_KERNEL=single selects the one-CTA kernel for A/B measurements.
  * Workspace and model_mem must be 1024-byte aligned.
  * ------------------------------------------------------------------------------------- */
 size_t vb_glm_fast_model_bytes(int64_t N, int d);
