@@ -333,6 +333,40 @@ def gen_diagnostics():
     print('diagnostics: %d arrays' % len(out))
 
 
+def mc_chains():
+    """Synthetic optimisation traces for the convergence statistics FASO / RAABBVI compute on the host
+    (optimization.py:550-605): an AR(1) iterate window with drift, [n_iters, n_params]."""
+    rs = np.random.RandomState(4242)
+    n, P = 600, 5
+    x = np.zeros((n, P))
+    phi = np.array([0.0, 0.5, 0.9, 0.97, -0.4])
+    e = rs.randn(n, P)
+    for t in range(1, n):
+        x[t] = phi * x[t - 1] + e[t]
+    x += np.linspace(0.0, 1.0, n)[:, None] * np.array([0.0, 0.0, 0.0, 2.0, 0.0])      # one drifting coordinate
+    return x
+
+
+def gen_mc_diagnostics():
+    from viabel import _mc_diagnostics as ref_mc
+    out = {}
+    x = mc_chains()
+    out['acov'] = ref_mc.autocov(x[:, :3].T)
+    out['ess_1chain'] = np.array([ref_mc.ess(x[:, j][None, :]) for j in range(x.shape[1])])
+    out['ess_4chains'] = np.array([ref_mc.ess(x[:, j].reshape(4, -1)) for j in range(x.shape[1])])
+    eff, mcse = ref_mc.MCSE(x)
+    out['mcse_ess'] = np.asarray(eff, dtype=np.float64)
+    out['mcse'] = np.asarray(mcse, dtype=np.float64)
+    out['rhat'] = np.asarray(ref_mc.compute_R_hat(x))
+    out['rhat_warm_odd'] = np.asarray(ref_mc.compute_R_hat(x, warmup=51))
+    windows = np.array([100, 200, 300, 450])
+    for tag, cols in (('stationary', [0, 1, 4]), ('drifting', [0, 3])):
+        ok, best_W = ref_mc.R_hat_convergence_check(x[:, cols], windows)
+        out['check_%s' % tag] = np.array([float(ok), float(best_W)])
+    np.savez_compressed(os.path.join(OUT, 'mc_diagnostics.npz'), **out)
+    print('mc_diagnostics: %d arrays' % len(out))
+
+
 if __name__ == '__main__':
     print('reference:', os.path.dirname(viabel.__file__))
     gen_families()
@@ -340,3 +374,4 @@ if __name__ == '__main__':
     gen_optimizers()
     gen_psis()
     gen_diagnostics()
+    gen_mc_diagnostics()

@@ -244,3 +244,37 @@ def test_sharded_psis_rule_equals_single(name, cuts):
     outs, k = vo.psislw_sharded([lw[cuts[i]:cuts[i + 1]] for i in range(len(cuts) - 1)])
     assert (np.isinf(k) and np.isinf(kref)) or k == kref
     np.testing.assert_allclose(np.concatenate(outs), ref, rtol=0, atol=1e-11)
+
+
+def _mc_chains():
+    """Same traces as oracle/make_golden.py::mc_chains (rebuilt by seed)."""
+    rs = np.random.RandomState(4242)
+    n, P = 600, 5
+    x = np.zeros((n, P))
+    phi = np.array([0.0, 0.5, 0.9, 0.97, -0.4])
+    e = rs.randn(n, P)
+    for t in range(1, n):
+        x[t] = phi * x[t - 1] + e[t]
+    x += np.linspace(0.0, 1.0, n)[:, None] * np.array([0.0, 0.0, 0.0, 2.0, 0.0])
+    return x
+
+
+def test_mc_diagnostics_golden(golden):
+    """Host-side convergence statistics of FASO / RAABBVI (viabel_b200/_mc_diagnostics.py, a numpy mirror of
+    viabel/_mc_diagnostics.py:7-184) against the unmodified reference: autocovariance, ESS, MCSE,
+    split R-hat and the window check."""
+    from viabel_b200 import _mc_diagnostics as mc
+    g = golden('mc_diagnostics')
+    x = _mc_chains()
+    np.testing.assert_allclose(mc.autocov(x[:, :3].T), g['acov'], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose([mc.ess(x[:, j][None, :]) for j in range(5)], g['ess_1chain'], rtol=1e-10)
+    np.testing.assert_allclose([mc.ess(x[:, j].reshape(4, -1)) for j in range(5)], g['ess_4chains'], rtol=1e-10)
+    eff, mcse = mc.MCSE(x)
+    np.testing.assert_allclose(np.asarray(eff, dtype=np.float64), g['mcse_ess'], rtol=1e-10)
+    np.testing.assert_allclose(np.asarray(mcse, dtype=np.float64), g['mcse'], rtol=1e-10)
+    np.testing.assert_allclose(mc.compute_R_hat(x), g['rhat'], rtol=1e-12)
+    np.testing.assert_allclose(mc.compute_R_hat(x, warmup=51), g['rhat_warm_odd'], rtol=1e-12)
+    windows = np.array([100, 200, 300, 450])
+    for tag, cols in (('stationary', [0, 1, 4]), ('drifting', [0, 3])):
+        ok, best = mc.R_hat_convergence_check(x[:, cols], windows)
+        assert [float(ok), float(best)] == g['check_%s' % tag].tolist()

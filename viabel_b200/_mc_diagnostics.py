@@ -22,7 +22,7 @@ def autocov(samples, axis=-1):
     return cov[tuple(sl)] / n
 
 
-def _ess_from_acov(acov):
+def _ess_from_acov(acov, n_chain=1):
     """Geyer initial positive / monotone sequence estimator on one chain's autocovariance
     (reference ess(), :56-99)."""
     n_draw = acov.shape[0]
@@ -50,7 +50,7 @@ def _ess_from_acov(acov):
             rho[t + 1] = (rho[t - 1] + rho[t]) / 2.0
             rho[t + 2] = rho[t + 1]
         t += 2
-    total = n_draw
+    total = n_chain * n_draw          # the reference keeps going for n_chain > 1 (its ValueError is never raised)
     tau = -1.0 + 2.0 * np.sum(rho[:max_t + 1]) + np.sum(rho[max_t + 1:max_t + 2])
     tau = max(tau, 1 / np.log10(total))
     out = total / tau
@@ -60,10 +60,10 @@ def _ess_from_acov(acov):
 
 
 def ess(samples):
-    """Effective sample size of a (1, n_iters) array."""
+    """Effective sample size of a (n_chains, n_iters) array (FASO passes one chain)."""
     samples = np.asarray(samples, dtype=np.float64)
     acov = autocov(samples, axis=1)
-    return _ess_from_acov(np.mean(acov, axis=0))
+    return _ess_from_acov(np.mean(acov, axis=0), samples.shape[0])
 
 
 def MCSE(sample):
