@@ -1,0 +1,50 @@
+"""CPU: argument checking of the host-side mirror -- same exception class and message as the reference
+(file:line of each message in the reference tree is quoted), and the no-CPU-fallback rule."""
+import numpy as np
+import pytest
+import torch
+
+import viabel_b200 as vb
+
+CASES = [
+    # (reference file:line, exception, message fragment, callable)
+    ('approximations.py:259', ValueError, 'df must be greater than 2', lambda: vb.MFStudentT(3, df=2)),
+    ('approximations.py:327', ValueError, 'df must be greater than 2', lambda: vb.MultivariateT(3, df=2)),
+    ('_psis.py:145', ValueError, 'More than one log-weight needed.', lambda: vb.psislw(np.zeros(1))),
+    ('_psis.py:143', ValueError, 'Argument `lw` must be 1 or 2 dimensional.', lambda: vb.psislw(np.zeros((2, 2, 2)))),
+    ('diagnostics.py:173', ValueError, 'alpha must be greater than 1', lambda: vb.divergence_bound(np.zeros(5), alpha=1.0)),
+    ('diagnostics.py:133', ValueError, 'must provides samples if moment_bound_fn not given', lambda: vb.wasserstein_bounds(0.5)),
+    ('optimization.py:74', ValueError, '"iterate_avg_prop" must be None or between 0 and 1', lambda: vb.RMSProp(0.1, iterate_avg_prop=1.5)),
+    ('optimization.py:506', ValueError, 'sgo must be a subclass of StochasticGradientOptimizer', lambda: vb.FASO(object())),
+    ('optimization.py:513', ValueError, '"mcse_threshold" must be greater than zero', lambda: vb.FASO(vb.RMSProp(0.1), mcse_threshold=0)),
+    ('optimization.py:515', ValueError, '"W_min" must be greater than zero', lambda: vb.FASO(vb.RMSProp(0.1), W_min=0)),
+    ('optimization.py:517', ValueError, '"k_check" must be greater than zero', lambda: vb.FASO(vb.RMSProp(0.1), k_check=0)),
+    ('optimization.py:519', ValueError, '"ESS_min" must be greater than zero', lambda: vb.FASO(vb.RMSProp(0.1), ESS_min=0)),
+    ('optimization.py:675', ValueError, '"rho" must be between zero and one', lambda: vb.RAABBVI(vb.RMSProp(0.1), rho=1.5)),
+    ('objectives.py:147', ValueError, "Name of approximation must be one of 'full', 'mean_only'",
+     lambda: vb.ExclusiveKL(vb.MFGaussian(2), vb.Model(lambda x: x), 10, hessian_approx_method='bogus')),
+    ('convenience.py:64', ValueError, 'either log_density or fit must be specified if objective not given', lambda: vb.bbvi(2)),
+    ('convenience.py:71', ValueError, 'if objective is specified, cannot specify fit, log_density, or approx',
+     lambda: vb.bbvi(2, log_density=lambda x: x, objective=object())),
+    ('convenience.py:124', ValueError, 'either objective or both model and approx must be specified',
+     lambda: vb.vi_diagnostics(np.zeros(4))),
+]
+
+
+@pytest.mark.parametrize('where,exc,msg,fn', CASES, ids=[c[0] for c in CASES])
+def test_reference_error_behaviour(where, exc, msg, fn):
+    with pytest.raises(exc) as e:
+        fn()
+    assert msg in str(e.value)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='only meaningful on a box without a GPU')
+def test_no_cpu_fallback():
+    """The product path must fail loudly without CUDA: no silent numpy / oracle route."""
+    fam = vb.MFGaussian(3)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        fam.sample(fam.init_param(), 4)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        vb.psislw(np.random.RandomState(0).randn(100))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        vb.bbvi(2, log_density=lambda x: -0.5 * (x ** 2).sum(-1), n_iters=5)
