@@ -48,3 +48,35 @@ def test_no_cpu_fallback():
         vb.psislw(np.random.RandomState(0).randn(100))
     with pytest.raises(RuntimeError, match='CUDA'):
         vb.bbvi(2, log_density=lambda x: -0.5 * (x ** 2).sum(-1), n_iters=5)
+
+
+# ---- closed forms of the mean-field families run on the host (numpy): pinned against the reference here as well
+from conftest import relerr  # noqa: E402
+
+
+@pytest.mark.parametrize('tag', ['mfg_dfNone_d1', 'mfg_dfNone_d3', 'mfg_dfNone_d8', 'mft_df20_d3', 'mft_df20_d8',
+                                 'mft_df5.5_d1', 'mft_df5.5_d3', 'mft_df5.5_d8'])
+def test_meanfield_closed_forms_golden(golden, tag):
+    """entropy, kl, mean_and_cov, pth_moment, init_param of MFGaussian / MFStudentT
+    (approximations.py:207-304) against the unmodified reference -- host code, no device needed."""
+    g = golden('families')
+    kind, df, d = tag.split('_')
+    d = int(d[1:])
+    fam = vb.MFGaussian(d) if kind == 'mfg' else vb.MFStudentT(d, float(df[2:]))
+    vp, vp1 = g[tag + '/var_param'], g[tag + '/var_param1']
+    assert relerr(fam.entropy(vp), g[tag + '/entropy']) < 1e-10
+    assert relerr(fam.init_param(), g[tag + '/init_param']) < 1e-15
+    if fam.supports_kl:
+        assert relerr(fam.kl(vp, vp1), g[tag + '/kl']) < 1e-10
+    else:
+        with pytest.raises(NotImplementedError):
+            fam.kl(vp, vp1)
+    mean, cov = fam.mean_and_cov(vp)
+    assert relerr(mean, g[tag + '/mean']) < 1e-10 and relerr(cov, g[tag + '/cov']) < 1e-10
+    for p in (2, 4):
+        key = tag + '/moment%d' % p
+        if key in g:
+            assert relerr(fam.pth_moment(vp, p), g[key]) < 1e-10
+        else:
+            with pytest.raises(ValueError):
+                fam.pth_moment(vp, p)
