@@ -80,3 +80,16 @@ def test_meanfield_closed_forms_golden(golden, tag):
         else:
             with pytest.raises(ValueError):
                 fam.pth_moment(vp, p)
+
+
+def test_host_optimizer_directions_golden(golden):
+    """RMSProp / Adam descent directions on numpy gradients (the host path a numpy caller gets;
+    optimization.py:188-197, :308-326 incl. Adam's first-step aliasing) against the reference."""
+    g = golden('optimizers')
+    grads = g['grads']
+    for name, mk in (('rmsprop', lambda: vb.RMSProp(0.01)), ('adam', lambda: vb.Adam(0.01)),
+                     ('rmsprop_b', lambda: vb.RMSProp(0.01, beta=0.5, jitter=1e-6)),
+                     ('adam_b', lambda: vb.Adam(0.01, beta1=0.7, beta2=0.9, jitter=1e-6))):
+        opt = mk()
+        for i, gr in enumerate(grads):
+            assert relerr(opt.descent_direction(gr.copy()), g[name + '/dirs'][i]) < 1e-13, (name, i)
