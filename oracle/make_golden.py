@@ -367,6 +367,40 @@ def gen_mc_diagnostics():
     print('mc_diagnostics: %d arrays' % len(out))
 
 
+def dis_inputs():
+    """Fixed (samples, log p, log q, temper prior) triples for the ESS bisection of DISInclusiveKL."""
+    rs = np.random.RandomState(515)
+    S, d = 400, 3
+    x = rs.randn(S, d) * 1.5
+    cases = {}
+    log_q = -0.5 * np.sum((x / 1.5) ** 2, axis=1) - d * np.log(1.5 * np.sqrt(2 * np.pi))
+    # target much narrower than q: the ESS target is reached strictly inside (0, 1)
+    cases['interior'] = (x, -0.5 * np.sum((x / 0.4) ** 2, axis=1), log_q, 120)
+    # target close to q: even eps = 0 (no tempering) satisfies the ESS target -> eps snaps to 0
+    cases['eps0'] = (x, -0.5 * np.sum((x / 1.4) ** 2, axis=1), log_q, 60)
+    # unreachable ESS target: eps stays at its upper end point 1
+    cases['eps1'] = (x, -0.5 * np.sum((x / 0.2) ** 2, axis=1), log_q, 399)
+    return cases
+
+
+def gen_dis():
+    from viabel.models import Model
+    from viabel.objectives import DISInclusiveKL
+    out = {}
+    for name, (x, log_p, log_q, target) in dis_inputs().items():
+        d = x.shape[1]
+        prior = MFGaussian(d)
+        obj = DISInclusiveKL(MFGaussian(d), Model(lambda z: -0.5 * anp.sum(z ** 2, axis=1)), x.shape[0], target,
+                             prior, np.zeros(2 * d))
+        eps, ess, w = obj._get_eps_and_weights(1, x, log_p, log_q)
+        out['%s/eps' % name] = np.asarray(float(eps))
+        out['%s/ess' % name] = np.asarray(float(ess))
+        out['%s/w' % name] = np.asarray(w, dtype=np.float64)
+        out['%s/log_prior' % name] = np.asarray(prior.log_density(np.zeros(2 * d), x), dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, 'dis.npz'), **out)
+    print('dis: %d arrays' % len(out))
+
+
 if __name__ == '__main__':
     print('reference:', os.path.dirname(viabel.__file__))
     gen_families()
@@ -375,3 +409,4 @@ if __name__ == '__main__':
     gen_psis()
     gen_diagnostics()
     gen_mc_diagnostics()
+    gen_dis()
