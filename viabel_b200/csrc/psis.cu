@@ -1000,7 +1000,39 @@ __global__ void __launch_bounds__(256) psis_pass_b_moments_kernel(const double* 
   const double maxv = sc->maxv, cutoff = sc->cutoff;
   const bool smoothed = sc->smoothed != 0;
   double sv = 0.0, se = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t done = 0;
+  if ((reinterpret_cast<uintptr_t>(lw) & 31) == 0) {
+    // same streaming structure as pass B: 2 x LDG.128 per thread with the next iteration's loads in flight,
+    // two independent accumulation chains
+    const int64_t n4 = n / 4;
+    double sv1 = 0.0, se1 = 0.0;
+    double2 na = make_double2(0.0, 0.0), nb = na;
+    if (tid < n4) {
+      na = __ldcs(reinterpret_cast<const double2*>(lw) + 2 * tid);
+      nb = __ldcs(reinterpret_cast<const double2*>(lw) + 2 * tid + 1);
+    }
+    for (int64_t q = tid; q < n4; q += nthreads) {
+      const double2 a = na, b = nb;
+      const int64_t qn = q + nthreads;
+      if (qn < n4) {
+        na = __ldcs(reinterpret_cast<const double2*>(lw) + 2 * qn);
+        nb = __ldcs(reinterpret_cast<const double2*>(lw) + 2 * qn + 1);
+      }
+      const double v0 = a.x - maxv, v1 = a.y - maxv, v2 = b.x - maxv, v3 = b.y - maxv;
+      const bool t0 = smoothed && v0 > cutoff, t1 = smoothed && v1 > cutoff, t2 = smoothed && v2 > cutoff,
+                 t3 = smoothed && v3 > cutoff;
+      sv += (t0 ? 0.0 : v0) + (t2 ? 0.0 : v2);
+      sv1 += (t1 ? 0.0 : v1) + (t3 ? 0.0 : v3);
+      se += (t0 ? 0.0 : exp_nonpos(2.0 * v0, etab)) + (t2 ? 0.0 : exp_nonpos(2.0 * v2, etab));
+      se1 += (t1 ? 0.0 : exp_nonpos(2.0 * v1, etab)) + (t3 ? 0.0 : exp_nonpos(2.0 * v3, etab));
+    }
+    sv += sv1;
+    se += se1;
+    done = n4 * 4;
+  }
+  for (int64_t i = done + tid; i < n; i += nthreads) {
     const double v = lw[i] - maxv;
     if (!(smoothed && v > cutoff)) {
       sv += v;
