@@ -120,3 +120,34 @@ def test_dis_ess_bisection_golden(golden, name):
     assert eps == float(g[name + '/eps'])
     assert abs(ess - float(g[name + '/ess'])) <= 1e-10 * float(g[name + '/ess'])
     np.testing.assert_allclose(w.numpy(), g[name + '/w'], rtol=1e-12, atol=0)
+
+
+def test_exp_table_constants_accuracy():
+    """The table-driven exp of the PSIS passes (csrc/psis.cu exp_nonpos): emulate its arithmetic in numpy with the
+    constants parsed from the source.  Guards the reduction constants (256/ln2, the two-part ln2/256) and the
+    degree-4 polynomial: a wrong digit shows up as an error far above the ~2 ulp of the float64 emulation."""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'viabel_b200', 'csrc', 'psis.cu')).read()
+    ntab = int(re.search(r'constexpr int kExpTab = (\d+);', src).group(1))
+    body = re.search(r'__constant__ double c_expk\[8\] = \{(.*?)\};', src, re.S).group(1)
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    c = [float(t) for t in body.replace('\n', ' ').split(',') if t.strip()]
+    assert len(c) == 8 and abs(c[0] - ntab / np.log(2.0)) < 1e-12 * c[0]
+    assert abs((c[2] + c[3]) + np.log(2.0) / ntab) < 1e-18              # -(ln2_hi + ln2_lo)/ntab
+    shift_bits = int(np.log2(ntab))
+    assert re.search(r'const int k = n >> %d;' % shift_bits, src)
+    tab = np.exp2(np.arange(ntab) / ntab)
+    rs = np.random.RandomState(0)
+    x = -np.concatenate([rs.uniform(0, 50, 200000), rs.uniform(0, 700, 50000), 10.0 ** rs.uniform(-12, 0, 50000)])
+    n = np.rint(x * c[0])                                  # the 1.5*2^52 shift rounds to nearest
+    r = (n * c[2] + x) + n * c[3]
+    p = c[4]
+    p = p * r + c[5]
+    p = p * r + c[6]
+    p = p * r + 1.0
+    p = p * r + 1.0
+    ni = n.astype(np.int64)
+    val = np.ldexp(p * tab[ni & (ntab - 1)], (ni >> shift_bits).astype(np.int64))
+    rel = np.abs(val - np.exp(x)) / np.exp(x)
+    assert rel.max() < 1e-15, rel.max()
