@@ -151,3 +151,60 @@ def test_exp_table_constants_accuracy():
     val = np.ldexp(p * tab[ni & (ntab - 1)], (ni >> shift_bits).astype(np.int64))
     rel = np.abs(val - np.exp(x)) / np.exp(x)
     assert rel.max() < 1e-15, rel.max()
+
+
+def test_fast_path_numerics_scheme_emulated():
+    """The operand scheme of the tensor-core sweep, emulated in numpy: fp16 hi+lo splits of y*X and Theta, three
+    products (Xh.Th + Xl.Th + Xh.Tl) accumulated in fp32, link epilogue in fp32, R rounded to fp16, second
+    contraction with fp16-exact draws.  Against the float64 oracle it must sit well inside the 1e-4 tolerance,
+    while a single bf16 pass (8-bit mantissa) does not -- the reason for the split."""
+    rs = np.random.RandomState(3)
+    N, d, S = 4096, 48, 32
+    X = rs.randn(N, d)
+    beta = rs.randn(d) / np.sqrt(d)
+    y = np.where(rs.rand(N) < 1 / (1 + np.exp(-X @ beta)), 1.0, -1.0)
+    base = rs.randn(S, d).astype(np.float16).astype(np.float64)          # fp16-exact draws
+    theta = beta + np.exp(-2.0) * base
+
+    def split16(a):
+        hi = a.astype(np.float16)
+        lo = (a - hi.astype(np.float64)).astype(np.float16)
+        return hi.astype(np.float32), lo.astype(np.float32)
+
+    def sweep(z32):
+        z = z32.astype(np.float32)
+        t = np.exp2(-np.abs(z) * np.float32(1.4426950408889634))
+        sp = np.maximum(-z, 0) + np.log2(1 + t) * np.float32(0.6931471805599453)
+        r = (np.where(z >= 0, t, np.float32(1.0)) / (1 + t)).astype(np.float32)
+        ll = -sp.astype(np.float64).sum(axis=0)
+        r16 = r.astype(np.float16).astype(np.float32)
+        Xy = (X * y[:, None])
+        T = r16 @ base.astype(np.float32)                                  # [N, d], fp32 accumulate
+        ge = (Xy * T.astype(np.float64)).sum(axis=0)
+        gmu = Xy.T @ r.astype(np.float64).sum(axis=1)
+        return ll, gmu, ge
+
+    Xh, Xl = split16(X * y[:, None])
+    Th, Tl = split16(theta)
+    z3 = Xh @ Th.T + Xl @ Th.T + Xh @ Tl.T
+    zb = (X * y[:, None]).astype(np.float32)
+    # bf16 emulation: keep 8 mantissa bits
+    def bf16(a):
+        b = a.astype(np.float32).view(np.uint32)
+        b = ((b + 0x7FFF + ((b >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)
+        return b.view(np.float32)
+    z1 = bf16(zb) @ bf16(theta.astype(np.float32)).T
+
+    a = (X @ theta.T) * y[:, None]
+    ll0 = -np.logaddexp(0, -a).sum(axis=0)
+    R0 = 1 / (1 + np.exp(a))
+    gmu0 = (X * y[:, None]).T @ R0.sum(axis=1)
+    ge0 = ((X * y[:, None]) * (R0 @ base)).sum(axis=0)
+
+    def err(z):
+        ll, gmu, ge = sweep(z)
+        return max(relerr(ll, ll0), relerr(gmu, gmu0), relerr(ge, ge0))
+
+    e3, e1 = err(z3), err(z1)
+    assert e3 < 3e-5, e3
+    assert e1 > 1e-4, e1
