@@ -303,7 +303,9 @@ def run_b200(args):
     objective = vb.ExclusiveKL(approx, model, S)
     opt = vb.RMSProp(0.01)
     vp = torch.as_tensor(approx.init_param(), device=dev)
-    launches_per_step = 10      # philox, sample, pack, sweep, 3x reduce, value, grad, rmsprop
+    # own kernels per step.  fast: philox, sample, operand pack, pair sweep, partial reduction, value, grad, rmsprop;
+    # f64: philox, sample, pack, sweep, 3x reduce, value, grad, rmsprop.  (The NCCL all-reduce at N > 1 is not ours.)
+    launches_per_step = 8 if path == 'fast' else 10
 
     def step():
         value, grad = objective(vp)
