@@ -208,3 +208,24 @@ def test_fast_path_numerics_scheme_emulated():
     e3, e1 = err(z3), err(z1)
     assert e3 < 3e-5, e3
     assert e1 > 1e-4, e1
+
+
+def test_product_never_touches_the_oracle_and_needs_its_library(tmp_path):
+    """The oracle is test infrastructure: no product module may mention it; and without the built CUDA library the
+    package must refuse to import (no silent fallback)."""
+    import glob
+    import os
+    import shutil
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f in glob.glob(os.path.join(root, 'viabel_b200', '*.py')) + glob.glob(os.path.join(root, 'viabel_b200', 'csrc', '*')):
+        if os.path.isfile(f):
+            assert 'oracle' not in open(f, errors='ignore').read(), f
+    pkg = tmp_path / 'viabel_b200'
+    pkg.mkdir()
+    for f in glob.glob(os.path.join(root, 'viabel_b200', '*.py')):
+        shutil.copy(f, pkg)                                  # the Python side only: no libviabel_b200.so
+    out = subprocess.run([sys.executable, '-c', 'import viabel_b200'], cwd=str(tmp_path), capture_output=True, text=True,
+                         timeout=120)
+    assert out.returncode != 0 and 'ImportError' in out.stderr and 'libviabel_b200' in out.stderr
