@@ -667,13 +667,13 @@ glm_fast_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
 //   GEMM2  M = 256 j (rank r owns j-block r of the 256-j pair block), N = 128 tile rows (64 from each CTA's R tile),
 //          two such units (tile-row halves) per group; each CTA stages only its half of E, one 16 KB slot per
 //          64 samples, released as soon as both units have consumed it
-//   E2     reads its X rows straight from global memory / L2 (256-bit loads; a thread owns column j, whose
-//          128 tile rows are one contiguous 256-byte run in the tile-transposed layout), so the operand ring
-//          only carries tensor-core operands
-// Operand fills per 128 rows drop from 1280 KB to 896 KB (d = 512) -- the single-CTA kernel is bound by the
-// L2 -> SM rate.  GEMM2/E2 of super-tile i-1 are interleaved with GEMM1 of super-tile i (the R tile of i-1 stays
-// valid until E1 of i starts, which is after every MMA issued before Z(i) was committed), and E2 has its own
-// warps, so the tensor pipe only idles during E1.
+//   E2     reads its X values straight from global memory / L2 (256-bit evict-first loads; a thread owns column j,
+//          whose 64 rows of a tile half are one contiguous 128-byte run in the tile-transposed layout), so the
+//          operand ring only carries tensor-core operands
+// Operand fills per 128 rows drop from 1280 KB to 896 KB (d = 512), 640 KB of them through TMA -- the single-CTA
+// kernel is bound by the per-SM fill rate.  GEMM2 of super-tile i-1 is interleaved with GEMM1 of super-tile i (the
+// R tile of i-1 stays valid until E1 of i starts, which is after every MMA issued before Z(i) was committed), so
+// the tensor pipe only idles during E1; one pool of 16 epilogue warps runs E2 of i-1 and then E1 of i.
 // Warps: 0 producer, 1 MMA (rank 0 issues for the pair), 2..17 epilogue (E2 of super-tile i-1, then E1 of i).
 constexpr int kThreadsP = 64 + 32 * 8 + 32 * 8;      // 576
 constexpr int kFullRing = 8;
@@ -759,7 +759,7 @@ __device__ __forceinline__ void link_chunk(float (&v)[32], uint32_t (&packed)[16
 }
 
 // Fill sequence of iteration i (identical in every role and in both CTAs; `fill` counts 16 KB slots):
-//   for kc in 0..KC-1:  slot A = X (hi n0 | hi n1 | lo n0 | lo n1), slot B = Theta_lo (2 groups) | Theta_hi (2 groups)
+//   for kc in 0..KC-1:  slot A = X (hi n0 | hi n1 | lo n0 | lo n1), slot B = Theta_hi (2 groups) | Theta_lo (2 groups)
 //       after the stages with (kc & 7) == 1 (and i > 0): the 4 E slots of GEMM2 group jbp = kc >> 3 of super-tile i-1,
 //       consumed after stage (kc & 7) == 3
 //   a last iteration i = nIter only carries the GEMM2 groups of the final super-tile.
