@@ -278,3 +278,22 @@ def test_mc_diagnostics_golden(golden):
     for tag, cols in (('stationary', [0, 1, 4]), ('drifting', [0, 3])):
         ok, best = mc.R_hat_convergence_check(x[:, cols], windows)
         assert [float(ok), float(best)] == g['check_%s' % tag].tolist()
+
+
+def test_sharded_psis_rule_random_partitions_and_ties():
+    """Property test of the record rule on tie-heavy data (values on a coarse grid, so the cutoff value is shared
+    by many draws on several ranks) and random, very uneven partitions -- including ranks with fewer than M+1
+    draws."""
+    rs = np.random.RandomState(77)
+    for trial in range(12):
+        n = int(rs.choice([300, 2000, 20000]))
+        x = np.round(rs.standard_t(3, n) * 2.0, 1 if trial % 2 else 2) - 5.0
+        R = int(rs.choice([2, 3, 5, 8]))
+        cuts = np.sort(rs.choice(np.arange(2, n - 2), R - 1, replace=False))
+        parts = np.split(x, cuts)
+        if min(len(p) for p in parts) < 2:
+            continue
+        ref, kref = vo.psislw_1d(x)
+        outs, k = vo.psislw_sharded(parts)
+        assert (np.isinf(k) and np.isinf(kref)) or abs(k - kref) <= 1e-12 * abs(kref), (trial, k, kref)
+        np.testing.assert_allclose(np.concatenate(outs), ref, rtol=0, atol=1e-11)
