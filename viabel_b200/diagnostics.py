@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._tensor import F64, device, is_host, to_dev
+from ._tensor import F64, device, to_dev
 
 __all__ = ['all_diagnostics', 'error_bounds', 'wasserstein_bounds', 'divergence_bound']
 

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._tensor import F64, device, is_host, like_input, to_dev
+from ._tensor import F64, device, is_host, to_dev
 from .approximations import MultivariateT, _MeanField
 from .models import GLMModel, Model
 

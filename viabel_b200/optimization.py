@@ -13,7 +13,7 @@ import torch
 import tqdm
 
 from . import _lib
-from ._tensor import F64, device, is_host, to_dev
+from ._tensor import F64, device, to_dev
 
 __all__ = ['Optimizer', 'StochasticGradientOptimizer', 'RMSProp', 'Adam', 'Adagrad', 'WindowedAdagrad',
            'AveragedRMSProp', 'AveragedAdam']
