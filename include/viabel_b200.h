@@ -158,6 +158,100 @@ int vb_adam_step_f64(double* var_param, const double* grad, double* m, double* n
                      double jitter, int first, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Peer-memory communicator (one process per GPU, NVLink / NVSwitch peer stores).  Replaces nothing in the
+ * reference (single process); it is the exchange step of the data-sharded path: the per-rank
+ * sweep sums [ll(S), gmu(d), ge(d)] are summed with a one-shot all-reduce INSIDE the step's last kernel.
+ *   vb_comm_create : allocates this rank's exchange buffer (cudaMalloc, 2 parities x world slots of slot_bytes)
+ *                    and writes its 64-byte CUDA IPC handle to handle_out (HOST pointer);
+ *   vb_comm_connect: all_handles = world x 64 bytes (HOST), rank order -- the caller all-gathers them with
+ *                    whatever transport it has (torch.distributed in viabel_b200/parallel.py);
+ *   vb_comm_connect_ptrs / vb_comm_buffer: the same for several ranks driven by one process;
+ *   vb_comm_allreduce_sum_f64: in-place sum of n <= slot_bytes/8 doubles, summed in rank order on every
+ *                    rank (bit-identical results everywhere); stream-ordered, no host synchronisation;
+ *   vb_comm_error  : 1 if a collective gave up waiting for a peer (4 s), else 0 (synchronises the device).
+ * ------------------------------------------------------------------------------------- */
+#define VB_COMM_HANDLE_BYTES 64
+int vb_comm_create(void** comm, int rank, int world, size_t slot_bytes, unsigned char* handle_out);
+int vb_comm_connect(void* comm, const unsigned char* all_handles);
+int vb_comm_connect_ptrs(void* comm, void* const* peer_ptrs);
+void* vb_comm_buffer(void* comm);
+int vb_comm_allreduce_sum_f64(void* comm, double* buf, int64_t n, cudaStream_t stream);
+int vb_comm_error(void* comm);
+int vb_comm_destroy(void* comm);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused ELBO-gradient step: the three calls of the reference loop (optimization.py:95-98)
+ *     value, grad = objective(var_param)              objectives.py:154-168
+ *     direction   = sgo.descent_direction(grad)       optimization.py:188-197 (RMSProp), :308-326 (Adam)
+ *     var_param   = objective.update(var_param, lr * direction)        objectives.py:57-59
+ * for ExclusiveKL (entropy or path-derivative form) with a mean-field family on a GLM plugin, enqueued as three
+ * kernels with no host round trip: [draw + reparameterise + operand pack] -> [sweep] -> [partial reduction +
+ * cross-rank all-reduce through `comm` + value + gradient + optimiser + histories].  Everything that changes
+ * from step to step (the draw-stream position, "first step" of the optimiser, history slot) lives in
+ * `counters` on the device, so a captured CUDA graph of one call can be replayed.
+ *
+ * Draws: element i of step t is element counters[2] + t * (S*d rounded up to even) + i of the family's Philox
+ * stream (vb_philox_normal_f64 / vb_philox_student_t_f64), t = counters[0]; with inject_base != 0 the
+ * caller's `base` is used instead (parity by draw injection).
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t family;        /* VB_FAMILY_MF_*                                             */
+  int32_t objective;     /* VB_OBJ_EXCLUSIVE_KL or VB_OBJ_EXCLUSIVE_KL_PATH            */
+  int32_t S, d;          /* Monte Carlo samples, model dimension                        */
+  int32_t optimizer;     /* 0: none (value + gradient only), 1: RMSProp, 2: Adam        */
+  int32_t quantize;      /* draw quantisation, as vb_philox_normal_f64                  */
+  int32_t inject_base;   /* != 0: `base` is an input                                    */
+  int32_t reserved;
+  double df;             /* MFStudentT degrees of freedom                               */
+  double prior_sd;       /* iid N(0, prior_sd^2) prior of the GLM plugin (inf: flat)    */
+  double lr;             /* learning rate                                               */
+  double beta1;          /* RMSProp beta / Adam beta1                                   */
+  double beta2;          /* Adam beta2                                                  */
+  double jitter;
+  uint64_t seed;         /* Philox key of the family's draw stream                      */
+} vb_step_config;
+
+typedef struct {
+  double* var_param;     /* [2d]  in/out (updated when optimizer != 0)                  */
+  double* opt_m;         /* [2d]  Adam momentum (NULL otherwise)                        */
+  double* opt_nu;        /* [2d]  RMSProp / Adam second-moment state                    */
+  uint64_t* counters;    /* [4]   [0] steps taken (history index), [1] optimiser steps taken,
+                          *       [2] stream offset of step 0 (caller-set), [3] reserved  */
+  double* base;          /* [S,d] base draws of the step (out; in when inject_base)     */
+  double* theta;         /* [S,d] out                                                   */
+  double* value;         /* [1]   out                                                   */
+  double* grad;          /* [2d]  out                                                   */
+  double* logp;          /* [S]   out, optional: model log density per sample           */
+  double* direction;     /* [2d]  out, optional: descent direction                      */
+  double* value_hist;    /* [hist_len] optional: value_hist[step]                       */
+  double* param_hist;    /* [ring, 2d] optional ring of the iterates after the update: row step % ring */
+  double* grad_hist;     /* [ring, 2d] optional ring of the gradients                   */
+  double* dir_hist;      /* [ring, 2d] optional ring of the descent directions          */
+  int64_t hist_len, ring;
+} vb_step_buffers;
+
+typedef struct {
+  /* tensor-core path: handle of vb_glm_fast_create and its workspace; or NULL for the float64 path */
+  void* fast_handle;
+  void* fast_workspace;
+  size_t fast_workspace_bytes;
+  /* float64 path: the arguments of vb_glm_sweep_f64; sweep_workspace holds vb_glm_sweep_workspace_bytes
+   * (rounded up to 256) + (S + 2d) * 8 bytes */
+  const double* X;
+  int64_t ldx;
+  const double* y;
+  int64_t N;
+  int32_t link;
+  int32_t reserved;
+  void* sweep_workspace;
+  size_t sweep_workspace_bytes;
+} vb_step_model;
+
+size_t vb_mf_step_workspace_bytes(int S, int d);
+int vb_mf_step_glm(const vb_step_config* cfg, const vb_step_buffers* buf, const vb_step_model* model,
+                   void* comm, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Pareto-smoothed importance sampling and divergence-bound moments
  * (viabel/_psis.py:113-209 psislw, :212-332 gpdfitnew, :335-377 gpinv, :380-396 sumlogs;
  *  viabel/diagnostics.py:148-186 divergence_bound).
@@ -207,8 +301,10 @@ int vb_psis_dist_apply(const double* lw, double* out, int64_t n_local, int64_t i
                        double reff, int world, int rank, double* result, void* workspace,
                        size_t workspace_bytes, cudaStream_t stream);
 
-/* out4[0] = max(lw), out4[1] = sum exp(lw - max)^alpha, out4[2] = sum lw  (out4[3] is scratch) */
-int vb_divergence_moments_f64(const double* lw, int64_t n, double alpha, double* out4,
+/* divergence_bound moments in ONE read of lw after the max (diagnostics.py:148-198), out8 = 8 device doubles:
+ * [0] max(lw), [1] sum r, [2] sum lw, [3] scratch, [4] sum (lw - max)^2, [5] sum r^2, with r = exp(lw - max)^alpha.
+ * [4] and [5] give the Monte Carlo standard errors mean_and_check_mc_error warns about. */
+int vb_divergence_moments_f64(const double* lw, int64_t n, double alpha, double* out8,
                               cudaStream_t stream);
 
 #ifdef __cplusplus

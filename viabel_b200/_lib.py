@@ -58,6 +58,16 @@ _PROTOS = {
     'vb_psis_dist_global': (c_int, [P, c_int64, c_int64, c_double, c_int, P, P, c_size_t, P]),
     'vb_psis_dist_apply': (c_int, [P, P, c_int64, c_int64, c_int64, c_double, c_int, c_int, P, P, c_size_t, P]),
     'vb_divergence_moments_f64': (c_int, [P, c_int64, c_double, P, P]),
+    # peer-memory communicator and the fused step (structures: viabel_b200/engine.py)
+    'vb_comm_create': (c_int, [P, c_int, c_int, c_size_t, P]),
+    'vb_comm_connect': (c_int, [P, P]),
+    'vb_comm_connect_ptrs': (c_int, [P, P]),
+    'vb_comm_buffer': (c_void_p, [P]),
+    'vb_comm_allreduce_sum_f64': (c_int, [P, P, c_int64, P]),
+    'vb_comm_error': (c_int, [P]),
+    'vb_comm_destroy': (c_int, [P]),
+    'vb_mf_step_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'vb_mf_step_glm': (c_int, [P, P, P, P, P, c_size_t, P]),
 }
 
 #: symbols declared in include/viabel_b200.h that this build exports

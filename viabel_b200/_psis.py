@@ -114,6 +114,8 @@ def psislw(lw, Reff=1.0, overwrite_lw=False, return_tail=False):
             kss[i] = res[R_KHAT]
         return out_np, kss
     cols = lw.to(F64).t().contiguous()           # [m, n]: each set contiguous
+    if cols.data_ptr() == lw.data_ptr() and not overwrite_lw:
+        cols = cols.clone()                      # [n,1] and F-ordered inputs: t() is already contiguous -> a view
     for i in range(m):
         res, _, _ = _psis_column(cols[i], cols[i], Reff, False)
         kss[i] = res[R_KHAT]

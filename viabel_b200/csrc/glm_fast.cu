@@ -30,8 +30,10 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
+#include "fast_internal.cuh"
 
 namespace vb {
 namespace fast {
@@ -1405,27 +1407,47 @@ extern "C" int vb_glm_fast_destroy(void* handle) {
   return VB_OK;
 }
 
-extern "C" int vb_glm_fast_sweep(void* handle, const double* theta, const double* base, const double* w, int64_t S,
-                                 int want_grad, double* out_ll, double* out_gmu, double* out_ge, void* workspace,
-                                 size_t workspace_bytes, float* debug, cudaStream_t stream) {
-  // want_grad bit 0: gradients wanted; bit 1: only sum_s ll[s] is needed (each out_ll[s] receives the mean)
-  // (debug + 49152*grid floats, when debug is given, is followed by 128 int64 timestamp slots)
+// ---- internal interface shared with engine.cu (fast_internal.cuh) ----------------------------------------------
+namespace vb {
+namespace fast {
+
+int fast_dims(void* handle, int64_t* N, int* d, int* d_pad) {
   FastModel* m = static_cast<FastModel*>(handle);
-  const int ll_total_only = (want_grad >> 1) & 1;
-  want_grad &= 1;
-  if (!m || !theta || !out_ll || S <= 0) return set_error(VB_ERR_INVALID_ARG, "glm_fast_sweep: bad arguments");
-  if (S > kSP) return set_error(VB_ERR_UNSUPPORTED, "glm_fast_sweep: at most 256 samples per sweep");
-  if (want_grad && (!base || !out_gmu || !out_ge)) return set_error(VB_ERR_INVALID_ARG, "glm_fast_sweep: want_grad needs base, out_gmu, out_ge");
+  if (!m) return set_error(VB_ERR_INVALID_ARG, "glm_fast: null handle");
+  if (N) *N = m->N;
+  if (d) *d = m->d;
+  if (d_pad) *d_pad = m->d_pad;
+  return VB_OK;
+}
+
+int fast_operands(void* handle, void* workspace, size_t workspace_bytes, FastOperands* ops) {
+  FastModel* m = static_cast<FastModel*>(handle);
+  if (!m || !ops) return set_error(VB_ERR_INVALID_ARG, "glm_fast: null handle");
   FastLayout L;
   fast_layout(m->N, m->d_pad, L);
   if (!workspace || workspace_bytes < L.total) return set_error(VB_ERR_WORKSPACE, "glm_fast_sweep: workspace too small");
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0)
     return set_error(VB_ERR_INVALID_ARG, "glm_fast_sweep: workspace must be 1024-byte aligned");
   char* ws = static_cast<char*>(workspace);
-  __half* Th = reinterpret_cast<__half*>(ws + L.off_Th);
-  __half* Tl = reinterpret_cast<__half*>(ws + L.off_Tl);
-  __half* E = reinterpret_cast<__half*>(ws + L.off_E);
-  float* wf = reinterpret_cast<float*>(ws + L.off_w);
+  ops->Th = reinterpret_cast<__half*>(ws + L.off_Th);
+  ops->Tl = reinterpret_cast<__half*>(ws + L.off_Tl);
+  ops->E = reinterpret_cast<__half*>(ws + L.off_E);
+  ops->wf = reinterpret_cast<float*>(ws + L.off_w);
+  return VB_OK;
+}
+
+// Launches the sweep kernel on operands already packed into the workspace (Th, Tl, E, wf); the per-CTA / per-pair
+// partial sums stay in the workspace and are described by `parts` (ll partials are sums of softplus: sign -1).
+int fast_launch(void* handle, void* workspace, size_t workspace_bytes, int S, int want_grad, int ll_total_only,
+                int uniform_w, float* debug, cudaStream_t stream, FastPartials* parts) {
+  FastModel* m = static_cast<FastModel*>(handle);
+  FastOperands ops;
+  int rc = fast_operands(handle, workspace, workspace_bytes, &ops);
+  if (rc) return rc;
+  if (S <= 0 || S > kSP) return set_error(VB_ERR_UNSUPPORTED, "glm_fast_sweep: at most 256 samples per sweep");
+  FastLayout L;
+  fast_layout(m->N, m->d_pad, L);
+  char* ws = static_cast<char*>(workspace);
 
   static thread_local const void* cached_ws = nullptr;
   static thread_local int cached_dpad = 0;
@@ -1436,26 +1458,24 @@ extern "C" int vb_glm_fast_sweep(void* handle, const double* theta, const double
     const uint32_t tb[4] = {64, 32, 2, 2};
     const uint64_t ed[3] = {64, (uint64_t)kSP, dp / 64}, es[2] = {128, (uint64_t)kSP * 128};
     const uint32_t eb[3] = {64, 64, 2};
-    if (reinterpret_cast<char*>(Tl) - reinterpret_cast<char*>(Th) != (ptrdiff_t)(dp * 512))
+    if (reinterpret_cast<char*>(ops.Tl) - reinterpret_cast<char*>(ops.Th) != (ptrdiff_t)(dp * 512))
       return set_error(VB_ERR_CUDA, "glm_fast_sweep: Theta hi/lo are not adjacent");
-    if (!encode_2d(&tmTh, Th, 4 * dp, 32) || !encode_2d(&tmTl, Tl, 4 * dp, 32) || !encode_2d(&tmE, E, (dp / 64) * kSP, 64) ||
-        !encode_nd(&tmTP, Th, 4, td, ts, tb) || !encode_nd(&tmEP, E, 3, ed, es, eb))
+    if (!encode_2d(&tmTh, ops.Th, 4 * dp, 32) || !encode_2d(&tmTl, ops.Tl, 4 * dp, 32) ||
+        !encode_2d(&tmE, ops.E, (dp / 64) * kSP, 64) || !encode_nd(&tmTP, ops.Th, 4, td, ts, tb) ||
+        !encode_nd(&tmEP, ops.E, 3, ed, es, eb))
       return set_error(VB_ERR_CUDA, "glm_fast_sweep: cuTensorMapEncodeTiled failed");
     cached_ws = workspace;
     cached_dpad = m->d_pad;
   }
 
-  VB_CUDA(launch_pdl(fast_prepare_theta_kernel, dim3(128), dim3(256), stream, theta, want_grad ? base : nullptr, w, S, m->d, m->d_pad,
-                     Th, Tl, E, wf));
-
   Params p;
   p.N = m->N;
   p.d_pad = m->d_pad;
-  p.S = (int)S;
+  p.S = S;
   p.numTiles = (int)m->numTiles;
   p.want_grad = want_grad;
   p.ll_total_only = ll_total_only;
-  p.w = wf;
+  p.w = ops.wf;
   p.ll_part = reinterpret_cast<double*>(ws + L.off_ll);
   p.gmu_part = reinterpret_cast<double*>(ws + L.off_gmu);
   p.ge_part = reinterpret_cast<double*>(ws + L.off_ge);
@@ -1463,33 +1483,45 @@ extern "C" int vb_glm_fast_sweep(void* handle, const double* theta, const double
   p.tim = debug ? reinterpret_cast<long long*>(debug + (size_t)49152 * L.grid) : nullptr;
   p.Xh = m->Xh;
   p.Xl = m->Xl;
-  p.uniform_w = w ? 0 : 1;
+  p.uniform_w = uniform_w;
   // kernel choice: the CTA-pair kernel unless the device cannot co-schedule clusters of two such CTAs
   // (VB_FAST_KERNEL=single forces the one-CTA kernel, for A/B measurements)
-  static int pair_clusters = -1;
-  if (pair_clusters < 0) {
-    VB_CUDA(cudaFuncSetAttribute(glm_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    VB_CUDA(cudaFuncSetAttribute(glm_fast_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    const char* env = getenv("VB_FAST_KERNEL");
-    int nc = 0;
-    if (!(env && strcmp(env, "single") == 0)) {
-      cudaLaunchConfig_t qc = {};
-      qc.gridDim = dim3(sm_count() & ~1);
-      qc.blockDim = dim3(kThreadsP);
-      qc.dynamicSmemBytes = kSmemBytes;
-      cudaLaunchAttribute qa[1];
-      qa[0].id = cudaLaunchAttributeClusterDimension;
-      qa[0].val.clusterDim.x = 2;
-      qa[0].val.clusterDim.y = 1;
-      qa[0].val.clusterDim.z = 1;
-      qc.attrs = qa;
-      qc.numAttrs = 1;
-      if (cudaOccupancyMaxActiveClusters(&nc, glm_fast_pair_kernel, &qc) != cudaSuccess) {
-        cudaGetLastError();
-        nc = 0;
+  int pair_clusters = 0;
+  {
+    // function attributes and the cluster occupancy are per device: cache them per device ordinal, under a lock
+    static std::mutex mu;
+    static int cached[64];
+    static bool ready[64] = {false};
+    int dev = 0;
+    VB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return set_error(VB_ERR_UNSUPPORTED, "glm_fast_sweep: device ordinal out of range");
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ready[dev]) {
+      VB_CUDA(cudaFuncSetAttribute(glm_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      VB_CUDA(cudaFuncSetAttribute(glm_fast_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      const char* env = getenv("VB_FAST_KERNEL");
+      int nc = 0;
+      if (!(env && strcmp(env, "single") == 0)) {
+        cudaLaunchConfig_t qc = {};
+        qc.gridDim = dim3(sm_count() & ~1);
+        qc.blockDim = dim3(kThreadsP);
+        qc.dynamicSmemBytes = kSmemBytes;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = 2;
+        qa[0].val.clusterDim.y = 1;
+        qa[0].val.clusterDim.z = 1;
+        qc.attrs = qa;
+        qc.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&nc, glm_fast_pair_kernel, &qc) != cudaSuccess) {
+          cudaGetLastError();
+          nc = 0;
+        }
       }
+      cached[dev] = nc;
+      ready[dev] = true;
     }
-    pair_clusters = nc;
+    pair_clusters = cached[dev];
   }
   int nblk_ll = L.grid, nblk_g = L.grid;
   if (pair_clusters > 0) {
@@ -1518,11 +1550,45 @@ extern "C" int vb_glm_fast_sweep(void* handle, const double* theta, const double
     glm_fast_kernel<<<L.grid, kThreads, kSmemBytes, stream>>>(m->tmXh, m->tmXl, m->tmXh2, m->tmXl2, tmTh, tmTl, tmE, p);
     VB_CHECK_LAUNCH();
   }
+  if (parts) {
+    parts->ll_part = p.ll_part;
+    parts->gmu_part = p.gmu_part;
+    parts->ge_part = p.ge_part;
+    parts->nblk_ll = nblk_ll;
+    parts->nblk_g = nblk_g;
+    parts->stride_ll = kSP;
+    parts->stride_g = m->d_pad;
+  }
+  return VB_OK;
+}
+
+}  // namespace fast
+}  // namespace vb
+
+extern "C" int vb_glm_fast_sweep(void* handle, const double* theta, const double* base, const double* w, int64_t S,
+                                 int want_grad, double* out_ll, double* out_gmu, double* out_ge, void* workspace,
+                                 size_t workspace_bytes, float* debug, cudaStream_t stream) {
+  // want_grad bit 0: gradients wanted; bit 1: only sum_s ll[s] is needed (each out_ll[s] receives the mean)
+  // (debug + 49152*grid floats, when debug is given, is followed by 128 int64 timestamp slots)
+  FastModel* m = static_cast<FastModel*>(handle);
+  const int ll_total_only = (want_grad >> 1) & 1;
+  want_grad &= 1;
+  if (!m || !theta || !out_ll || S <= 0) return set_error(VB_ERR_INVALID_ARG, "glm_fast_sweep: bad arguments");
+  if (S > kSP) return set_error(VB_ERR_UNSUPPORTED, "glm_fast_sweep: at most 256 samples per sweep");
+  if (want_grad && (!base || !out_gmu || !out_ge)) return set_error(VB_ERR_INVALID_ARG, "glm_fast_sweep: want_grad needs base, out_gmu, out_ge");
+  FastOperands ops;
+  int rc = fast_operands(handle, workspace, workspace_bytes, &ops);
+  if (rc) return rc;
+  VB_CUDA(launch_pdl(fast_prepare_theta_kernel, dim3(128), dim3(256), stream, theta, want_grad ? base : nullptr, w, S, m->d, m->d_pad,
+                     ops.Th, ops.Tl, ops.E, ops.wf));
+  FastPartials parts;
+  rc = fast_launch(handle, workspace, workspace_bytes, (int)S, want_grad, ll_total_only, w ? 0 : 1, debug, stream, &parts);
+  if (rc) return rc;
   // ll = -sum softplus; gradient partials summed over the pairs -- one launch for the three arrays
   Reduce3 r;
-  r.part[0] = p.ll_part;  r.out[0] = out_ll;  r.nblk[0] = nblk_ll; r.stride[0] = kSP;      r.n[0] = S;                    r.sign[0] = -1.0;
-  r.part[1] = p.gmu_part; r.out[1] = out_gmu; r.nblk[1] = nblk_g;  r.stride[1] = m->d_pad; r.n[1] = want_grad ? m->d : 0; r.sign[1] = 1.0;
-  r.part[2] = p.ge_part;  r.out[2] = out_ge;  r.nblk[2] = nblk_g;  r.stride[2] = m->d_pad; r.n[2] = want_grad ? m->d : 0; r.sign[2] = 1.0;
+  r.part[0] = parts.ll_part;  r.out[0] = out_ll;  r.nblk[0] = parts.nblk_ll; r.stride[0] = kSP;      r.n[0] = S;                    r.sign[0] = -1.0;
+  r.part[1] = parts.gmu_part; r.out[1] = out_gmu; r.nblk[1] = parts.nblk_g;  r.stride[1] = m->d_pad; r.n[1] = want_grad ? m->d : 0; r.sign[1] = 1.0;
+  r.part[2] = parts.ge_part;  r.out[2] = out_ge;  r.nblk[2] = parts.nblk_g;  r.stride[2] = m->d_pad; r.n[2] = want_grad ? m->d : 0; r.sign[2] = 1.0;
   const int64_t nmax = want_grad && m->d > S ? m->d : S;
   VB_CUDA(launch_pdl(reduce_partials3_kernel, dim3((unsigned)((nmax + 31) / 32), want_grad ? 3 : 1), dim3(256), stream, r));
   return VB_OK;

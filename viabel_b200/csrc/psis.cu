@@ -17,6 +17,8 @@
 // reported and the caller re-runs in exact mode, which finds the cutoff with full radix passes.
 #include <float.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace vb {
@@ -1131,7 +1133,8 @@ __global__ void psis_exact_scan_kernel(PsisScalars* sc, int shift, int bits, uns
 __global__ void psis_exact_begin_kernel(PsisScalars* sc) { sc->kth = (unsigned long long)sc->M + 1; sc->prefix = 0; }
 
 // ---- stand-alone divergence-bound moments (diagnostics.py:148-186) --------------------------------
-// pass 1: max; pass 2: sum exp(alpha (x - max)), sum x.  out[0]=max, out[1]=sum exp, out[2]=sum x
+// pass 1: max; pass 2: sums.  out[0]=max, out[1]=sum r, out[2]=sum x, out[4]=sum (x-max)^2, out[5]=sum r^2,
+// r = exp(x - max)^alpha (the second moments feed mean_and_check_mc_error, diagnostics.py:189-198)
 __global__ void __launch_bounds__(256) dbound_max_kernel(const double* __restrict__ x, int64_t n, unsigned long long* mk) {
   double mx = -INFINITY;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -1143,17 +1146,25 @@ __global__ void __launch_bounds__(256) dbound_sum_kernel(const double* __restric
                                                          const unsigned long long* mk, double* __restrict__ out) {
   __shared__ double red[32];
   const double mx = dkey_inv(*mk);
-  double se = 0.0, sx = 0.0;
+  double se = 0.0, sx = 0.0, sc = 0.0, se2 = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double v = x[i];
-    se += pow(exp(v - mx), alpha);        // np.exp(lw - max) ** alpha
+    const double r = pow(exp(v - mx), alpha);        // np.exp(lw - max) ** alpha
+    se += r;
+    se2 += r * r;
     sx += v;
+    const double c = v - mx;
+    sc += c * c;
   }
   se = block_sum(se, red);
   sx = block_sum(sx, red);
+  sc = block_sum(sc, red);
+  se2 = block_sum(se2, red);
   if (threadIdx.x == 0) {
     atomicAdd(&out[1], se);
     atomicAdd(&out[2], sx);
+    atomicAdd(&out[4], sc);
+    atomicAdd(&out[5], se2);
     if (blockIdx.x == 0) out[0] = mx;
   }
 }
@@ -1222,13 +1233,20 @@ static void psis_plan(int64_t n, double reff, PsisPlan& p, int64_t n_global = 0,
   p.total = off;
 }
 
-static bool g_tab_ready = false;
+// The table is a per-device __device__ symbol: track its upload per device (a process may drive several GPUs)
+// and serialise the first upload (several host threads may enter together).
+static std::mutex g_tab_mutex;
+static bool g_tab_ready[64] = {false};
 static int ensure_exp_table() {
-  if (g_tab_ready) return VB_OK;
+  int dev = 0;
+  VB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return set_error(VB_ERR_UNSUPPORTED, "psis: device ordinal out of range");
+  std::lock_guard<std::mutex> lock(g_tab_mutex);
+  if (g_tab_ready[dev]) return VB_OK;
   double tab[kExpTab];
   for (int j = 0; j < kExpTab; ++j) tab[j] = exp2((double)j / (double)kExpTab);
   VB_CUDA(cudaMemcpyToSymbol(g_exp2_tab, tab, sizeof(tab)));
-  g_tab_ready = true;
+  g_tab_ready[dev] = true;
   return VB_OK;
 }
 
@@ -1539,8 +1557,8 @@ extern "C" int vb_psis_dist_apply(const double* lw, double* out, int64_t n_local
 extern "C" int vb_divergence_moments_f64(const double* lw, int64_t n, double alpha, double* out3, cudaStream_t stream) {
   if (n <= 0 || !lw || !out3) return set_error(VB_ERR_INVALID_ARG, "divergence_moments: bad arguments");
   if (!(alpha > 1.0)) return set_error(VB_ERR_INVALID_ARG, "alpha must be greater than 1");      // diagnostics.py:172-173
-  // out3[3] doubles as scratch for the max key
-  VB_CUDA(cudaMemsetAsync(out3, 0, sizeof(double) * 4, stream));
+  // out[3] doubles as scratch for the max key
+  VB_CUDA(cudaMemsetAsync(out3, 0, sizeof(double) * 8, stream));
   int grid = sm_count() * 8;
   const int64_t need = (n + 255) / 256;
   if (need < grid) grid = (int)need;

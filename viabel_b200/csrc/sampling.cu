@@ -1,32 +1,9 @@
 // Counter-based base draws (Philox4x32-10): normal, chi-square, Student-t.
 // Replaces numpy RandomState.randn / chisquare / standard_t (reference approximations.py:216,
 // :274, :345-347).  The numpy MT19937 streams are NOT reproduced; parity is by draw injection.
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
-
-#include "common.cuh"
+#include "philox_draws.cuh"
 
 namespace vb {
-
-// quantize: 1 = bfloat16 (8-bit mantissa), 2 = float16 (11-bit mantissa); both are exact operands
-// of the fp16 tensor-core path (a bf16 value in the normal fp16 range is an fp16 value)
-__device__ __forceinline__ double quantize_draw(double x, int mode) {
-  if (mode == 2) return (double)__half2float(__float2half_rn((float)x));
-  return (double)__bfloat162float(__float2bfloat16_rn((float)x));
-}
-
-// two independent N(0,1) from one Philox block (Box-Muller, 53-bit uniforms)
-__device__ __forceinline__ void normal_pair(const Philox& ph, uint64_t ctr, uint64_t stream_id, double& z0,
-                                            double& z1) {
-  uint32_t r[4];
-  ph(ctr, stream_id, r);
-  const double u1 = u01_53(r[0], r[1]), u2 = u01_53(r[2], r[3]);
-  const double rad = sqrt(-2.0 * log(u1));
-  double sn, cs;
-  sincospi(2.0 * u2, &sn, &cs);
-  z0 = rad * cs;
-  z1 = rad * sn;
-}
 
 template <typename T>
 __global__ void philox_normal_kernel(T* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset,
@@ -54,30 +31,6 @@ __global__ void philox_normal_kernel(T* __restrict__ out, int64_t n, uint64_t se
     out[2 * p] = (T)z0;
     if (2 * p + 1 < n) out[2 * p + 1] = (T)z1;
   }
-}
-
-// Marsaglia-Tsang gamma(shape a >= 1/3 boosted), counter = element, attempts on the high word
-__device__ double gamma_draw(const Philox& ph, uint64_t elem, uint64_t stream_id, double a) {
-  double boost = 1.0;
-  if (a < 1.0) {
-    uint32_t r[4];
-    ph(elem, stream_id | (1ull << 62), r);
-    boost = pow(u01_53(r[0], r[1]), 1.0 / a);
-    a += 1.0;
-  }
-  const double dd = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * dd);
-  for (uint64_t attempt = 0; attempt < 64; ++attempt) {
-    double x, unused;
-    normal_pair(ph, elem, stream_id | ((2 * attempt + 1) << 40), x, unused);
-    double v = 1.0 + c * x;
-    if (v <= 0.0) continue;
-    v = v * v * v;
-    uint32_t r[4];
-    ph(elem, stream_id | ((2 * attempt + 2) << 40), r);
-    const double u = u01_53(r[0], r[1]);
-    if (log(u) < 0.5 * x * x + dd - dd * v + dd * log(v)) return boost * dd * v;
-  }
-  return boost * dd;  // unreachable in practice (acceptance > 95% per attempt)
 }
 
 __global__ void philox_chisquare_kernel(double* __restrict__ out, int64_t n, double df, uint64_t seed,

@@ -16,16 +16,18 @@ __all__ = ['all_diagnostics', 'error_bounds', 'wasserstein_bounds', 'divergence_
 
 
 def _moments(log_weights, alpha):
+    """max, sum r, sum lw, sum (lw-max)^2, sum r^2 with r = exp(lw-max)^alpha: one kernel pair, one D2H copy."""
     lw = to_dev(log_weights).reshape(-1)
-    out = torch.empty(4, dtype=F64, device=lw.device)
+    out = torch.empty(8, dtype=F64, device=lw.device)
     _lib.check(_lib.lib.vb_divergence_moments_f64(_lib.ptr(lw), lw.numel(), float(alpha), _lib.ptr(out),
                                                   _lib.stream()))
-    mx, sexp, sx, _ = out.cpu().numpy()
-    return lw, float(mx), float(sexp), float(sx)
+    h = out.cpu().numpy()
+    return lw.numel(), float(h[0]), float(h[1]), float(h[2]), float(h[4]), float(h[5])
 
 
-def _mc_warn(mean, sumsq_centered, n, name, atol=0.01):
-    s = np.sqrt(max(sumsq_centered, 0.0) / n) / np.sqrt(n)
+def _mc_warn(mean, second_moment, n, name, atol=0.01):
+    """mean_and_check_mc_error (diagnostics.py:189-198): warn when std(a) / sqrt(n) > atol."""
+    s = np.sqrt(max(second_moment - mean * mean, 0.0)) / np.sqrt(n)
     if s > atol:  # pragma: no cover
         warn('significant Monte Carlo error when computing {} (mean = {}, standard deviation = {})'
              .format(name, mean, s))
@@ -35,12 +37,12 @@ def divergence_bound(log_weights, *, alpha=2., log_norm_bound=None, return_log_n
     """Bound on the alpha-divergence (diagnostics.py:148-186)."""
     if alpha <= 1:
         raise ValueError('alpha must be greater than 1')
-    lw, mx, sexp, sx = _moments(log_weights, alpha)
-    n = lw.numel()
+    n, mx, sexp, sx, sc2, sexp2 = _moments(log_weights, alpha)
+    _mc_warn(sexp / n, sexp2 / n, n, 'CUBO')
     cubo = np.log(sexp / n) / alpha + mx
     if log_norm_bound is None:
         log_norm_bound = sx / n
-        _mc_warn(log_norm_bound, float(((lw - log_norm_bound) ** 2).sum()), n, 'ELBO')
+        _mc_warn(log_norm_bound - mx, sc2 / n, n, 'ELBO')      # moments of lw - max: same variance
     dalpha = alpha / (alpha - 1) * (cubo - log_norm_bound)
     if return_log_norm_bound:
         return dalpha, log_norm_bound

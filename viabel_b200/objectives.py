@@ -14,6 +14,7 @@ from . import _lib
 from ._tensor import F64, device, is_host, to_dev
 from .approximations import MultivariateT, _MeanField
 from .models import GLMModel, Model
+from .parallel import broadcast_seed, is_distributed
 
 __all__ = ['VariationalObjective', 'StochasticVariationalObjective', 'ExclusiveKL', 'AlphaDivergence',
            'DISInclusiveKL']
@@ -193,7 +194,26 @@ class ExclusiveKL(StochasticVariationalObjective):
             raise ValueError("Name of approximation must be one of 'full', 'mean_only', 'loo_diag_approx', 'loo_direct_approx' or None object.")
         super().__init__(approx, model, num_mc_samples)
 
+    def _engine(self, inject, S):
+        """Cached fused step (engine.FusedStep, no optimiser) for this objective, or None when the
+        (family, model) pair has none."""
+        from .engine import FusedStep, fused_step_supported
+        if not fused_step_supported(self):
+            return None
+        key = (bool(inject), int(S))
+        eng = self._engines.get(key)
+        if eng is not None and not eng.matches(self):
+            eng = None
+        if eng is None:
+            try:
+                eng = FusedStep(self, None, inject_base=inject, S=S)
+            except NotImplementedError:
+                return None
+            self._engines[key] = eng
+        return eng
+
     def _update_objective_and_grad(self):
+        self._engines = {}
         if self.hessian_approx_method is not None:
             def unsupported(var_param):
                 raise NotImplementedError('control-variate estimators are not on the B200 hot path yet')
@@ -203,6 +223,17 @@ class ExclusiveKL(StochasticVariationalObjective):
 
         def objective_and_grad(var_param, base=None):
             host = is_host(var_param)
+            S = self.num_mc_samples if base is None else int(base.shape[0] if hasattr(base, 'shape') else len(base))
+            eng = self._engine(base is not None, S) if self.approx is not None and self.model is not None else None
+            if eng is not None:
+                # draw + reparameterise + pack | sweep | reduce + value + gradient: three kernels, one graph launch
+                if base is not None:
+                    eng.base.copy_(to_dev(base).reshape(S, -1))
+                if host:
+                    return eng.evaluate_host(var_param)
+                eng.set_param(var_param)
+                eng.run(1)
+                return eng.value[0].clone(), eng.grad.clone()
             value, grad = _mf_objective(self.approx, self.model, self.num_mc_samples, obj, 0.0,
                                         var_param, base=base)
             if host:
@@ -235,6 +266,9 @@ class AlphaDivergence(StochasticVariationalObjective):
             host = is_host(var_param)
             # objectives.py:455: a fresh seed from the GLOBAL numpy RNG, shared by both passes
             seed = np.random.randint(2 ** 32, dtype=np.uint64) if base is None else None
+            if seed is not None and getattr(self.model, 'sharded', False):
+                # every rank must evaluate the SAME samples: rank 0's seed wins (ranks' global RNGs are not in step)
+                seed = broadcast_seed(int(seed), getattr(self.model, 'process_group', None))
             value, grad = _mf_objective(self.approx, self.model, self.num_mc_samples, _lib.OBJ_ALPHA,
                                         self.alpha, var_param, base=base, seed=seed)
             if host:
@@ -300,6 +334,37 @@ class DISInclusiveKL(StochasticVariationalObjective):
             eps_guess = self._max_eps
         return eps_guess, ess, w
 
+    def _clip_weights(self, w):
+        """Clip weights to `w_clip_threshold` x their sum, scaling the others up (objectives.py:368-386).
+        The reference's branch for a threshold below 1 calls a float (`sum_unclipped(...)`, :385) and raises
+        TypeError; this is the evident intent: clipped weights take the value that makes each of them exactly
+        `threshold` x the new total."""
+        thr = float(self._w_clip_threshold)
+        w = w.clone()
+        for _ in range(int(w.numel()) + 1):
+            total = w.sum()
+            if not bool((w > total * thr).any()):
+                return w
+            to_clip = w >= total * thr
+            n_to_clip = int(to_clip.sum())
+            sum_unclipped = w[~to_clip].sum()
+            if float(sum_unclipped) == 0.0 or thr * n_to_clip >= 1.0:
+                return w                        # impossible to clip further
+            w[to_clip] = thr * sum_unclipped / (1.0 - thr * n_to_clip)
+        return w
+
+    def _resample_indices(self, S, p):
+        """np.random.choice from the GLOBAL numpy RNG, as the reference (:408-409).  With a sharded model every
+        rank must resample the same draws: rank 0 draws, the others receive."""
+        idx = np.random.choice(S, size=self._resampling_batch_size, p=p / p.sum())
+        group = getattr(self.model, 'process_group', None)
+        if getattr(self.model, 'sharded', False) and is_distributed(group):
+            import torch.distributed as dist
+            t = torch.as_tensor(idx, dtype=torch.int64, device=device())
+            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            idx = t.cpu().numpy()
+        return idx
+
     def _score_terms(self, vp, x):
         """-log q(lambda; x) summed with weights needs d(log q)/d[mu, log sigma] at fixed x."""
         approx = self.approx
@@ -337,7 +402,8 @@ class DISInclusiveKL(StochasticVariationalObjective):
                 log_prior = self._temper_prior.log_density(to_dev(self._temper_prior_params), x)
                 self._eps, ess, w = self._get_eps_and_weights(self._eps, log_prior, self._state_log_p,
                                                               self._state_log_q)
-                self._state_w = w                       # clipping (:368-386) is unreachable at threshold 10
+                w = self._clip_weights(w)               # a no-op for thresholds >= 1 (the default is 10)
+                self._state_w = w
                 self._state_w_sum = w.sum()
                 self._state_w_normalized = w / self._state_w_sum
             self._objective_step += 1
@@ -346,7 +412,7 @@ class DISInclusiveKL(StochasticVariationalObjective):
                 value = -(wts * approx.log_density(vp, xs)).sum()
             else:
                 p = self._state_w_normalized.cpu().numpy()
-                idx = np.random.choice(S, size=self._resampling_batch_size, p=p / p.sum())   # global RNG (:408)
+                idx = self._resample_indices(S, p)
                 xs = self._state_samples[torch.as_tensor(idx, device=vp.device)]
                 scale = self._state_w_sum / S / xs.shape[0]
                 wts = scale.expand(xs.shape[0])

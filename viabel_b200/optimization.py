@@ -27,7 +27,7 @@ def _to_numpy_results(results):
     out = {}
     for key, hist in results.items():
         if isinstance(hist, list) and len(hist) and isinstance(hist[0], torch.Tensor):
-            out[key] = torch.stack([h.reshape(-1) if h.dim() else h for h in hist]).cpu().numpy()
+            out[key] = torch.stack(list(hist)).cpu().numpy()       # keeps the parameter's own shape
         elif isinstance(hist, torch.Tensor):
             out[key] = hist.cpu().numpy()
         else:
@@ -67,10 +67,77 @@ class StochasticGradientOptimizer(Optimizer):
         var_param -= self._learning_rate * direction
         return direction if want_dir else None
 
+    # -- fused path: the whole loop as graph replays of the three-kernel step (engine.FusedStep) -------
+    def _export_state(self, eng):
+        """Optimiser state -> engine (the state persists across optimize() calls, as in the reference)."""
+
+    def _import_state(self, eng):
+        """Engine -> optimiser state."""
+
+    def _history_length(self, n_iters):
+        """Length of the reference's trimmed iterate list after n_iters iterations (optimization.py:103-106)."""
+        iap = self._iterate_avg_prop
+        if iap is None:
+            return n_iters if self._diagnostics else 0
+        L = 0
+        for k in range(n_iters):
+            L += 1
+            if L > iap * k:
+                L -= 1
+        return L
+
+    def _optimize_fused(self, n_iters, objective, init_param):
+        from .engine import FusedStep
+        iap = self._iterate_avg_prop
+        L = self._history_length(n_iters)
+        window = max(1, int((n_iters - 1) * iap)) if iap is not None else 0
+        ring = n_iters if self._diagnostics else max(L, window, 1)
+        eng = FusedStep(objective, self, ring=ring, hist_len=n_iters, want_dir_hist=self._diagnostics)
+        eng.set_param(init_param)
+        self._export_state(eng)
+        done = 0
+        chunk = 100 if self.progress else 1000
+        bar = tqdm.tqdm(total=n_iters, disable=not self.progress)
+        try:
+            while done < n_iters:
+                m = min(chunk, n_iters - done)
+                eng.run(m)
+                done += m
+                if self.progress:
+                    bar.update(m)
+                    recent = eng.value_hist[max(0, done - 1000):done]
+                    bar.set_description('average loss = {:,.5g}'.format(float(recent.mean())))
+        except (KeyboardInterrupt, StopIteration):  # pragma: no cover
+            pass
+        finally:
+            bar.close()
+        torch.cuda.current_stream().synchronize()
+        eng.check_comm()
+        self._import_state(eng)
+        results = {'value_history': eng.value_hist[:done].cpu().numpy()}
+        k = done - 1
+        if (self._diagnostics or iap is not None) and done > 0:
+            keep = self._history_length(done)
+            results['variational_param_history'] = eng.last_rows(eng.param_hist, keep).cpu().numpy()
+        if self._diagnostics:
+            results['descent_dir_history'] = eng.last_rows(eng.dir_hist, done).cpu().numpy()
+        if iap is not None and done > 0 and self._history_length(done) > 0:
+            w = min(max(1, int(k * iap)), self._history_length(done))
+            results['opt_param'] = eng.last_rows(eng.param_hist, w).mean(dim=0).cpu().numpy()
+        else:
+            results['opt_param'] = eng.vp.cpu().numpy()
+        return results
+
     def optimize(self, n_iters, objective, init_param, init_hamflow_model_param=None,
                  init_hamflow_rho_param=None):
         """The reference loop (optimization.py:83-127) with device-resident state."""
+        from .engine import fused_step_supported
         from .objectives import VariationalObjective
+        if n_iters > 0 and np.ndim(init_param) == 1 and fused_step_supported(objective, self):
+            try:
+                return self._optimize_fused(n_iters, objective, init_param)
+            except NotImplementedError:
+                pass
         var_param = to_dev(init_param).clone()
         iap = self._iterate_avg_prop
         results = defaultdict(list)
@@ -137,6 +204,17 @@ class RMSProp(StochasticGradientOptimizer):
         self._avg_grad_sq = nu
         return grad / _sqrt(self._jitter + nu)
 
+    def _export_state(self, eng):
+        if self._avg_grad_sq is not None:
+            eng.opt_nu.copy_(to_dev(self._avg_grad_sq))
+            eng.counters[1] = 1
+        else:
+            eng.counters[1] = 0
+
+    def _import_state(self, eng):
+        if eng.steps_done > 0:
+            self._avg_grad_sq = eng.opt_nu.clone()
+
     def _fused_step(self, var_param, grad, want_dir):
         first = self._avg_grad_sq is None or not isinstance(self._avg_grad_sq, torch.Tensor)
         if first:
@@ -177,6 +255,19 @@ class Adam(StochasticGradientOptimizer):
             nu = nu + (1. - b2) * grad ** 2
         self._momentum, self._avg_grad_sq = m, nu
         return m / _sqrt(self._jitter + nu)
+
+    def _export_state(self, eng):
+        if self._momentum is not None:
+            eng.opt_m.copy_(to_dev(self._momentum))
+            eng.opt_nu.copy_(to_dev(self._avg_grad_sq))
+            eng.counters[1] = 1
+        else:
+            eng.counters[1] = 0
+
+    def _import_state(self, eng):
+        if eng.steps_done > 0:
+            self._momentum = eng.opt_m.clone()
+            self._avg_grad_sq = eng.opt_nu.clone()
 
     def _fused_step(self, var_param, grad, want_dir):
         first = self._momentum is None or not isinstance(self._momentum, torch.Tensor)
