@@ -4,17 +4,28 @@ Bayesian logistic regression N=1e6, d=512, S=256, MFGaussian + RMSProp (syntheti
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--path f64|fast] [--impl reference]
 
-One "step" = objective(var_param) (Philox draws -> fused sweep over all N observations ->
-value + gradient) followed by the fused RMSProp update, exactly the three hot-path calls of the
-reference loop (optimization.py:95-98).  For N > 1 the observations are sharded over the ranks
-(strong scaling of the same problem) and the S + 2d partial sums are all-reduced with NCCL.
-Prints ONE JSON line (rank 0).
+One "step" = the three hot-path calls of the reference loop (optimization.py:95-98):
+objective(var_param) (Philox draws -> sweep over all N observations -> value + gradient),
+descent_direction(grad) and update -- here ONE enqueue of three kernels (viabel_b200.engine.FusedStep,
+the same object RMSProp.optimize() drives), replayed from a CUDA graph.  For N > 1 the observations
+are sharded over the ranks (strong scaling of the same problem) and the S + 2d partial sums are
+exchanged inside the step's last kernel through peer memory.  Prints ONE JSON line (rank 0).
+
+`--impl reference` times the CPU arm: the numpy float64 oracle (a port: the reference's own
+autograd path cannot run in this image) on the FULL problem, row blocks spread over all host cores.
 """
+import os
+import sys
+
+if '--impl' in sys.argv and 'reference' in sys.argv:
+    # the CPU arm spreads row blocks over a thread pool: one BLAS thread per worker (torchrun exports
+    # OMP_NUM_THREADS=1 anyway; set before numpy loads its BLAS)
+    for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_v] = '1'
+
 import argparse
 import json
-import os
 import subprocess
-import sys
 import tempfile
 import time
 
@@ -25,7 +36,7 @@ sys.path.insert(0, ROOT)
 
 N_OBS, DIM, S_MC = 1000000, 512, 256
 DATA_SEED, DRAW_SEED = 20260117, 1234
-CPU_SAMPLE_ROWS = 100000
+CPU_SAMPLE_ROWS = 200000
 
 
 def parse():
@@ -40,13 +51,21 @@ def parse():
     ap.add_argument('--mc', type=int, default=S_MC)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-psis', action='store_true')
+    ap.add_argument('--no-f64', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='enqueue every step from Python instead of replaying graphs')
     ap.add_argument('--psis-draws', type=int, default=100000000)
+    ap.add_argument('--ref-seconds', type=float, default=150.0, help='time budget of the reference arm')
     return ap.parse_args()
+
+
+def workload_name(N, d, S):
+    return 'bayes-logistic N=%d d=%d S=%d MFGaussian+RMSProp (BASELINE configs[%d])' % (
+        N, d, S, 2 if (N, d) == (10000000, 1024) else 1)
 
 
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the numpy oracle (a port of the reference iteration; the reference's own autograd
-# path cannot run in this image -- autograd/paragami are absent) on a bounded sample of rows.
+# path cannot run in this image -- autograd/paragami are absent), row blocks over all host cores.
 # ----------------------------------------------------------------------------------------------
 def host_problem(n_rows, d, seed):
     rs = np.random.RandomState(seed)
@@ -56,49 +75,81 @@ def host_problem(n_rows, d, seed):
     return X, y
 
 
-def cpu_iterations(n_rows, d, S, steps, warmup):
-    """Returns seconds per iteration of the oracle on n_rows observations."""
+class CpuIteration(object):
+    """The oracle's ELBO step with the N observations split into row blocks evaluated by a thread pool
+    (numpy releases the GIL in BLAS and in its elementwise loops): the same arithmetic as
+    oracle.viabel_oracle.elbo_step_logistic, using every host core."""
+
+    def __init__(self, X, y, workers):
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import viabel_oracle as vo
+        self.vo, self.X, self.y = vo, X, y
+        self.workers = max(1, int(workers))
+        self.pool = ThreadPoolExecutor(self.workers)
+        n = X.shape[0]
+        nb = max(self.workers * 4, 1)
+        edges = np.linspace(0, n, nb + 1).astype(np.int64)
+        self.blocks = [(int(a), int(b)) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+        self.state = {}
+
+    def model(self, theta):
+        vo = self.vo
+        lp, gp = vo.gauss_prior(theta, 10.0)
+
+        def part(blk):
+            f, G = vo.logistic_logp_grad(theta, self.X[blk[0]:blk[1]], self.y[blk[0]:blk[1]], 10.0, chunk=16384)
+            return f - lp, G - gp
+
+        f, G = lp.copy(), gp.copy()
+        for fb, Gb in self.pool.map(part, self.blocks):
+            f += fb
+            G += Gb
+        return f, G
+
+    def step(self, vp, eps, lr=0.01):
+        vo = self.vo
+        value, grad, _ = vo.exclusive_kl_meanfield(vp, eps, self.model)
+        return vp - lr * vo.rmsprop_direction(self.state, grad), value, grad
+
+
+def cpu_iterations(n_rows, d, S, steps, warmup, budget_s=None):
+    """(seconds per iteration, iterations timed) of the oracle on n_rows observations."""
     from oracle import viabel_oracle as vo
     X, y = host_problem(n_rows, d, DATA_SEED)
+    it = CpuIteration(X, y, os.cpu_count() or 1)
     rs = np.random.RandomState(DRAW_SEED)
     vp = vo.mfg_init_param(d)
-    state = {}
     times = []
-    for it in range(warmup + steps):
+    t_start = time.perf_counter()
+    for k in range(warmup + steps):
         eps = rs.standard_normal((S, d))
         t0 = time.perf_counter()
-        vp, _, _ = vo.elbo_step_logistic(vp, eps, X, y, state, lr=0.01)
-        if it >= warmup:
-            times.append(time.perf_counter() - t0)
-    return float(np.mean(times))
-
-
-def cpu_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        n = [p.get('num_threads', 1) for p in threadpool_info() if p.get('user_api') == 'blas']
-        return max(n) if n else (os.cpu_count() or 1)
-    except Exception:
-        return os.cpu_count() or 1
+        vp, _, _ = it.step(vp, eps)
+        dt = time.perf_counter() - t0
+        if k >= warmup:
+            times.append(dt)
+        if budget_s is not None and len(times) >= 2 and time.perf_counter() - t_start + dt > budget_s:
+            break
+    return float(np.mean(times)), len(times), it.workers
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    rows = min(CPU_SAMPLE_ROWS, args.n_obs)
-    sec = cpu_iterations(rows, args.dim, args.mc, args.steps, max(1, min(args.warmup, 1)))
-    scaled = sec * (args.n_obs / rows)          # seconds per full-size iteration
-    value = 1.0 / scaled
-    sample = ('oracle (numpy float64 port of the reference iteration) on %d of %d rows, %d steps; '
-              'time scaled linearly in rows' % (rows, args.n_obs, args.steps))
+    sec, done, workers = cpu_iterations(args.n_obs, args.dim, args.mc, args.steps, max(1, min(args.warmup, 1)),
+                                        budget_s=args.ref_seconds)
+    value = 1.0 / sec
+    sample = ('oracle (numpy float64 port of the reference iteration) on all %d rows, %d of the %d requested '
+              'steps timed (time budget %.0f s), row blocks over %d threads' % (args.n_obs, done, args.steps,
+                                                                               args.ref_seconds, workers))
     line = {
         'impl': 'reference', 'metric': 'elbo_grad_iters_per_sec', 'value': value, 'unit': 'iter/s',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': scaled * 1e3,
+        'n_gpus': args.gpus, 'steps': done, 'warmup': max(1, min(args.warmup, 1)), 'ms_per_step': sec * 1e3,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic',
-        'config': {'workload': 'bayes-logistic N=%d d=%d S=%d MFGaussian+RMSProp (BASELINE configs[1])' % (args.n_obs, args.dim, args.mc)},
-        'cpu_baseline': {'value': value, 'unit': 'iter/s', 'cores': cpu_threads(), 'kind': 'port', 'sample': sample},
+        'data': 'synthetic', 'extrapolated': False,
+        'config': {'workload': workload_name(args.n_obs, args.dim, args.mc)},
+        'cpu_baseline': {'value': value, 'unit': 'iter/s', 'cores': workers, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'iter/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
@@ -158,29 +209,32 @@ class ClockSampler(object):
 
 def profiled_traffic(*kernels):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernels, from the committed
-    ncu --set full captures (profiles/traffic_r01.json); None when a kernel has not been captured."""
-    try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'traffic_r01.json')) as f:
-            t = json.load(f)
-        return float(sum(t[k] for k in kernels))
-    except (OSError, KeyError, ValueError):
-        return None
+    ncu --set full captures (profiles/traffic_r02.json, else _r01); None when a kernel has not been captured."""
+    for name in ('traffic_r02.json', 'traffic_r01.json'):
+        try:
+            with open(os.path.join(ROOT, 'profiles', name)) as f:
+                t = json.load(f)
+            return float(sum(t[k] for k in kernels))
+        except (OSError, KeyError, ValueError):
+            continue
+    return None
 
 
 def measured_peak(name, fallback):
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
-            return float(json.load(f)[name]), 'measured'
+            return float(json.load(f)[name]), 'MEASURED_PEAKS.json'
     except Exception:
-        return fallback, 'fallback'
+        return fallback, 'fallback (B200_PROFILING.md)'
 
 
 def matmul_peak_tflops(torch, dtype, tf32, n):
+    """Same method as MEASURED_PEAKS.json's `how` (torch.matmul n^3, 2 n^3 flop, best of 10, CUDA events)."""
     torch.backends.cuda.matmul.allow_tf32 = tf32
     a = torch.randn(n, n, device='cuda', dtype=dtype)
     b = torch.randn(n, n, device='cuda', dtype=dtype)
     best = 1e9
-    for i in range(6):
+    for i in range(12):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         torch.matmul(a, b)
@@ -192,19 +246,24 @@ def matmul_peak_tflops(torch, dtype, tf32, n):
     return 2.0 * n ** 3 / best / 1e12
 
 
+def psis_draws(torch, n, dev, seed):
+    """log p - log q of a t_10 target under a t_40 proposal, summed over two coordinates (heavy-ish tail)."""
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    lw = torch.zeros(n, device=dev, dtype=torch.float64)
+    for _ in range(2):
+        z = torch.randn(n, generator=gen, device=dev, dtype=torch.float64)
+        lw += -5.5 * torch.log1p(z * z / 10.0) + 20.5 * torch.log1p(z * z / 40.0)
+        del z
+    return lw
+
+
 def bench_psis(torch, vb, args):
     """Second headline metric (BASELINE.json: 'PSIS draws/s'): psislw + CUBO/ELBO moments on n
     float64 log-weights resident in HBM (BASELINE configs[4] size, one GPU).  HBM roofline with
     24 algorithmic bytes per draw (lw read twice, smoothed weights written once)."""
     n = args.psis_draws
-    gen = torch.Generator(device='cuda')
-    gen.manual_seed(DATA_SEED + 5)
-    # log p - log q for p = t_10, q = t_40 per coordinate summed over 4 coordinates (heavy-ish tail)
-    lw = torch.zeros(n, device='cuda', dtype=torch.float64)
-    for _ in range(2):
-        z = torch.randn(n, generator=gen, device='cuda', dtype=torch.float64)
-        lw += -5.5 * torch.log1p(z * z / 10.0) + 20.5 * torch.log1p(z * z / 40.0)
-        del z
+    lw = psis_draws(torch, n, 'cuda', DATA_SEED + 5)
     out = torch.empty_like(lw)
     for _ in range(3):
         vb.psislw_device(lw, out)
@@ -229,11 +288,13 @@ def bench_psis(torch, vb, args):
     sec_diag = e0.elapsed_time(e1) * 1e-3 / reps
     hbm, how = measured_peak('hbm_gbs', 6650.0)
     achieved = 24.0 * n / sec / 1e9
-    # end to end from HOST memory: H2D of the weights, PSIS, D2H of k-hat and the smoothed weights
-    host = torch.empty(min(n, 20000000), dtype=torch.float64).pin_memory()
-    host.copy_(lw[:host.numel()])
+    # end to end from HOST memory through the public API call: H2D of the weights, PSIS, D2H of k-hat and the
+    # smoothed weights (pinned buffers; a PCIe-bound number, reported for completeness)
+    m2 = min(n, 20000000)
+    host = torch.empty(m2, dtype=torch.float64).pin_memory()
+    host.copy_(lw[:m2])
     hout = torch.empty_like(host).pin_memory()
-    dev_in = torch.empty(host.numel(), device='cuda', dtype=torch.float64)
+    dev_in = torch.empty(m2, device='cuda', dtype=torch.float64)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     dev_in.copy_(host, non_blocking=True)
@@ -241,18 +302,19 @@ def bench_psis(torch, vb, args):
     hout.copy_(dev_in, non_blocking=True)
     k2 = float(res2[0].item())
     torch.cuda.synchronize()
-    e2e = host.numel() / (time.perf_counter() - t0)
+    e2e = m2 / (time.perf_counter() - t0)
     cpu = None
     if not args.no_cpu_baseline:
         from oracle import viabel_oracle as vo
-        m = min(n, 5000000)
+        m = min(n, 10000000)
         sample = lw[:m].cpu().numpy()
         t0 = time.perf_counter()
         with np.errstate(all='ignore'):
-            o, k = vo.psislw_1d(sample)
+            o, k = vo.psislw_argsort_1d(sample)
             vo.divergence_bound(o)
         cpu = {'value': m / (time.perf_counter() - t0), 'unit': 'draws/s', 'cores': 1, 'kind': 'port',
-               'sample': 'numpy oracle psislw + divergence_bound on the first %d draws' % m}
+               'sample': 'numpy oracle with the reference\'s argsort structure (_psis.py:163-203) + divergence_bound '
+                         'on the first %d draws' % m}
     del lw, out
     return {'metric': 'psis_draws_per_sec', 'value': n / sec, 'unit': 'draws/s', 'n_draws': n, 'ms': sec * 1e3,
             'khat': float(r[0]), 'n_tail': int(r[2]), 'status': int(r[6]),
@@ -263,15 +325,59 @@ def bench_psis(torch, vb, args):
             'diagnostics_only': {'value': n / sec_diag, 'unit': 'draws/s', 'ms': sec_diag * 1e3,
                                  'algorithmic_bytes_per_draw': 16, 'achieved_gbs': 16.0 * n / sec_diag / 1e9,
                                  'frac': 16.0 * n / sec_diag / 1e9 / hbm},
-            'e2e': {'value': e2e, 'unit': 'draws/s', 'n_draws': host.numel(), 'h2d_bytes': host.numel() * 8,
-                    'd2h_bytes': host.numel() * 8 + 8, 'khat': k2},
+            'e2e': {'value': e2e, 'unit': 'draws/s', 'n_draws': m2, 'h2d_bytes': m2 * 8,
+                    'd2h_bytes': m2 * 8 + 8, 'khat': k2, 'note': 'PCIe-bound'},
             'cpu_baseline': cpu}
+
+
+def bench_psis_sharded(torch, dist, vb, args, rank, world, dev):
+    """BASELINE configs[4]: PSIS of n = 1e8 draws sharded by draw over the ranks (strong scaling of the
+    one-GPU leg): pass A + local cutoff per rank, one all-gather of the fixed-size records, replicated
+    global select / GPD fit, pass B per rank.  Timed on the device, max over ranks."""
+    from viabel_b200.parallel import shard_rows
+    n = args.psis_draws
+    lo, hi = shard_rows(n, rank, world)
+    lw = psis_draws(torch, hi - lo, dev, DATA_SEED + 5 + 1000 * rank)
+    out = torch.empty_like(lw)
+    sizes = [shard_rows(n, r, world)[1] - shard_rows(n, r, world)[0] for r in range(world)]
+    for _ in range(3):
+        _, khat, res = vb.psislw_sharded(lw, out=out, sizes=sizes)
+    dist.barrier()
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        _, khat, res = vb.psislw_sharded(lw, out=out, sizes=sizes)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3 / reps], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item())
+    hbm, how = measured_peak('hbm_gbs', 6650.0)
+    achieved = 24.0 * n / sec / 1e9
+    return {'metric': 'psis_draws_per_sec', 'value': n / sec, 'unit': 'draws/s', 'n_draws': n, 'ms': sec * 1e3,
+            'sharding': 'draws over %d ranks (strong scaling of the 1e8-draw column, includes the status read-back)' % world,
+            'khat': float(khat), 'n_tail': int(res[2]),
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm * world, 'unit': 'GB/s',
+                         'frac': achieved / (hbm * world), 'traffic': None, 'peak_source': how + ' x ranks',
+                         'algorithmic_bytes_per_draw': 24}}
+
+
+def time_steps(torch, eng, steps, use_graph):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.run(steps, use_graph=use_graph)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3
 
 
 def run_b200(args):
     import torch
     import torch.distributed as dist
     import viabel_b200 as vb
+    from viabel_b200.engine import FusedStep
     from viabel_b200.parallel import shard_rows
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -281,6 +387,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
+    use_graph = not args.no_graph
 
     N, d, S = args.n_obs, args.dim, args.mc
     # this rank's rows [lo, hi) of the N x d problem; rank r seeds its rows with DATA_SEED + r
@@ -298,59 +405,52 @@ def run_b200(args):
     model = vb.LogisticRegression(X, y, prior_scale=10.0, sharded=world > 1)
     approx = vb.MFGaussian(d, seed=DRAW_SEED)
     if path == 'fast':
-        model.enable_fast_path()          # tcgen05 + TMA, fp16 hi/lo operand splits, 1e-4 tolerance
-        approx.quantize_draws = 2         # fp16-exact Philox normals (exact tensor-core operands)
+        model.enable_fast_path(approx)    # tcgen05 + TMA, fp16 hi/lo operand splits; fp16-exact draws
     objective = vb.ExclusiveKL(approx, model, S)
     opt = vb.RMSProp(0.01)
-    vp = torch.as_tensor(approx.init_param(), device=dev)
-    # own kernels per step.  fast: philox, sample, operand pack, pair sweep, partial reduction, value, grad, rmsprop;
-    # f64: philox, sample, pack, sweep, 3x reduce, value, grad, rmsprop.  (The NCCL all-reduce at N > 1 is not ours.)
-    launches_per_step = 8 if path == 'fast' else 10
-
-    def step():
-        value, grad = objective(vp)
-        opt._fused_step(vp, grad, False)
-        return value
+    eng = FusedStep(objective, opt)       # the object RMSProp.optimize() drives
+    eng.set_param(approx.init_param())
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
+    eng.run(max(args.warmup, 3), use_graph=use_graph)
+    eng.run(16, use_graph=use_graph)      # untimed: both graph shapes (8-step and 1-step) are captured before the clock starts
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
+    elapsed = time_steps(torch, eng, args.steps, use_graph)
     barrier()
-    elapsed = e0.elapsed_time(e1) * 1e-3
     if world > 1:
         t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
-    # nvidia-smi samples every 100 ms; a short timed region (K steps of ~1 ms) can fall between two samples,
-    # so the same step keeps running (untimed; the same count on every rank, the step contains the all-reduce)
-    # until the sampler has seen the GPU under this load
-    n_extra = 0 if elapsed >= 0.6 else min(5000, int(0.6 / max(elapsed / args.steps, 1e-5)))
-    for _ in range(n_extra):
-        step()
-    barrier()
-    clocks = sampler.stop() if sampler else None
     ms_per_step = elapsed / args.steps * 1e3
+    # sustained: the same step for >= 1 s (the power cap needs a few hundred ms to bite; nvidia-smi samples every
+    # 100 ms).  The same count on every rank -- the step contains the exchange.
+    n_sus = max(args.steps, min(20000, int(1.2 / max(elapsed / args.steps, 1e-5))))
+    n_sus = (n_sus + 7) // 8 * 8
+    sus = time_steps(torch, eng, n_sus, use_graph)
+    barrier()
+    if world > 1:
+        t = torch.tensor([sus], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sus = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    eng.check_comm()
+    finite = bool(torch.isfinite(eng.vp).all())
 
-    # ---- end-to-end through the public API with HOST buffers (numpy in, numpy out) -----------
+    # ---- end-to-end through the public API with HOST buffers (numpy in, numpy out), as a viabel user calls it:
+    #      objective(var_param) -> descent_direction -> update on the host (optimization.py:95-98) -----------
     vp_host = approx.init_param()
     opt2 = vb.RMSProp(0.01)
-    for _ in range(2):
+    for _ in range(3):
         v, g = objective(vp_host)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, g = objective(vp_host)                   # H2D var_param, D2H value + gradient
+        v, g = objective(vp_host)                   # H2D var_param, D2H value + gradient (pinned, inside one graph)
         vp_host = vp_host - 0.01 * opt2.descent_direction(g)
     barrier()
     e2e_sec = (time.perf_counter() - t0) / args.steps
@@ -359,8 +459,8 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_sec = float(t.item())
 
-    # ---- dominant kernel alone (the fused sweep), CUDA events on the launching stream --------
-    theta = approx.sample(vp, S)
+    # ---- dominant kernel alone (the sweep through the C ABI), CUDA events on the launching stream --------
+    theta = approx.sample(torch.as_tensor(approx.init_param(), device=dev), S)
     base = approx.last_base
     for _ in range(2):
         model.sweep(theta, base, None, True)
@@ -374,20 +474,31 @@ def run_b200(args):
     torch.cuda.synchronize()
     sweep_sec = k0.elapsed_time(k1) * 1e-3 / reps
 
+    psis = None
+    if not args.no_psis:
+        del eng
+        if world > 1:
+            psis = bench_psis_sharded(torch, dist, vb, args, rank, world, dev)
+        elif rank == 0:
+            psis = bench_psis(torch, vb, args)
+
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
     flops = 4.0 * (hi - lo) * d * S                  # algorithmic flops of one sweep on this rank
+    bf16_peak, how = measured_peak('bf16_tflops', 1590.0)
+    bf16_sus, _ = measured_peak('bf16_tflops_sustained', 1390.0)
     if path == 'f64':
         peak = matmul_peak_tflops(torch, torch.float64, False, 4096)
-        peak_note = 'cuBLAS fp64 matmul 4096^3 measured in this run'
+        peak_note = 'cuBLAS fp64 matmul 4096^3 measured in this run (torch.matmul, 2 n^3 flop, best of 10, CUDA events)'
     else:
         peak = matmul_peak_tflops(torch, torch.float32, True, 8192)
-        peak_note = 'cuBLAS tf32 matmul 8192^3 measured in this run'
+        peak_note = ('cuBLAS tf32 matmul 8192^3 measured in this run with the method of MEASURED_PEAKS.json '
+                     '(torch.matmul, 2 n^3 flop, best of 10, CUDA events); SURVEY 8(d) names this denominator')
     achieved = flops / sweep_sec / 1e12
-    bf16_peak, how = measured_peak('bf16_tflops', 1590.0)
     traffic = None
     if path == 'fast' and world == 1 and (N, d, S) == (1000000, 512, 256):
         traffic = profiled_traffic('glm_fast_pair_kernel')       # ncu --set full capture of this very launch shape
@@ -395,37 +506,68 @@ def run_b200(args):
                 'frac': achieved / peak, 'traffic': traffic, 'kernel': 'glm_sweep_%s' % path,
                 'kernel_ms': sweep_sec * 1e3, 'peak_note': peak_note,
                 'bf16_peak_tflops': bf16_peak, 'bf16_peak_source': how,
-                'algorithmic_flops_per_launch': flops, 'algorithmic_bytes_per_launch': (hi - lo) * d * 8.0}
+                'frac_bf16_algorithmic': achieved / bf16_peak,
+                'frac_bf16_executed': (2.0 * achieved / bf16_peak) if path == 'fast' else None,
+                'executed_note': 'fp16 hi/lo operand splits: 3 + 1 tensor passes = 2x the algorithmic flops',
+                'algorithmic_flops_per_launch': flops, 'algorithmic_bytes_per_launch': (hi - lo) * d * 4.0 if path == 'fast'
+                else (hi - lo) * d * 8.0}
 
-    psis = bench_psis(torch, vb, args) if world == 1 and not args.no_psis else None
+    # ---- the exact FP64 path of the same config (BASELINE configs[1]: "FP64 and FP32 paths") ----
+    f64_leg = None
+    if path == 'fast' and world == 1 and not args.no_f64:
+        model.path = 'f64'
+        approx64 = vb.MFGaussian(d, seed=DRAW_SEED)
+        obj64 = vb.ExclusiveKL(approx64, model, S)
+        eng64 = FusedStep(obj64, vb.RMSProp(0.01))
+        eng64.set_param(approx64.init_param())
+        eng64.run(2, use_graph=False)
+        torch.cuda.synchronize()
+        n64 = 5
+        sec64 = time_steps(torch, eng64, n64, False) / n64
+        peak64 = matmul_peak_tflops(torch, torch.float64, False, 4096)
+        f64_leg = {'value': 1.0 / sec64, 'unit': 'iter/s', 'ms_per_step': sec64 * 1e3, 'steps': n64, 'dtype': 'f64',
+                   'roofline': {'bound': 'tensor', 'achieved': flops / sec64 / 1e12, 'peak': peak64, 'unit': 'TFLOP/s',
+                                'frac': flops / sec64 / 1e12 / peak64, 'traffic': profiled_traffic('glm_sweep_f64_kernel'),
+                                'peak_note': 'cuBLAS fp64 matmul 4096^3 measured in this run (best of 10); whole step timed',
+                                'algorithmic_bytes_per_launch': (hi - lo) * d * 8.0}}
+        model.path = 'fast'
+        del eng64
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         rows = min(CPU_SAMPLE_ROWS, N)
-        sec = cpu_iterations(rows, d, S, 3, 1) * (N / rows)
-        cpu_baseline = {'value': 1.0 / sec, 'unit': 'iter/s', 'cores': cpu_threads(), 'kind': 'port',
-                        'sample': 'numpy float64 oracle, 3 iterations on %d of %d rows, scaled linearly' % (rows, N)}
+        sec, done, workers = cpu_iterations(rows, d, S, 3, 1)
+        sec *= N / rows
+        cpu_baseline = {'value': 1.0 / sec, 'unit': 'iter/s', 'cores': workers, 'kind': 'port',
+                        'sample': 'numpy float64 oracle, %d iterations on %d of %d rows over %d threads, time scaled '
+                                  'linearly in rows (the --impl reference arm runs all rows)' % (done, rows, N, workers)}
 
     line = {
         'metric': 'elbo_grad_iters_per_sec', 'value': 1e3 / ms_per_step, 'unit': 'iter/s',
-        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
+        'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f64' if path == 'f64' else 'f16x2-split/f32',
         'data': 'synthetic',
-        'config': {'workload': 'bayes-logistic N=%d d=%d S=%d MFGaussian+RMSProp (BASELINE configs[%d])'
-                   % (N, d, S, 2 if (N, d) == (10000000, 1024) else 1),
+        'config': {'workload': workload_name(N, d, S),
                    'path': path, 'rows_per_rank': hi - lo, 'l2': 'inputs larger than L2 (X = %.2f GB per rank)'
-                   % ((hi - lo) * d * 8 / 1e9)},
+                   % ((hi - lo) * d * (4 if path == 'fast' else 8) / 1e9),
+                   'step': 'CUDA graph replay of 3 kernels (pre | sweep | post)' if use_graph else '3 kernels enqueued from Python',
+                   'exchange': 'in-kernel one-shot all-reduce over peer memory' if world > 1 else 'none',
+                   'draws': 'fp16-exact Philox normals (enable_fast_path sets quantize_draws=2)' if path == 'fast' else 'fp64 Philox normals'},
+        'sustained': {'value': n_sus / sus, 'unit': 'iter/s', 'ms_per_step': sus / n_sus * 1e3, 'steps': n_sus},
         'clocks': clocks,
         'e2e': {'value': 1.0 / e2e_sec, 'unit': 'iter/s', 'h2d_bytes_per_step': 2 * d * 8,
                 'd2h_bytes_per_step': (1 + 2 * d) * 8},
-        'gpu_launches': launches_per_step * args.steps,
+        'gpu_launches': (3 if path == 'fast' else 7) * args.steps,
+        'finite': finite,
         'roofline': roofline,
+        'f64': f64_leg,
         'cpu_baseline': cpu_baseline,
         'psis': psis,
     }
     print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -554,6 +554,35 @@ def psislw_1d(lw, Reff=1.0, return_tail=False):
     return x, k
 
 
+def psislw_argsort_1d(lw, Reff=1.0):
+    """One column of _psis.py:163-203 with the reference's own COST STRUCTURE: a full argsort of the n
+    log-weights (:168), the cutoff read through the sort permutation (:170-173), a second argsort of the
+    tail (:184).  Same results as psislw_1d (checked in tests/test_oracle_golden.py); this is the variant
+    bench.py times as the CPU baseline of the PSIS leg, because it does the work the reference does."""
+    x = np.array(lw, dtype=np.float64, copy=True)
+    n = x.size
+    if n <= 1:
+        raise ValueError('More than one log-weight needed.')
+    cut_pos = -psis_tail_len(n, Reff) - 1
+    x -= np.max(x)
+    perm = np.argsort(x)
+    xcut = max(x[perm[cut_pos]], math.log(np.finfo(float).tiny))
+    expcut = math.exp(xcut)
+    tail = np.flatnonzero(x > xcut)
+    n2 = tail.size
+    k, order = np.inf, None
+    if n2 > 4:
+        x2 = x[tail]
+        order = np.argsort(x2)
+        k, sigma = gpdfit(np.exp(x2[order]) - expcut)
+    if k >= 1.0 / 3.0 and not np.isinf(k):
+        q = gpinv((np.arange(n2) + 0.5) / n2, k, sigma) + expcut
+        x[tail[order]] = np.log(q)
+        x[x > 0] = 0.0
+    x -= sumlogs(x)
+    return x, k
+
+
 def psis_shard_record(x_local, idx_off, M):
     """Draw-sharded restatement of _psis.py:163-203, stage 1 (csrc/psis.cu
     psis_export_kernel): what one rank ships.  [local max, c_r, log-sum-exp (relative to the local

@@ -50,8 +50,14 @@ def test_fast_sweep_vs_oracle(vb, vo, N, d, S):
     # weighted second pass (AlphaDivergence) and the forward-only model call
     vp = points['conv']
     v, gr = vb.AlphaDivergence(approx, model, S, 2.0)(vp, base=base)
-    v0, g0, _ = vo.alpha_divergence_meanfield(vp, base, oracle_model, 2.0)
-    assert relerr(v, v0) < TOL_FAST and relerr(gr, g0) < 5 * TOL_FAST     # weights exp(2 lw) amplify lw error
+    v0, g0, lw0 = vo.alpha_divergence_meanfield(vp, base, oracle_model, 2.0)
+    # AlphaDivergence weights are exp(alpha (lw - max)): an ABSOLUTE error e in a log-weight is a RELATIVE error
+    # alpha * e in that sample's weight, on top of the sweep's own 1e-4.  lw sums N fp32-accumulated terms, so e
+    # grows like sqrt(N) (DESIGN.md 4.2 'AlphaDivergence on the fast path'); the gradient is held to
+    # 1e-4 + alpha * max|lw - lw_oracle| with the measured log-weight error, and that error itself to its budget.
+    dlw = float(np.max(np.abs(approx.last_log_weights.cpu().numpy() - lw0)))
+    assert dlw < 4e-6 * np.sqrt(N) + 1e-9 * abs(lw0).max()
+    assert relerr(v, v0) < TOL_FAST and relerr(gr, g0) < TOL_FAST + 2.0 * dlw
     theta = vo.mfg_sample(vp, base)
     assert relerr(model(theta), oracle_model(theta)[0]) < TOL_FAST
     # general float64 draws (not fp16-exact) still meet the tolerance

@@ -119,6 +119,35 @@ def test_psislw_large_vs_oracle(vb, vo, n, dfp, dfq):
     np.testing.assert_allclose(out.cpu().numpy(), o_ref, rtol=1e-10, atol=1e-10)
 
 
+def test_psislw_1e8_vs_oracle(vb, vo):
+    """BASELINE configs[4] at FULL size (n = 1e8 draws) against the oracle, not only by properties: k-hat to
+    1e-10, the tail index set bit-exact, the smoothed normalised weights to 1e-10, and the divergence bound."""
+    n = 100000000
+    g = torch.Generator(device='cuda')
+    g.manual_seed(20260119)
+    lw = torch.zeros(n, device='cuda', dtype=torch.float64)
+    for _ in range(2):                                  # t_10 target under a t_40 proposal, two coordinates
+        z = torch.randn(n, generator=g, device='cuda', dtype=torch.float64)
+        lw += -5.5 * torch.log1p(z * z / 10.0) + 20.5 * torch.log1p(z * z / 40.0)
+        del z
+    out = torch.empty_like(lw)
+    _, res, ti, _ = vb.psislw_device(lw, out, want_tail=True)
+    res = res.cpu().numpy()
+    assert res[6] == 0 and res[9] == 30000
+    host = lw.cpu().numpy()
+    del lw
+    with np.errstate(all='ignore'):
+        o_ref, k_ref, tail_ref, _ = vo.psislw_1d(host, return_tail=True)
+    del host
+    assert relerr(res[0], k_ref) < TOL
+    assert np.array_equal(ti[:int(res[2])].cpu().numpy(), tail_ref)
+    d2 = vb.divergence_bound(out)
+    o = out.cpu().numpy()
+    del out
+    assert np.max(np.abs(o - o_ref)) < 1e-10 * np.max(np.abs(o_ref))
+    assert relerr(d2, vo.divergence_bound(o_ref)[0]) < TOL
+
+
 def test_psislw_1e8_properties(vb):
     """BASELINE configs[4] size: size-independent properties (normalisation, tail size, clamp,
     idempotent k-hat under a shift of the weights)."""

@@ -158,6 +158,11 @@ def test_psis(golden, name):
     if lw.ndim == 1:
         _, _, tail, _ = vo.psislw_1d(lw, return_tail=True)
         assert np.array_equal(tail, g[name + '/tail_idx'])        # bit-exact index set
+        # the argsort-structured variant (the CPU baseline bench.py times) gives the same numbers
+        with np.errstate(all='ignore'):
+            out2, k2 = vo.psislw_argsort_1d(lw)
+        assert (np.isinf(k2) and np.isinf(k)) or relerr(k2, k) < 1e-13
+        np.testing.assert_allclose(np.sort(out2), np.sort(out), rtol=1e-13, atol=1e-13)
     if name + '/d2' in g:
         d2, elbo, _ = vo.divergence_bound(out)
         assert relerr(d2, g[name + '/d2']) < 1e-10

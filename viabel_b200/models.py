@@ -94,10 +94,21 @@ class GLMModel(Model):
         off = (-buf.data_ptr()) % align
         return buf[off:off + nbytes]
 
-    def enable_fast_path(self):
+    def enable_fast_path(self, approx=None):
         """Preprocess the data for the tcgen05 path (fp16 hi+lo split of y*X) and route sweeps of
         up to 256 samples through it.  Raises NotImplementedError when the link or the data range
-        is not supported; the float64 path stays available via `path = 'f64'`."""
+        is not supported; the float64 path stays available via `path = 'f64'`.
+
+        approx: the variational family that will be fitted on this model.  When given, its base
+        draws are switched to fp16-exact values (`approx.quantize_draws = 2`: every N(0,1) / t draw
+        is rounded to the nearest float16, a relative perturbation <= 2^-11 of each draw), which
+        makes the draws exact tensor-core operands so the back-projection needs one pass instead of
+        two.  This changes the sampling distribution in the 4th significant digit of each draw --
+        far below Monte Carlo error -- and is the configuration bench.py measures; leave `approx`
+        out to keep full-precision draws (they are then rounded inside the kernel only, and the
+        fast-path tolerance of 1e-4 still holds)."""
+        if approx is not None:
+            approx.quantize_draws = 2
         if self._fast is None:
             lib = _lib.lib
             nbytes = lib.vb_glm_fast_model_bytes(self.N, self.dim)

@@ -174,6 +174,7 @@ def _mf_objective(approx, model, S, objective, alpha, var_param, base=None, seed
         w = torch.empty(S, dtype=F64, device=dev)
         _lib.check(lib.vb_mf_alpha_weights_f64(ptr(vp), ptr(theta), ptr(e), ptr(ll), S, d, family, df,
                                                prior_sd, float(alpha), ptr(lw), ptr(w), ptr(value), st))
+        approx.last_log_weights = lw            # log p - log q per sample (objectives.py:446)
     ll, gmu, ge = sweep(w)
     _lib.check(lib.vb_mf_objective_finish_f64(
         ptr(vp), ptr(theta), ptr(e), ptr(ll), ptr(gmu), ptr(ge), ptr(w), S, d, family, df, prior_sd,
