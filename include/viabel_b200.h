@@ -247,9 +247,37 @@ typedef struct {
   size_t sweep_workspace_bytes;
 } vb_step_model;
 
+/* The workspace carries state between calls (the block ticket of the last kernel): zero it once before the
+ * first call and hand the same buffer to every later call of the same engine. */
 size_t vb_mf_step_workspace_bytes(int S, int d);
 int vb_mf_step_glm(const vb_step_config* cfg, const vb_step_buffers* buf, const vb_step_model* model,
                    void* comm, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * GLM plugin: derivatives of the log-LIKELIHOOD at one point theta[d] (the caller adds the prior's part), for
+ * the control-variate ExclusiveKL estimators (objectives.py:170-273), which take them from autograd:
+ *   out_grad[d]      = grad f(theta)            `grad_f(m_mean)`             :203, :221
+ *   out_hvp[K,d]     = H v_k for V[K,d]         `make_hvp(f_model)(m_mean)`  :220, :238, :256   (K in 0..4 or 8)
+ *   out_hessian[d,d] = H (optional)             `hessian(f_model)(m_mean)`   :200-204
+ *   out_ll[1]        = f(theta) (optional)
+ * Gradient and HVPs are ONE pass over X; the Hessian is a weighted SYRK on the FP64 tensor pipe.
+ * Logistic and probit links.
+ * ------------------------------------------------------------------------------------- */
+size_t vb_glm_point_workspace_bytes(int64_t N, int d, int K, int want_hessian);
+int vb_glm_point_f64(const double* X, int64_t ldx, const double* y, int64_t N, int d, int link,
+                     const double* theta, const double* V, int K, double* out_ll, double* out_grad,
+                     double* out_hvp, double* out_hessian, void* workspace, size_t workspace_bytes,
+                     cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Sample moments of x[n,d] (row-major, pitch ldx): the sample branch of wasserstein_bounds
+ * (diagnostics.py:137-141) and the covariance all_diagnostics takes from np.cov (diagnostics.py:58-59).
+ *   mean[d]; m2[d], m4[d] = sum_n (x_nj - mean_j)^2, ^4 (both or neither); cov[d,d] = np.cov(x.T) (optional,
+ *   1/(n-1) normalisation, FP64 tensor-pipe SYRK).  Deterministic (fixed summation order).
+ * ------------------------------------------------------------------------------------- */
+size_t vb_sample_moments_workspace_bytes(int64_t n, int d, int want_cov);
+int vb_sample_moments_f64(const double* x, int64_t n, int d, int64_t ldx, double* mean, double* m2, double* m4,
+                          double* cov, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Pareto-smoothed importance sampling and divergence-bound moments

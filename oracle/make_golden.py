@@ -210,6 +210,44 @@ def gen_objectives():
     print('objectives: %d arrays' % len(out))
 
 
+def gen_objectives_cv():
+    """ExclusiveKL with the control-variate estimators (objectives.py:170-273): every hessian_approx_method, with and
+    without the path derivative, mean-field families.  autograd's hessian / make_hvp / elementwise_grad are the torch
+    stand-ins of oracle/refshim."""
+    out = {}
+    rs = np.random.RandomState(1639)
+    models = {}
+    X, y, _ = logistic_problem(60, 4, seed=11)
+    models['logistic_d4'] = (4, logistic_log_p(X, y, 10.0))
+    X, y, _ = logistic_problem(1000, 10, seed=12)
+    models['logistic_d10'] = (10, logistic_log_p(X, y, 10.0))
+    X, y, _ = logistic_problem(200, 6, seed=13)
+    models['probit_d6'] = (6, probit_log_p(X, y, 10.0))
+    mean, sd = target_params(5, seed=14)
+    models['gauss_d5'] = (5, gauss_log_p(mean, sd))
+    models['student_d5'] = (5, student_log_p(mean, sd, 10.0))
+    for mname, (d, logp2d) in models.items():
+        # the estimators also evaluate the model at the 1-D variational mean (objectives.py:203, :221): the
+        # reference's own test density broadcasts over that (tests/test_objectives.py:18-19); these promote it
+        logp = (lambda f: (lambda th: f(anp.atleast_2d(th))))(logp2d)
+        for kind, df in (('mfg', None), ('mft', 8)):
+            fam = make_family(kind, d, df, seed=1214)
+            vp = random_var_param(fam, kind, d, rs)
+            for method in ('full', 'mean_only', 'loo_diag_approx', 'loo_direct_approx'):
+                for path in (False, True):
+                    tag = '%s/%s_df%s/%s/%s' % (mname, kind, df, method, 'path' if path else 'plain')
+                    obj = ExclusiveKL(fam, logp, 9, use_path_deriv=path, hessian_approx_method=method)
+                    with Recorder() as rec:
+                        value, grad = obj(vp)
+                    for k, v in first_draws(rec, kind).items():
+                        out[tag + '/' + k] = v
+                    out[tag + '/var_param'] = vp
+                    out[tag + '/value'] = float(value)
+                    out[tag + '/grad'] = np.asarray(grad, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, 'objectives_cv.npz'), **out)
+    print('objectives_cv: %d arrays' % len(out))
+
+
 def gen_optimizers():
     out = {}
     rs = np.random.RandomState(153)
@@ -405,6 +443,7 @@ if __name__ == '__main__':
     print('reference:', os.path.dirname(viabel.__file__))
     gen_families()
     gen_objectives()
+    gen_objectives_cv()
     gen_optimizers()
     gen_psis()
     gen_diagnostics()

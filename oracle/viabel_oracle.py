@@ -297,6 +297,30 @@ def student_target_logp_grad(theta, loc, scale, df):
     return lp, -(df + 1.0) * z / ((df + z * z) * scale)
 
 
+def logistic_hessian(theta, X, y, prior_sd=10.0):
+    """Hessian of logistic_logp_grad's f at ONE point: -X^T diag(p(1-p)) X - I/prior_sd^2."""
+    a = (X @ theta) * y
+    c = sigmoid(a) * sigmoid(-a)
+    return -(X * c[:, None]).T @ X - np.eye(theta.size) / prior_sd ** 2
+
+
+def probit_hessian(theta, X, y, prior_sd=10.0):
+    """d^2/da^2 log Phi(a) = -r (a + r), r = phi(a)/Phi(a)."""
+    a = (X @ theta) * y
+    r = np.exp(-0.5 * a * a - 0.5 * LOG_2PI - sps.log_ndtr(a))
+    c = r * (a + r)
+    return -(X * c[:, None]).T @ X - np.eye(theta.size) / prior_sd ** 2
+
+
+def gauss_target_hessian(theta, mean, sd):
+    return np.diag(-1.0 / (sd * sd) * np.ones_like(theta))
+
+
+def student_target_hessian(theta, loc, scale, df):
+    z = (theta - loc) / scale
+    return np.diag(-(df + 1.0) * (df - z * z) / ((df + z * z) ** 2 * scale * scale))
+
+
 def hier_linear_layout(G, p):
     """theta = [beta(G*p, group-major), m(p), log_tau, log_sigma]."""
     return G * p + p + 2
@@ -366,6 +390,61 @@ def exclusive_kl_meanfield(var_param, base, model, family='gaussian', df=None, p
         gmu = -np.mean(g, axis=0)
         gls = -np.mean(g * base, axis=0) * sig - 1.0
     return value, np.concatenate([gmu, gls]), f
+
+
+def exclusive_kl_cv_meanfield(var_param, base, model, hessian, method, family='gaussian', df=None, path_deriv=False):
+    """ExclusiveKL with the control-variate gradient estimators (objectives.py:170-273, after Miller et al.),
+    restated per sample exactly as the reference computes them.  `model(theta[S,d]) -> (f[S], G[S,d])`,
+    `hessian(m[d]) -> H[d,d]` (the reference obtains both from autograd).  Returns (value, grad[2d])."""
+    S, d = base.shape
+    mu, ls = mf_unpack(var_param, d)
+    sig = np.exp(ls)
+    z = mu + sig * base                                                  # approx.sample (:171)
+    if family == 'gaussian':
+        m_mean, s_scale = mu, np.sqrt(np.exp(2 * ls))                    # mean_and_cov (:172-173)
+    else:
+        m_mean, s_scale = mu, np.sqrt(df / (df - 2.0) * np.exp(2 * ls))
+    eps = (z - m_mean) / s_scale                                         # :174
+    f, dLdm = model(z)
+    if path_deriv:                                                       # :176-183
+        logq = mfg_log_density(var_param, z) if family == 'gaussian' else mft_log_density(var_param, z, df)
+        lower = np.mean(f - logq)
+    else:
+        H_ent = mfg_entropy(var_param, d) if family == 'gaussian' else mft_entropy(var_param, d)
+        lower = np.mean(f) + H_ent
+    dLdlns = dLdm * eps * s_scale + 1                                    # :196
+    g_hat = np.column_stack([dLdm, dLdlns])
+    gm = model(m_mean[None, :])[1][0]                                    # gradient at the mean
+    Hm = hessian(m_mean)
+    hvps = (s_scale * eps) @ Hm                                          # H symmetric: row s = H (s_scale * eps_s)
+    if method == 'full':                                                 # :199-215
+        dLdz = gm + hvps
+        dLds = dLdz * eps * s_scale + 1.0
+        tilde = np.column_stack([dLdz, dLds])
+        tilde_mean = np.concatenate([gm, (np.diag(Hm) * s_scale + 1 / s_scale) * s_scale])
+        g = np.mean(g_hat - (tilde - tilde_mean), axis=0)
+    elif method == 'mean_only':                                          # :216-232
+        g_tilde = np.column_stack([gm + hvps, np.zeros_like(hvps)])
+        E = np.concatenate([gm, np.zeros(d)])
+        g = np.mean(g_hat - (g_tilde - E), axis=0)
+    elif method == 'loo_diag_approx':                                    # :233-254
+        dLdz = gm + hvps
+        dLds = dLdz * (eps * s_scale) + 1
+        Hd_sum = np.sum(eps * hvps, axis=0)
+        Hd_s = (Hd_sum[None, :] - eps * hvps) / float(S - 1)
+        dLds_mu = (Hd_s + 1 / s_scale[None, :]) * s_scale
+        g = g_hat.copy()
+        g[:, :d] -= hvps
+        g[:, d:] -= (dLds - dLds_mu)
+        g = np.mean(g, axis=0)
+    elif method == 'loo_direct_approx':                                  # :255-268
+        dLdz = gm + hvps
+        dLds = (dLdz * eps + 1 / s_scale[None, :]) * s_scale
+        dLds_mu = (np.sum(dLds, axis=0)[None, :] - dLds) / float(S - 1)
+        g = np.mean(g_hat - np.column_stack([hvps, dLds - dLds_mu]), axis=0)
+    else:
+        raise RuntimeError('Invalid hessian approximation method!')
+    return -lower, -g
 
 
 def alpha_divergence_meanfield(var_param, base, model, alpha, family='gaussian', df=None):

@@ -302,3 +302,41 @@ def test_sharded_psis_rule_random_partitions_and_ties():
         outs, k = vo.psislw_sharded(parts)
         assert (np.isinf(k) and np.isinf(kref)) or abs(k - kref) <= 1e-12 * abs(kref), (trial, k, kref)
         np.testing.assert_allclose(np.concatenate(outs), ref, rtol=0, atol=1e-11)
+
+
+CV_MODELS = ['logistic_d4', 'logistic_d10', 'probit_d6', 'gauss_d5', 'student_d5']
+
+
+def cv_model(name):
+    """(model(theta) -> (f, G), hessian(m) -> H) of the control-variate golden cases (oracle/make_golden.py)."""
+    if name.startswith('logistic'):
+        N, d, seed = (60, 4, 11) if name == 'logistic_d4' else (1000, 10, 12)
+        X, y, _ = logistic_problem(N, d, seed=seed)
+        return (lambda th: vo.logistic_logp_grad(th, X, y, 10.0)), (lambda m: vo.logistic_hessian(m, X, y, 10.0))
+    if name == 'probit_d6':
+        X, y, _ = logistic_problem(200, 6, seed=13)
+        return (lambda th: vo.probit_logp_grad(th, X, y, 10.0)), (lambda m: vo.probit_hessian(m, X, y, 10.0))
+    mean, sd = target_params(5, seed=14)
+    if name == 'gauss_d5':
+        return (lambda th: vo.gauss_target_logp_grad(th, mean, sd)), (lambda m: vo.gauss_target_hessian(m, mean, sd))
+    return (lambda th: vo.student_target_logp_grad(th, mean, sd, 10.0)), \
+        (lambda m: vo.student_target_hessian(m, mean, sd, 10.0))
+
+
+@pytest.mark.parametrize('mname', CV_MODELS)
+def test_control_variate_objectives(golden, mname):
+    """ExclusiveKL with hessian_approx_method (objectives.py:170-273): all four estimators x {plain, path-derivative}
+    x {MFGaussian, MFStudentT} against the unmodified reference run through the autograd stand-in."""
+    g = golden('objectives_cv')
+    model, hess = cv_model(mname)
+    n = 0
+    for key in [k for k in g if k.startswith(mname + '/') and k.endswith('/value')]:
+        tag = key[:-len('/value')]
+        _, fam, method, mode = tag.split('/')
+        family, df = ('gaussian', None) if fam.startswith('mfg') else ('student', 8.0)
+        v, gr = vo.exclusive_kl_cv_meanfield(g[tag + '/var_param'], g[tag + '/base'], model, hess, method, family, df,
+                                             mode == 'path')
+        assert relerr(v, g[tag + '/value']) < 1e-12, tag
+        assert relerr(gr, g[tag + '/grad']) < 1e-10, tag
+        n += 1
+    assert n == 16

@@ -58,6 +58,10 @@ _PROTOS = {
     'vb_psis_dist_global': (c_int, [P, c_int64, c_int64, c_double, c_int, P, P, c_size_t, P]),
     'vb_psis_dist_apply': (c_int, [P, P, c_int64, c_int64, c_int64, c_double, c_int, c_int, P, P, c_size_t, P]),
     'vb_divergence_moments_f64': (c_int, [P, c_int64, c_double, P, P]),
+    'vb_glm_point_workspace_bytes': (c_size_t, [c_int64, c_int, c_int, c_int]),
+    'vb_glm_point_f64': (c_int, [P, c_int64, P, c_int64, c_int, c_int, P, P, c_int, P, P, P, P, P, c_size_t, P]),
+    'vb_sample_moments_workspace_bytes': (c_size_t, [c_int64, c_int, c_int]),
+    'vb_sample_moments_f64': (c_int, [P, c_int64, c_int, c_int64, P, P, P, P, P, c_size_t, P]),
     # peer-memory communicator and the fused step (structures: viabel_b200/engine.py)
     'vb_comm_create': (c_int, [P, c_int, c_int, c_size_t, P]),
     'vb_comm_connect': (c_int, [P, P]),

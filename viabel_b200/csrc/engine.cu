@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) comm_allreduce_kernel(CommView c, double*
 // ---------------------------------------------------------------------------------------------
 struct StepCfg {
   int family, objective, S, d, optimizer, quantize, inject, fast;
-  int d_pad, chunks, rowsA;          // A-part geometry: rowsA rows x chunks blocks of 256 columns
+  int d_pad, chunks, rowsA;          // pre-kernel geometry: rowsA sample rows, `chunks` column tiles of 64
   double df, tconst, inv_tau2, prior_const;
   double lr, beta1, beta2, jitter;
   unsigned long long seed, stride;
@@ -161,58 +161,107 @@ __device__ __forceinline__ double draw_element(const StepCfg& c, const Philox& p
   return student_element(ph, e, c.df, c.quantize);
 }
 
-// blocks [0, rowsA*chunks): element order [s][j] (coalesced base / theta / E writes, per-sample partial sums)
-// blocks [rowsA*chunks, +d_pad), fast path only: column j, all samples -> Theta^T hi/lo (contiguous along s)
+// One block = a tile of 16 samples x 64 columns (grid: column tiles x sample tiles).  Each thread owns one column
+// pair and two rows, so a Box-Muller pair is evaluated once when the element index is even (the common case),
+// base / theta / E rows are written as contiguous runs, Theta^T hi/lo go through a shared-memory transpose into
+// 32-byte runs, and the per-sample partial sums are warp reductions (one warp = one row of the tile).
+constexpr int kPreRows = 16, kPreCols = 64;
+
 __global__ void __launch_bounds__(256) mf_pre_kernel(StepCfg c, StepPtrs p, fast::FastOperands ops) {
   PDL_SYNC();
-  __shared__ double red[32];
+  __shared__ float tt[kPreCols][kPreRows + 1];
   const Philox ph(c.seed);
   const unsigned long long offset = p.counters[2] + p.counters[0] * c.stride;
-  const int nA = c.rowsA * c.chunks;
   const int d = c.d;
-  if ((int)blockIdx.x < nA) {
-    const int s = blockIdx.x / c.chunks, ch = blockIdx.x - s * c.chunks;
-    const int j = ch * 256 + threadIdx.x;
-    const bool valid = s < c.S && j < d;
-    double e = 0.0, th = 0.0, ls = 0.0;
-    if (valid) {
-      const int64_t i = (int64_t)s * d + j;
-      e = c.inject ? p.base[i] : draw_element(c, ph, offset, i);
-      if (!c.inject) p.base[i] = e;
-      ls = p.vp[d + j];
-      th = p.vp[j] + exp(ls) * e;
-      p.theta[i] = th;
+  const int s0 = blockIdx.y * kPreRows, j0 = blockIdx.x * kPreCols;
+  const int cp = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int j = j0 + 2 * cp;
+  const bool path = c.objective == VB_OBJ_EXCLUSIVE_KL_PATH;
+  double mu[2] = {0.0, 0.0}, ls[2] = {0.0, 0.0}, sig[2] = {0.0, 0.0};
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+    if (j + u < d) {
+      mu[u] = p.vp[j + u];
+      ls[u] = p.vp[d + j + u];
+      sig[u] = exp(ls[u]);
     }
-    if (c.fast && j < c.d_pad)
-      ops.E[((size_t)(j >> 6) * fast::kPadS + s) * 64 + (j & 63)] = __float2half_rn((float)e);
-    if (s < c.S) {      // block-uniform
-      const double sq = block_sum(valid ? th * th : 0.0, red);
-      if (threadIdx.x == 0) p.sq_part[s * c.chunks + ch] = sq;
-      if (c.objective == VB_OBJ_EXCLUSIVE_KL_PATH) {
-        double lq = 0.0;
-        if (valid) {
-          if (c.family == VB_FAMILY_MF_GAUSSIAN) lq = -0.5 * e * e - ls - 0.5 * kLog2Pi;
-          else lq = c.tconst - 0.5 * (c.df + 1.0) * log1p(e * e / c.df) - ls;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = w + 8 * r, s = s0 + row;
+    double e[2] = {0.0, 0.0}, th[2] = {0.0, 0.0};
+    if (s < c.S) {
+      const int64_t i = (int64_t)s * d + j;
+      if (c.inject) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (j + u < d) e[u] = p.base[i + u];
+      } else {
+        const unsigned long long e0 = offset + (unsigned long long)i;
+        if (c.family == VB_FAMILY_MF_GAUSSIAN && !(e0 & 1) && j + 1 < d) {
+          normal_pair(ph, e0 >> 1, 0, e[0], e[1]);          // both elements of one Philox counter
+          if (c.quantize) {
+            e[0] = quantize_draw(e[0], c.quantize);
+            e[1] = quantize_draw(e[1], c.quantize);
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (j + u < d) e[u] = draw_element(c, ph, offset, i + u);
         }
-        lq = block_sum(lq, red);
-        if (threadIdx.x == 0) p.lq_part[s * c.chunks + ch] = lq;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (j + u < d) p.base[i + u] = e[u];
       }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (j + u < d) {
+          th[u] = mu[u] + sig[u] * e[u];
+          p.theta[i + u] = th[u];
+        }
     }
-  } else {
-    const int j = blockIdx.x - nA;
-    const int s = threadIdx.x;                 // kPadS == blockDim.x == 256
-    float t = 0.0f;
-    if (s < c.S && j < d) {
-      const int64_t i = (int64_t)s * d + j;
-      const double e = c.inject ? p.base[i] : draw_element(c, ph, offset, i);
-      t = (float)(p.vp[j] + exp(p.vp[d + j]) * e);
+    if (c.fast) {
+      if (j < c.d_pad) {
+        const __half2 h2 = __floats2half2_rn((float)e[0], (float)e[1]);
+        *reinterpret_cast<__half2*>(ops.E + ((size_t)blockIdx.x * fast::kPadS + s) * 64 + 2 * cp) = h2;
+      }
+      tt[2 * cp][row] = (float)th[0];
+      tt[2 * cp + 1][row] = (float)th[1];
     }
-    const __half hi = __float2half_rn(t);
-    const size_t o = ((size_t)(s >> 6) * c.d_pad + j) * 64 + (s & 63);
-    ops.Th[o] = hi;
-    ops.Tl[o] = __float2half_rn(t - __half2float(hi));
-    if (j == 0) ops.wf[s] = s < c.S ? 1.0f : 0.0f;
+    // per-sample partial sums over this tile's 64 columns: the 32 lanes of this warp hold row `row`
+    double sq = th[0] * th[0] + th[1] * th[1];
+    sq = warp_sum(sq);
+    if (cp == 0 && s < c.S) p.sq_part[(size_t)s * c.chunks + blockIdx.x] = sq;
+    if (path) {
+      double lq = 0.0;
+      if (s < c.S) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (j + u < d)
+            lq += c.family == VB_FAMILY_MF_GAUSSIAN ? -0.5 * e[u] * e[u] - ls[u] - 0.5 * kLog2Pi
+                                                    : c.tconst - 0.5 * (c.df + 1.0) * log1p(e[u] * e[u] / c.df) - ls[u];
+      }
+      lq = warp_sum(lq);
+      if (cp == 0 && s < c.S) p.lq_part[(size_t)s * c.chunks + blockIdx.x] = lq;
+    }
   }
+  if (!c.fast) return;
+  __syncthreads();
+  {   // Theta^T hi / lo: column jj of the tile, 4 consecutive samples per thread -> 8-byte stores, 32-byte runs
+    const int jj = threadIdx.x >> 2, q4 = (threadIdx.x & 3) * 4;
+    __align__(8) __half hi[4];
+    __align__(8) __half lo[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float t = tt[jj][q4 + u];
+      hi[u] = __float2half_rn(t);
+      lo[u] = __float2half_rn(t - __half2float(hi[u]));
+    }
+    const int sg = s0 + q4;                                     // 16 | 64: the 4 samples stay inside one 64-group
+    const size_t o = ((size_t)(sg >> 6) * c.d_pad + (j0 + jj)) * 64 + (sg & 63);
+    *reinterpret_cast<uint2*>(ops.Th + o) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(ops.Tl + o) = *reinterpret_cast<const uint2*>(lo);
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0) ops.wf[threadIdx.x] = (int)threadIdx.x < c.S ? 1.0f : 0.0f;
 }
 
 struct PartDesc {
@@ -224,9 +273,11 @@ struct PartDesc {
   double sign_ll;
 };
 
-__global__ void __launch_bounds__(256) mf_post_kernel(StepCfg c, StepPtrs p, PartDesc q, CommView cm) {
+constexpr int kPostGroups = 32;      // row groups of the post kernel's reduction: block = 32 columns x 32 groups
+
+__global__ void __launch_bounds__(32 * kPostGroups) mf_post_kernel(StepCfg c, StepPtrs p, PartDesc q, CommView cm) {
   PDL_SYNC();
-  __shared__ double sm[3][8][33];
+  __shared__ double sm[3][kPostGroups][33];
   __shared__ double red[32];
   __shared__ unsigned int last;
   const int S = c.S, d = c.d, nvec = S + 2 * d;
@@ -249,9 +300,11 @@ __global__ void __launch_bounds__(256) mf_post_kernel(StepCfg c, StepPtrs p, Par
       if (i < S) { kind = 0; col = i; part = q.ll_part; nblk = q.nblk_ll; stride = q.stride_ll; }
       else if (i < S + d) { kind = 1; col = i - S; part = q.gmu_part; nblk = q.nblk_g; stride = q.stride_g; }
       else { kind = 2; col = i - S - d; part = q.ge_part; nblk = q.nblk_g; stride = q.stride_g; }
-      for (int b = y; b < nblk; b += 8) acc += part[(size_t)b * stride + col];
+#pragma unroll 4
+      for (int b = y; b < nblk; b += kPostGroups) acc += part[(size_t)b * stride + col];
       if (kind == 1) {
-        for (int s = y; s < S; s += 8) {
+#pragma unroll 4
+        for (int s = y; s < S; s += kPostGroups) {
           const double th = p.theta[(size_t)s * d + col];
           pp += th;                                            // sum_s theta_sj
           if (path) {
@@ -260,7 +313,8 @@ __global__ void __launch_bounds__(256) mf_post_kernel(StepCfg c, StepPtrs p, Par
           }
         }
       } else if (kind == 2) {
-        for (int s = y; s < S; s += 8) {
+#pragma unroll 4
+        for (int s = y; s < S; s += kPostGroups) {
           const double th = p.theta[(size_t)s * d + col], ee = p.base[(size_t)s * d + col];
           pp += th * ee;                                       // sum_s theta_sj e_sj
           if (path) pq += c.family == VB_FAMILY_MF_GAUSSIAN ? ee * ee : (c.df + 1.0) / (c.df + ee * ee) * ee * ee;
@@ -272,7 +326,7 @@ __global__ void __launch_bounds__(256) mf_post_kernel(StepCfg c, StepPtrs p, Par
     if (y == 0 && i < nvec) {
       double t = 0.0, tp = 0.0, tq = 0.0;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) { t += sm[0][r][x]; tp += sm[1][r][x]; tq += sm[2][r][x]; }     // fixed order
+      for (int r = 0; r < kPostGroups; ++r) { t += sm[0][r][x]; tp += sm[1][r][x]; tq += sm[2][r][x]; }     // fixed order
       t *= kind == 0 ? q.sign_ll : 1.0;
       if (multi) {
         for (int r = 0; r < cm.world; ++r) cm.data_peer[r][par_off + (int64_t)cm.rank * cm.slot_doubles + i] = t;
@@ -524,7 +578,7 @@ struct StepLayout {
 
 static void step_layout(int S, int d, int fast, StepLayout& L) {
   L.d_pad = fast ? (int)(ceil_div(d, 256) * 256) : d;
-  L.chunks = (int)ceil_div(L.d_pad, 256);
+  L.chunks = (int)ceil_div(L.d_pad, kPreCols);          // column tiles of the pre kernel
   L.rowsA = fast ? fast::kPadS : S;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -617,8 +671,7 @@ extern "C" int vb_mf_step_glm(const vb_step_config* cfg, const vb_step_buffers* 
     if (rc) return rc;
   }
   // 1. draws + reparameterisation + operand pack
-  const int nblocks_pre = L.rowsA * L.chunks + (fast ? L.d_pad : 0);
-  VB_CUDA(launch_pdl(mf_pre_kernel, dim3(nblocks_pre), dim3(256), stream, c, p, ops));
+  VB_CUDA(launch_pdl(mf_pre_kernel, dim3(L.chunks, (unsigned)ceil_div(L.rowsA, kPreRows)), dim3(256), stream, c, p, ops));
 
   // 2. the sweep over this rank's observations
   PartDesc q;
@@ -650,6 +703,6 @@ extern "C" int vb_mf_step_glm(const vb_step_config* cfg, const vb_step_buffers* 
 
   // 3. reduce + exchange + finish + optimiser
   const int nblocks_post = (S + 2 * d + 31) / 32;
-  VB_CUDA(launch_pdl(mf_post_kernel, dim3(nblocks_post), dim3(256), stream, c, p, q, view));
+  VB_CUDA(launch_pdl(mf_post_kernel, dim3(nblocks_post), dim3(32 * kPostGroups), stream, c, p, q, view));
   return VB_OK;
 }

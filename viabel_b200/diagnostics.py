@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._tensor import F64, device, to_dev
 
-__all__ = ['all_diagnostics', 'error_bounds', 'wasserstein_bounds', 'divergence_bound']
+__all__ = ['all_diagnostics', 'error_bounds', 'wasserstein_bounds', 'divergence_bound', 'sample_moments']
 
 
 def _moments(log_weights, alpha):
@@ -49,20 +49,36 @@ def divergence_bound(log_weights, *, alpha=2., log_norm_bound=None, return_log_n
     return dalpha
 
 
+def sample_moments(samples, want_cov=False):
+    """(mean[d], m2[d], m4[d], cov[d,d] or None) of samples[n,d] through vb_sample_moments_f64:
+    m2 / m4 are the per-coordinate central power sums sum_n (x_nj - mean_j)^{2,4}; cov = np.cov(samples.T)."""
+    x = to_dev(samples)
+    if x.dim() == 1:
+        x = x[:, None].contiguous()
+    n, d = int(x.shape[0]), int(x.shape[1])
+    out = torch.empty(3 * d + (d * d if want_cov else 0), dtype=F64, device=x.device)
+    mean, m2, m4 = out[:d], out[d:2 * d], out[2 * d:3 * d]
+    cov = out[3 * d:].view(d, d) if want_cov else None
+    ws = torch.empty(max(8, _lib.lib.vb_sample_moments_workspace_bytes(n, d, int(want_cov))), dtype=torch.uint8,
+                     device=x.device)
+    _lib.check(_lib.lib.vb_sample_moments_f64(_lib.ptr(x), n, d, x.stride(0), _lib.ptr(mean), _lib.ptr(m2), _lib.ptr(m4),
+                                              _lib.ptr(cov), _lib.ptr(ws), ws.numel(), _lib.stream()))
+    return mean, m2, m4, cov
+
+
 def wasserstein_bounds(d2, *, samples=None, moment_bound_fn=None):
     """1- and 2-Wasserstein bounds from a 2-divergence bound (diagnostics.py:106-145)."""
     results = dict()
     if moment_bound_fn is None:
         if samples is None:
             raise ValueError('must provides samples if moment_bound_fn not given')
-        x = to_dev(samples)
-        if x.dim() == 1:
-            x = x[:, None]
-        centered = x - x.mean(dim=0, keepdim=True)
+        n = int(np.shape(samples)[0]) if not isinstance(samples, torch.Tensor) else int(samples.shape[0])
+        _, m2, m4, _ = sample_moments(samples)
+        sums = {2: float(m2.sum()), 4: float(m4.sum())}
 
         def moment_bound_fn(p):
-            # per-coordinate central power sums, as the reference (diagnostics.py:140-141)
-            return float((centered ** p).sum(dim=1).mean())
+            # mean over draws of the per-coordinate central power sums, as the reference (diagnostics.py:140-141)
+            return sums[p] / n
     for p in [1, 2]:
         Cp = moment_bound_fn(2 * p)
         results['W{}'.format(p)] = 2 * Cp ** (.5 / p) * np.expm1(d2) ** (.5 / p)
@@ -92,8 +108,9 @@ def all_diagnostics(log_weights, *, samples=None, moment_bound_fn=None, q_var=No
                                           return_log_norm_bound=True)
     results = wasserstein_bounds(d2, samples=samples, moment_bound_fn=moment_bound_fn)
     if q_var is None and samples is not None:
-        x = to_dev(samples)
-        q_var = torch.cov(x if x.dim() == 1 else x.t()).cpu().numpy()     # np.cov(samples.T)
+        q_var = sample_moments(samples, want_cov=True)[3].cpu().numpy()   # np.cov(samples.T), SYRK on the FP64 tensor pipe
+        if q_var.shape == (1, 1):
+            q_var = q_var.reshape(())                                      # np.cov of one variable is a scalar
     results.update(error_bounds(q_var=q_var, p_var=p_var, **results))
     results['d2'] = d2
     results['log_norm_bound'] = log_norm_bound

@@ -107,7 +107,8 @@ class FusedStep(object):
         self.grad_hist = torch.zeros(self.ring, 2 * d, dtype=F64, device=dev) if ring and want_grad_hist else None
         self.dir_hist = torch.zeros(self.ring, 2 * d, dtype=F64, device=dev) if ring and want_dir_hist else None
         self.direction = None
-        self.ws = torch.empty(_lib.lib.vb_mf_step_workspace_bytes(S, d), dtype=torch.uint8, device=dev)
+        # zero-initialised: the workspace carries the kernels' block ticket across calls
+        self.ws = torch.zeros(_lib.lib.vb_mf_step_workspace_bytes(S, d), dtype=torch.uint8, device=dev)
         self.steps_done = 0
         self.launches_per_step = 3
         self.path = model.path

@@ -50,6 +50,25 @@ class Model(object):
             (g,) = torch.autograd.grad(lp.sum(), t)
         return lp.detach(), g
 
+    def point_derivatives(self, m, V=None, want_hessian=False):
+        """Derivatives of the log density at ONE point m[d] (CUDA tensor), for the control-variate
+        ExclusiveKL estimators (objectives.py:200-204, :220-221, :238-239): (grad[d], H V^T as [K,d] or None,
+        H[d,d] or None).  Generic models are differentiated by torch autograd (the reference uses autograd's
+        grad / make_hvp / hessian); plugins override this with analytic forms."""
+        m = m.detach()
+
+        def f(x):
+            return self._log_density(x[None, :]).sum()
+
+        with torch.enable_grad():
+            x = m.clone().requires_grad_(True)
+            (g,) = torch.autograd.grad(f(x), x)
+            HV = None
+            if V is not None:
+                HV = torch.stack([torch.autograd.functional.hvp(f, m, v)[1] for v in V])
+            H = torch.autograd.functional.hessian(f, m) if want_hessian else None
+        return g.detach(), HV, H
+
     def constrain(self, model_param):
         raise NotImplementedError()
 
@@ -206,6 +225,43 @@ class GLMModel(Model):
         ll, G = buf[:S], buf[S:].view_as(theta)
         return ll + self.log_prior(theta), G - theta / self.prior_scale ** 2
 
+    def point_derivatives(self, m, V=None, want_hessian=False):
+        """Model.point_derivatives through vb_glm_point_f64: gradient and up to 8 Hessian-vector products in one
+        pass over X, the full Hessian as a weighted SYRK on the FP64 tensor pipe; the prior's part added here.
+        Sums are all-reduced when the observations are sharded."""
+        d = self.dim
+        m = m.detach().to(F64).contiguous()
+        K = 0 if V is None else int(V.shape[0])
+        if K > 8:
+            parts = [self.point_derivatives(m, V[i:i + 8], False)[1] for i in range(0, K, 8)]
+            g, _, H = self.point_derivatives(m, None, want_hessian)
+            return g, torch.cat(parts), H
+        Kp = K if K <= 4 else 8
+        Vp = None
+        if K:
+            Vp = torch.zeros(Kp, d, dtype=F64, device=m.device)
+            Vp[:K] = V
+        nbytes = _lib.lib.vb_glm_point_workspace_bytes(self.N, d, Kp, int(want_hessian))
+        ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=m.device)
+        n_out = d + Kp * d + (d * d if want_hessian else 0)
+        out = torch.zeros(n_out, dtype=F64, device=m.device)
+        g, HV = out[:d], out[d:d + Kp * d].view(Kp, d) if Kp else None
+        H = out[d + Kp * d:].view(d, d) if want_hessian else None
+        _lib.check(_lib.lib.vb_glm_point_f64(
+            _lib.ptr(self.X), self.X.stride(0), _lib.ptr(self.y), self.N, d, self.link, _lib.ptr(m), _lib.ptr(Vp), Kp,
+            None, _lib.ptr(g), _lib.ptr(HV) if Kp else None, _lib.ptr(H) if want_hessian else None,
+            _lib.ptr(ws), ws.numel(), _lib.stream()))
+        self._allreduce(out)
+        it2 = 1.0 / self.prior_scale ** 2
+        g = g - m * it2
+        if K:
+            HV = HV[:K] - V * it2
+        else:
+            HV = None
+        if want_hessian:
+            H = H - it2 * torch.eye(d, dtype=F64, device=m.device)
+        return g, HV, H
+
     def log_prior(self, theta):
         d = self.dim
         return (-0.5 * (theta * theta).sum(dim=1) / self.prior_scale ** 2
@@ -283,6 +339,11 @@ class GaussianTarget(Model):
         z = (theta - self.mean) / self.sd
         return -0.5 * (z * z).sum(dim=1) + self._const, -z / self.sd
 
+    def point_derivatives(self, m, V=None, want_hessian=False):
+        h = -1.0 / (self.sd * self.sd)                    # diagonal Hessian
+        g = -(m - self.mean) / (self.sd * self.sd)
+        return g, None if V is None else V * h, torch.diag(h) if want_hessian else None
+
 
 class StudentTTarget(Model):
     """Product Student-t target sum_j t_df(theta_j; loc_j, scale_j)."""
@@ -301,3 +362,10 @@ class StudentTTarget(Model):
         z = (theta - self.loc) / self.scale
         lp = -0.5 * (df + 1.0) * torch.log1p(z * z / df).sum(dim=1) + self._const
         return lp, -(df + 1.0) * z / ((df + z * z) * self.scale)
+
+    def point_derivatives(self, m, V=None, want_hessian=False):
+        df = self.df
+        z = (m - self.loc) / self.scale
+        g = -(df + 1.0) * z / ((df + z * z) * self.scale)
+        h = -(df + 1.0) * (df - z * z) / ((df + z * z) ** 2 * self.scale * self.scale)
+        return g, None if V is None else V * h, torch.diag(h) if want_hessian else None
