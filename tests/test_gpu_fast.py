@@ -51,13 +51,16 @@ def test_fast_sweep_vs_oracle(vb, vo, N, d, S):
     vp = points['conv']
     v, gr = vb.AlphaDivergence(approx, model, S, 2.0)(vp, base=base)
     v0, g0, lw0 = vo.alpha_divergence_meanfield(vp, base, oracle_model, 2.0)
-    # AlphaDivergence weights are exp(alpha (lw - max)): an ABSOLUTE error e in a log-weight is a RELATIVE error
-    # alpha * e in that sample's weight, on top of the sweep's own 1e-4.  lw sums N fp32-accumulated terms, so e
-    # grows like sqrt(N) (DESIGN.md 4.2 'AlphaDivergence on the fast path'); the gradient is held to
-    # 1e-4 + alpha * max|lw - lw_oracle| with the measured log-weight error, and that error itself to its budget.
-    dlw = float(np.max(np.abs(approx.last_log_weights.cpu().numpy() - lw0)))
-    assert dlw < 4e-6 * np.sqrt(N) + 1e-9 * abs(lw0).max()
-    assert relerr(v, v0) < TOL_FAST and relerr(gr, g0) < TOL_FAST + 2.0 * dlw
+    # AlphaDivergence weights are exp(alpha (lw - max lw)): an error e_s in log-weight s that is NOT common to all
+    # samples is a RELATIVE error alpha * e_s in that sample's weight, on top of the sweep's own 1e-4 (a common shift
+    # -- the fp32 softplus has a systematic relative bias ~2e-6 -- cancels in the weights and only moves the value).
+    # The gradient is held to 1e-4 + alpha * max_s |e_s - mean e| with the MEASURED log-weight error, and that spread
+    # to the budget stated in DESIGN.md 4.2 ("AlphaDivergence on the fast path").
+    e = approx.last_log_weights.cpu().numpy() - lw0
+    spread = float(np.max(np.abs(e - e.mean())))
+    print('alpha fast path: N=%d d=%d common shift %.3e, spread %.3e, grad err %.3e' % (N, d, e.mean(), spread, relerr(gr, g0)))
+    assert spread < 2.5e-4
+    assert relerr(v, v0) < TOL_FAST and relerr(gr, g0) < TOL_FAST + 2.0 * spread
     theta = vo.mfg_sample(vp, base)
     assert relerr(model(theta), oracle_model(theta)[0]) < TOL_FAST
     # general float64 draws (not fp16-exact) still meet the tolerance
