@@ -280,6 +280,28 @@ int vb_sample_moments_f64(const double* x, int64_t n, int d, int64_t ldx, double
                           double* cov, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Device-side convergence statistics of FASO / RAABBVI on the iterate ring written by the fused step
+ * (vb_step_buffers.param_hist: row t % ring holds the iterate after step t).  `end` is the physical row one past
+ * the newest iterate; a window of W rows is rows end-W .. end-1 (mod ring), oldest first.
+ *   vb_faso_rhat_f64  : max over parameters of the split-R-hat of the last W iterates, for nwin <= 16 window sizes
+ *                       at once (windows_host: HOST array) -- _mc_diagnostics.py:124-184, optimization.py:551-563;
+ *   vb_ring_mean_f64  : column means (and optionally sum (x-mean)^2) of a window -- the iterate average
+ *                       (optimization.py:563, :568) and np.var(ddof=1) of MCSE (:119);
+ *   vb_faso_center_f64: the window minus `mean`, zero padded to m rows, layout [m, P] -- the input of the
+ *                       FFT autocovariance (_mc_diagnostics.py:21-37; the FFT is a cuFFT call made by the host side);
+ *   vb_faso_ess_f64   : Geyer's initial positive / monotone sequence ESS of every parameter from the autocovariances
+ *                       acov[t][p] = scale * acov_raw[t * ld + p] (_mc_diagnostics.py:56-99).  acov_raw is overwritten.
+ * ------------------------------------------------------------------------------------- */
+size_t vb_faso_rhat_workspace_bytes(int P, int nwin);
+int vb_faso_rhat_f64(const double* hist, int64_t ring, int P, int64_t end, const int64_t* windows_host, int nwin,
+                     double jitter, double* rhat_max, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int vb_ring_mean_f64(const double* hist, int64_t ring, int P, int64_t end, int64_t W, double* mean, double* css,
+                     cudaStream_t stream);
+int vb_faso_center_f64(const double* hist, int64_t ring, int P, int64_t end, int64_t W, int64_t m, const double* mean,
+                       double* centered, cudaStream_t stream);
+int vb_faso_ess_f64(double* acov_raw, int64_t ld, double scale, int64_t n_draw, int P, double* ess, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Pareto-smoothed importance sampling and divergence-bound moments
  * (viabel/_psis.py:113-209 psislw, :212-332 gpdfitnew, :335-377 gpinv, :380-396 sumlogs;
  *  viabel/diagnostics.py:148-186 divergence_bound).

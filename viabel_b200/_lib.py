@@ -62,6 +62,11 @@ _PROTOS = {
     'vb_glm_point_f64': (c_int, [P, c_int64, P, c_int64, c_int, c_int, P, P, c_int, P, P, P, P, P, c_size_t, P]),
     'vb_sample_moments_workspace_bytes': (c_size_t, [c_int64, c_int, c_int]),
     'vb_sample_moments_f64': (c_int, [P, c_int64, c_int, c_int64, P, P, P, P, P, c_size_t, P]),
+    'vb_faso_rhat_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'vb_faso_rhat_f64': (c_int, [P, c_int64, c_int, c_int64, P, c_int, c_double, P, P, c_size_t, P]),
+    'vb_ring_mean_f64': (c_int, [P, c_int64, c_int, c_int64, c_int64, P, P, P]),
+    'vb_faso_center_f64': (c_int, [P, c_int64, c_int, c_int64, c_int64, c_int64, P, P, P]),
+    'vb_faso_ess_f64': (c_int, [P, c_int64, c_double, c_int64, c_int, P, P]),
     # peer-memory communicator and the fused step (structures: viabel_b200/engine.py)
     'vb_comm_create': (c_int, [P, c_int, c_int, c_size_t, P]),
     'vb_comm_connect': (c_int, [P, P]),

@@ -108,7 +108,8 @@ __global__ void geyer_ess_kernel(double* __restrict__ raw, long long ld, double 
   const double var_plus = mean_var * (nd - 1.0) / nd;
   double even = 1.0;
   double odd = 1.0 - (mean_var - a[ld] * scale) / var_plus;
-  bool nan_seen = isnan(odd);
+  const bool nan_seen = isnan(odd);     // the reference's isnan(rho).any(): only rho[1] can be NaN (the others are stored
+                                        // only when their pair sum compares >= 0)
   a[0] = even;
   a[ld] = odd;
   long long t = 1;
@@ -122,7 +123,6 @@ __global__ void geyer_ess_kernel(double* __restrict__ raw, long long ld, double 
       a[(t + 1) * ld] = 0.0;
       a[(t + 2) * ld] = 0.0;
     }
-    nan_seen = nan_seen || isnan(even) || isnan(odd);
     t += 2;
   }
   const long long max_t = t - 2;
