@@ -248,6 +248,59 @@ def gen_objectives_cv():
     print('objectives_cv: %d arrays' % len(out))
 
 
+def gen_lr_gaussian():
+    """LRGaussian (approximations.py:610-731): family functions, then ExclusiveKL / AlphaDivergence on it."""
+    from viabel.approximations import LRGaussian
+    out = {}
+    rs = np.random.RandomState(153)
+    for d, k in ((3, 0), (3, 1), (8, 3), (6, 6)):
+        tag = 'lr_d%d_k%d' % (d, k)
+        fam = LRGaussian(d, seed=226, k=k)
+        vp = np.concatenate([rs.randn(d), 0.4 * rs.randn(d) - 0.3, 0.5 * rs.randn(d * k)])
+        vp1 = np.concatenate([rs.randn(d), 0.4 * rs.randn(d) - 0.3, 0.5 * rs.randn(d * k)])
+        with Recorder() as rec:
+            x = fam.sample(vp, 40)
+        assert rec[0][0] == 'randn' and rec[1][0] == 'randn'
+        out[tag + '/z'] = rec[0][2]
+        out[tag + '/eps'] = rec[1][2]
+        out[tag + '/var_param'] = vp
+        out[tag + '/var_param1'] = vp1
+        out[tag + '/sample'] = x
+        out[tag + '/log_density'] = np.asarray(fam.log_density(vp, x))
+        out[tag + '/log_density_1d'] = np.asarray(fam.log_density(vp, x[0]))
+        out[tag + '/entropy'] = np.asarray(fam.entropy(vp))
+        out[tag + '/kl'] = np.asarray(fam.kl(vp, vp1))
+        mean, cov = fam.mean_and_cov(vp)
+        out[tag + '/mean'] = mean
+        out[tag + '/cov'] = cov
+        for p in (2, 4):
+            out[tag + '/moment%d' % p] = np.asarray(fam.pth_moment(vp, p))
+        out[tag + '/init_head'] = fam.init_param()[:2 * d]
+    models = {}
+    X, y, _ = logistic_problem(60, 4, seed=11)
+    models['logistic_d4'] = (4, logistic_log_p(X, y, 10.0))
+    mean, sd = target_params(5, seed=14)
+    models['gauss_d5'] = (5, gauss_log_p(mean, sd))
+    for mname, (d, logp) in models.items():
+        for k in (0, 2):
+            fam = LRGaussian(d, seed=1214, k=k)
+            vp = np.concatenate([rs.randn(d), 0.4 * rs.randn(d) - 0.3, 0.5 * rs.randn(d * k)])
+            objs = {'ekl': lambda: ExclusiveKL(fam, logp, 7), 'ekl_path': lambda: ExclusiveKL(fam, logp, 7, use_path_deriv=True),
+                    'alpha2': lambda: AlphaDivergence(fam, logp, 7, 2.0)}
+            for oname, mk in objs.items():
+                tag = 'obj/%s/k%d/%s' % (mname, k, oname)
+                np.random.seed(5039)
+                with Recorder() as rec:
+                    value, grad = mk()(vp)
+                out[tag + '/z'] = rec[0][2]
+                out[tag + '/eps'] = rec[1][2]
+                out[tag + '/var_param'] = vp
+                out[tag + '/value'] = np.asarray(float(value))
+                out[tag + '/grad'] = np.asarray(grad, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, 'lr_gaussian.npz'), **out)
+    print('lr_gaussian: %d arrays' % len(out))
+
+
 def gen_optimizers():
     out = {}
     rs = np.random.RandomState(153)
@@ -444,6 +497,7 @@ if __name__ == '__main__':
     gen_families()
     gen_objectives()
     gen_objectives_cv()
+    gen_lr_gaussian()
     gen_optimizers()
     gen_psis()
     gen_diagnostics()

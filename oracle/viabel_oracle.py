@@ -543,6 +543,98 @@ def adam_direction(state, grad, beta1=0.9, beta2=0.999, jitter=1e-8):
 
 
 # --------------------------------------------------------------------------
+# LRGaussian (approximations.py:552-731): var_param = [mu(d), log_sigma(d), B(d,k) row-major]
+# (PatternDict insertion order :552-557), Sigma = B B^T + diag(exp(2 log_sigma)).
+# Dense d x d algebra on purpose: an independent restatement of what the Woodbury / determinant-lemma
+# code of the reference computes.
+# --------------------------------------------------------------------------
+def lr_unpack(var_param, dim, k):
+    vp = np.asarray(var_param, dtype=np.float64)
+    return vp[:dim], vp[dim:2 * dim], vp[2 * dim:].reshape(dim, k)
+
+
+def lr_sigma(var_param, dim, k):
+    _, ls, B = lr_unpack(var_param, dim, k)
+    return B @ B.T + np.diag(np.exp(2 * ls))
+
+
+def lr_sample(var_param, z, eps):
+    """mu + z B^T + exp(log_sigma) * eps with z drawn FIRST (approximations.py:638-646)."""
+    d, k = eps.shape[1], z.shape[1]
+    mu, ls, B = lr_unpack(var_param, d, k)
+    return mu + z @ B.T + np.exp(ls) * eps
+
+
+def lr_entropy(var_param, dim, k):
+    return 0.5 * dim * (LOG_2PI + 1.0) + 0.5 * np.linalg.slogdet(lr_sigma(var_param, dim, k))[1]
+
+
+def lr_log_density(var_param, x, k):
+    x = np.atleast_2d(x)
+    d = x.shape[1]
+    mu = lr_unpack(var_param, d, k)[0]
+    Sig = lr_sigma(var_param, d, k)
+    diff = x - mu
+    maha = np.sum(diff * np.linalg.solve(Sig, diff.T).T, axis=1)
+    return -0.5 * (d * LOG_2PI + np.linalg.slogdet(Sig)[1] + maha)
+
+
+def lr_kl(vp0, vp1, dim, k):
+    mu0, mu1 = lr_unpack(vp0, dim, k)[0], lr_unpack(vp1, dim, k)[0]
+    S0, S1 = lr_sigma(vp0, dim, k), lr_sigma(vp1, dim, k)
+    md = mu0 - mu1
+    return 0.5 * (np.linalg.slogdet(S1)[1] - np.linalg.slogdet(S0)[1] - dim + md @ np.linalg.solve(S1, md)
+                  + np.trace(np.linalg.solve(S1, S0)))
+
+
+def lr_mean_and_cov(var_param, dim, k):
+    return lr_unpack(var_param, dim, k)[0].copy(), lr_sigma(var_param, dim, k)
+
+
+def lr_pth_moment(var_param, dim, k, p):
+    ev = np.linalg.eigvalsh(lr_sigma(var_param, dim, k))
+    return np.sum(ev) if p == 2 else 2 * np.sum(ev ** 2) + np.sum(ev) ** 2
+
+
+def lr_objective(var_param, z, eps, model, kind, alpha=None):
+    """ExclusiveKL ('ekl', 'ekl_path'; objectives.py:154-164) and AlphaDivergence ('alpha'; :443-460) for LRGaussian
+    with analytic gradients.  Returns (value, grad)."""
+    S, d = eps.shape
+    k = z.shape[1]
+    mu, ls, B = lr_unpack(var_param, d, k)
+    sig = np.exp(ls)
+    theta = mu + z @ B.T + sig * eps
+    f, G = model(theta)
+    Sinv = np.linalg.inv(lr_sigma(var_param, d, k))
+    u = theta - mu
+    a = u @ Sinv                                          # rows: Sigma^-1 u_s
+    if kind == 'ekl':
+        value = -(np.mean(f) + lr_entropy(var_param, d, k))
+        gmu = -np.mean(G, axis=0)
+        gls = -(np.mean(G * eps, axis=0) * sig + sig * sig * np.diag(Sinv))
+        gB = -(G.T @ z / S + Sinv @ B)
+    elif kind == 'ekl_path':
+        value = -np.mean(f - lr_log_density(var_param, theta, k))
+        gt = G + a
+        gmu = -np.mean(gt, axis=0)
+        gls = -np.mean(gt * eps, axis=0) * sig
+        gB = -gt.T @ z / S
+    else:
+        lw = f - lr_log_density(var_param, theta, k)
+        m = np.max(lw)
+        sv = np.exp(lw - m) ** alpha
+        value = np.log(np.mean(sv)) / alpha + m
+        gmu = alpha / S * (sv @ G)
+        dls = G * eps * sig + a * eps * sig + sig * sig * np.diag(Sinv) - sig * sig * a * a
+        gls = alpha / S * (sv @ dls)
+        gB = np.zeros((d, k))
+        for s_ in range(S):
+            gB += sv[s_] * (np.outer(G[s_] + a[s_], z[s_]) + Sinv @ B - np.outer(a[s_], a[s_] @ B))
+        gB *= alpha / S
+    return value, np.concatenate([gmu, gls, gB.reshape(-1)])
+
+
+# --------------------------------------------------------------------------
 # PSIS (_psis.py:113-396) -- selection restatement (no full argsort)
 # --------------------------------------------------------------------------
 def psis_tail_len(n, Reff=1.0):

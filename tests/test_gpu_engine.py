@@ -262,3 +262,77 @@ def test_fused_step_two_ranks_one_process(vb, vo):
         del engs
         for c in comms:
             lib.vb_comm_destroy(c.handle)
+
+
+def _ar1_chains(n, P, seed):
+    rs = np.random.RandomState(seed)
+    phi = rs.uniform(0.0, 0.95, size=P)
+    x = np.zeros((n, P))
+    e = rs.randn(n, P)
+    for t in range(1, n):
+        x[t] = phi * x[t - 1] + e[t]
+    x += np.linspace(0, 1.5, n)[:, None] * (rs.rand(P) < 0.2)          # some coordinates still drifting
+    x[:, 3] = 0.25                                                     # a constant coordinate
+    return x
+
+
+@pytest.mark.parametrize('n,P,ring,shift', [(900, 37, 900, 0), (1500, 130, 2000, 700), (640, 1024, 640, 411)])
+def test_ring_statistics_vs_host_mirror(vb, n, P, ring, shift):
+    """csrc/faso.cu on a (wrapped) device ring against the numpy mirror of _mc_diagnostics.py (itself pinned to the
+    reference in tests/golden/mc_diagnostics.npz): split-R-hat per window, window means, ESS and MCSE."""
+    from viabel_b200 import _mc_diagnostics as mc
+    x = _ar1_chains(n, P, seed=n + P)
+    hist = torch.zeros(ring, P, dtype=torch.float64, device='cuda')
+    idx = (np.arange(n) + shift) % ring                                # row t of the chain lives at (t + shift) % ring
+    hist[torch.as_tensor(idx, device='cuda')] = torch.as_tensor(x, device='cuda')
+    end = (shift + n) % ring
+    stats = mc.RingStats(hist, ring, P)
+    windows = np.linspace(200, int(0.95 * n), num=5, dtype=int)
+    got = stats.rhat_max(end, windows)
+    with np.errstate(all='ignore'):
+        want = np.array([np.max(mc.compute_R_hat(x[-int(w):], 0)) for w in windows])
+    np.testing.assert_allclose(got, want, rtol=1e-10)
+    ok, best = stats.convergence_check(end, windows)
+    ok0, best0 = mc.R_hat_convergence_check(x, windows)
+    assert ok == ok0 and best == best0
+    for W in (201, 400, n):
+        mean = stats.window_mean(end, W).cpu().numpy()
+        np.testing.assert_allclose(mean, x[-W:].mean(axis=0), rtol=1e-12, atol=1e-13)
+        ess, mcse, mean2 = stats.mcse(end, W)
+        with np.errstate(all='ignore'):
+            ess0, mcse0 = mc.MCSE(x[-W:])
+        ess0 = np.asarray(ess0)
+        fin = np.isfinite(ess0)
+        assert np.array_equal(np.isnan(ess), np.isnan(ess0))
+        np.testing.assert_allclose(ess[fin], ess0[fin], rtol=1e-7)
+        np.testing.assert_allclose(mcse[fin], mcse0[fin], rtol=1e-7)
+
+
+def test_faso_fused_matches_unfused(vb, monkeypatch, capsys):
+    """FASO (optimization.py:521-633) through graph-replayed steps + device-ring statistics takes the same decisions
+    (k_Rhat, k_conv, k_stopped) and returns the same iterate average as the per-iteration loop on the same draws."""
+    import viabel_b200.engine as engine
+    N, d, S = 3000, 6, 12
+    X, y, beta = logistic_problem(N, d, seed=44)
+    model = vb.LogisticRegression(X, y)
+    out = {}
+    for fused in (True, False):
+        if not fused:
+            monkeypatch.setattr(engine, 'fused_step_supported', lambda *a, **k: False)
+        approx = vb.MFGaussian(d, seed=17)
+        sgo = vb.RMSProp(0.05, diagnostics=True)
+        sgo.progress = False
+        faso = vb.FASO(sgo, W_min=100, k_check=100, mcse_threshold=0.2)
+        out[fused] = faso.optimize(3000, vb.ExclusiveKL(approx, model, S), approx.init_param())
+    a, b = out[True], out[False]
+    assert a['k_Rhat'] == b['k_Rhat'] and a['k_conv'] == b['k_conv'] and a['k_stopped'] == b['k_stopped']
+    assert a['k_conv'] is not None
+    n = len(b['value_history'])
+    assert a['value_history'].shape == (n,) and a['variational_param_history'].shape == b['variational_param_history'].shape
+    assert relerr(a['value_history'], b['value_history']) < 1e-9
+    assert relerr(a['variational_param_history'], b['variational_param_history']) < 1e-9
+    assert relerr(a['grad_history'], b['grad_history']) < 1e-8
+    assert relerr(a['descent_dir_history'], b['descent_dir_history']) < 1e-8
+    assert relerr(a['opt_param'], b['opt_param']) < 1e-9
+    if 'mcse_history' in b and len(b['mcse_history']):
+        assert relerr(a['mcse_history'][-1], b['mcse_history'][-1]) < 1e-6

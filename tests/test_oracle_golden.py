@@ -340,3 +340,32 @@ def test_control_variate_objectives(golden, mname):
         assert relerr(gr, g[tag + '/grad']) < 1e-10, tag
         n += 1
     assert n == 16
+
+
+def test_lr_gaussian(golden):
+    """LRGaussian family functions and objectives (approximations.py:610-731) against the unmodified reference."""
+    g = golden('lr_gaussian')
+    for d, k in ((3, 0), (3, 1), (8, 3), (6, 6)):
+        t = 'lr_d%d_k%d' % (d, k)
+        vp, vp1 = g[t + '/var_param'], g[t + '/var_param1']
+        x = vo.lr_sample(vp, g[t + '/z'], g[t + '/eps'])
+        assert relerr(x, g[t + '/sample']) < 1e-13
+        assert relerr(vo.lr_log_density(vp, x, k), g[t + '/log_density']) < 1e-11
+        assert relerr(vo.lr_log_density(vp, x[0], k), g[t + '/log_density_1d']) < 1e-11
+        assert relerr(vo.lr_entropy(vp, d, k), g[t + '/entropy']) < 1e-12
+        assert relerr(vo.lr_kl(vp, vp1, d, k), g[t + '/kl']) < 1e-10
+        mean, cov = vo.lr_mean_and_cov(vp, d, k)
+        assert relerr(mean, g[t + '/mean']) < 1e-14 and relerr(cov, g[t + '/cov']) < 1e-13
+        for p in (2, 4):
+            assert relerr(vo.lr_pth_moment(vp, d, k, p), g[t + '/moment%d' % p]) < 1e-12
+    models = {'logistic_d4': cv_model('logistic_d4')[0], 'gauss_d5': cv_model('gauss_d5')[0]}
+    n = 0
+    for key in [q for q in g if q.startswith('obj/') and q.endswith('/value')]:
+        t = key[:-len('/value')]
+        _, mname, kk, oname = t.split('/')
+        kind = 'alpha' if oname == 'alpha2' else oname
+        v, gr = vo.lr_objective(g[t + '/var_param'], g[t + '/z'], g[t + '/eps'], models[mname], kind, 2.0)
+        assert relerr(v, g[t + '/value']) < 1e-11, t
+        assert relerr(gr, g[t + '/grad']) < 1e-9, t
+        n += 1
+    assert n == 12

@@ -5,7 +5,7 @@ Python, :119)."""
 import numpy as np
 from scipy.fft import next_fast_len
 
-__all__ = ['autocov', 'ess', 'MCSE', 'compute_R_hat', 'R_hat_convergence_check']
+__all__ = ['autocov', 'ess', 'MCSE', 'compute_R_hat', 'R_hat_convergence_check', 'RingStats']
 
 
 def autocov(samples, axis=-1):
@@ -101,3 +101,62 @@ def R_hat_convergence_check(samples, windows, Rhat_threshold=1.1):
     vals = [np.max(compute_R_hat(samples[-int(w):], 0)) for w in windows]
     best = int(np.argmin(vals))
     return vals[best] <= Rhat_threshold, windows[best]
+
+
+class RingStats(object):
+    """The same statistics computed ON THE DEVICE over the iterate ring the fused step writes (engine.FusedStep.
+    param_hist), batched over all parameters: nothing but a handful of scalars (R-hat per window) or two
+    P-vectors (ESS, MCSE) ever crosses to the host.  Kernels: csrc/faso.cu; the FFT is cuFFT through torch.fft."""
+
+    def __init__(self, hist, ring, P):
+        import torch
+        self.torch = torch
+        self.hist, self.ring, self.P = hist, int(ring), int(P)
+
+    def rhat_max(self, end, windows, jitter=1e-8):
+        """max over parameters of the split-R-hat of the last W iterates, one value per window (host array)."""
+        import ctypes
+        from . import _lib
+        torch = self.torch
+        wins = [int(w) for w in windows]
+        out = torch.empty(len(wins), dtype=torch.float64, device=self.hist.device)
+        ws = torch.empty(max(8, _lib.lib.vb_faso_rhat_workspace_bytes(self.P, len(wins))), dtype=torch.uint8,
+                         device=self.hist.device)
+        arr = (ctypes.c_int64 * len(wins))(*wins)
+        _lib.check(_lib.lib.vb_faso_rhat_f64(_lib.ptr(self.hist), self.ring, self.P, int(end), arr, len(wins), float(jitter),
+                                             _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream()))
+        return out.cpu().numpy()
+
+    def convergence_check(self, end, windows, Rhat_threshold=1.1):
+        """R_hat_convergence_check (:163-184) on the ring."""
+        vals = self.rhat_max(end, windows)
+        best = int(np.argmin(vals))
+        return bool(vals[best] <= Rhat_threshold), windows[best]
+
+    def window_mean(self, end, W, want_css=False):
+        """Column means of the last W iterates (device tensor); with want_css also sum (x - mean)^2."""
+        from . import _lib
+        torch = self.torch
+        mean = torch.empty(self.P, dtype=torch.float64, device=self.hist.device)
+        css = torch.empty(self.P, dtype=torch.float64, device=self.hist.device) if want_css else None
+        _lib.check(_lib.lib.vb_ring_mean_f64(_lib.ptr(self.hist), self.ring, self.P, int(end), int(W), _lib.ptr(mean),
+                                             _lib.ptr(css), _lib.stream()))
+        return (mean, css) if want_css else mean
+
+    def mcse(self, end, W):
+        """(ess[P], mcse[P], mean[P]) of the last W iterates as host arrays (MCSE, :102-121)."""
+        from . import _lib
+        torch = self.torch
+        W = int(W)
+        mean, css = self.window_mean(end, W, want_css=True)
+        m = int(next_fast_len(2 * W))
+        centered = torch.empty(m, self.P, dtype=torch.float64, device=self.hist.device)
+        _lib.check(_lib.lib.vb_faso_center_f64(_lib.ptr(self.hist), self.ring, self.P, int(end), W, m, _lib.ptr(mean),
+                                               _lib.ptr(centered), _lib.stream()))
+        f = torch.fft.rfft(centered, dim=0)
+        acov = torch.fft.irfft(f * f.conj(), n=m, dim=0).contiguous()          # [m, P], unnormalised
+        ess_d = torch.empty(self.P, dtype=torch.float64, device=self.hist.device)
+        _lib.check(_lib.lib.vb_faso_ess_f64(_lib.ptr(acov), self.P, 1.0 / W, W, self.P, _lib.ptr(ess_d), _lib.stream()))
+        sd = torch.sqrt(css / (W - 1.0))
+        out = torch.stack([ess_d, sd / torch.sqrt(ess_d), mean]).cpu().numpy()
+        return out[0], out[1], out[2]

@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from ._tensor import F64, device, is_host, like_input, to_dev
 
-__all__ = ['ApproximationFamily', 'MFGaussian', 'MFStudentT', 'MultivariateT']
+__all__ = ['ApproximationFamily', 'MFGaussian', 'MFStudentT', 'MultivariateT', 'LRGaussian']
 
 
 class ApproximationFamily(ABC):
@@ -373,3 +373,124 @@ class MultivariateT(ApproximationFamily):
 
     def supports_pth_moment(self, p):
         return p in [2, 4] and p < self._df
+
+
+class LRGaussian(ApproximationFamily):
+    """A low rank Gaussian approximation family (approximations.py:610-731): Sigma = B B^T + diag(exp(2 log_sigma)),
+    var_param = [mu(d), log_sigma(d), B(d,k) row-major] (the PatternDict order of :552-557).  Supports entropy and KL,
+    so RAABBVI can run on it.  Everything is evaluated through the k x k capacitance matrix
+    M = I + B^T D^-2 B (Woodbury / determinant lemma): O(n d k) for n draws, never a d x d inverse.
+    Base draws: z[n,k] FIRST, then eps[n,d] (:641-642), from the family's Philox stream."""
+
+    def __init__(self, dim, seed=1, k=0):
+        self._k = int(k)
+        self._seed = int(seed)
+        self._offset = 0
+        self.last_base = None
+        super().__init__(dim, 2 * dim + dim * self._k, True, True)
+
+    @property
+    def k(self):
+        return self._k
+
+    def _normals(self, n, seed, offset):
+        out = torch.empty(n, dtype=F64, device=device())
+        if n:
+            _lib.check(_lib.lib.vb_philox_normal_f64(_lib.ptr(out), n, seed, offset, 0, _lib.stream()))
+        return out
+
+    def init_param(self):
+        # mu = 0, log_sigma = 1, B ~ N(0,1) from the family's stream (approximations.py:630-634)
+        B = self._normals(self.dim * self._k, self._seed, self._offset).cpu().numpy()
+        self._offset += B.size + (B.size & 1)
+        return np.concatenate([np.zeros(self.dim), np.ones(self.dim), B])
+
+    def unpack(self, vp):
+        d, k = self.dim, self._k
+        if vp.numel() != self.var_param_dim:
+            raise ValueError('var_param has the wrong length')
+        return vp[:d], vp[d:2 * d], vp[2 * d:].reshape(d, k)
+
+    def base_draws(self, n_samples, seed=None):
+        n, d, k = int(n_samples), self.dim, self._k
+        s, off = (self._seed, self._offset) if seed is None else (int(seed), 0)
+        z = self._normals(n * k, s, off).view(n, k)
+        off2 = off + n * k + ((n * k) & 1)
+        eps = self._normals(n * d, s, off2).view(n, d)
+        if seed is None:
+            self._offset = off2 + n * d + ((n * d) & 1)
+        return z, eps
+
+    def sample(self, var_param, n_samples, seed=None, base=None):
+        host = is_host(var_param)
+        mu, ls, B = self.unpack(to_dev(var_param))
+        z, eps = self.base_draws(n_samples, seed) if base is None else (to_dev(base[0]), to_dev(base[1]))
+        self.last_base = (z, eps)
+        return like_input(mu + z @ B.T + torch.exp(ls) * eps, host)
+
+    # -- Woodbury pieces on torch tensors (differentiable: the objectives reuse them under autograd) --------
+    @staticmethod
+    def _capacitance(ls, B):
+        Dinv2 = torch.exp(-2 * ls)
+        M = torch.eye(B.shape[1], dtype=B.dtype, device=B.device) + B.T @ (B * Dinv2[:, None])
+        return Dinv2, M
+
+    @classmethod
+    def log_det(cls, ls, B):
+        """log det(B B^T + D^2) = 2 sum(log_sigma) + log det(I + B^T D^-2 B)   (_get_log_determinant :559-573)."""
+        _, M = cls._capacitance(ls, B)
+        return 2 * ls.sum() + torch.linalg.slogdet(M)[1]
+
+    @classmethod
+    def log_density_t(cls, mu, ls, B, x):
+        d = x.shape[1]
+        Dinv2, M = cls._capacitance(ls, B)
+        diff = x - mu
+        t = (diff * Dinv2) @ B                                            # [n, k]
+        maha = (diff * diff * Dinv2).sum(dim=1) - (t * torch.linalg.solve(M, t.T).T).sum(dim=1)
+        return -0.5 * (d * np.log(2 * np.pi) + 2 * ls.sum() + torch.linalg.slogdet(M)[1] + maha)
+
+    def log_density(self, var_param, x):
+        host = is_host(x)
+        xd = to_dev(x)
+        if xd.dim() == 1:
+            xd = xd[None, :]
+        mu, ls, B = self.unpack(to_dev(var_param))
+        return like_input(self.log_density_t(mu, ls, B, xd), host)
+
+    def _entropy(self, var_param):
+        mu, ls, B = self.unpack(to_dev(var_param))
+        return float(0.5 * self.dim * (np.log(2 * np.pi) + 1) + 0.5 * self.log_det(ls, B))
+
+    def _kl(self, var_param0, var_param1):
+        # 0.5 (log det S1 - log det S0 - d + md^T S1^-1 md + tr(S1^-1 S0))   (:661-687), S1^-1 by Woodbury
+        mu0, ls0, B0 = self.unpack(to_dev(var_param0))
+        mu1, ls1, B1 = self.unpack(to_dev(var_param1))
+        Dinv2, M = self._capacitance(ls1, B1)
+        md = mu0 - mu1
+        t = (md * Dinv2) @ B1
+        maha = (md * md * Dinv2).sum() - t @ torch.linalg.solve(M, t)
+        # tr(S1^-1 S0) with S0 = B0 B0^T + D0^2: tr(D1^-2 S0) - tr(M^-1 (B1^T D1^-2) S0 (D1^-2 B1))
+        D0sq = torch.exp(2 * ls0)
+        W = B1 * Dinv2[:, None]                                           # D1^-2 B1, [d, k]
+        tr1 = (Dinv2 * D0sq).sum() + ((B0 * B0) * Dinv2[:, None]).sum()
+        WS0W = W.T @ (W * D0sq[:, None]) + (W.T @ B0) @ (B0.T @ W)
+        tr2 = torch.trace(torch.linalg.solve(M, WS0W))
+        return float(0.5 * (self.log_det(ls1, B1) - self.log_det(ls0, B0) - self.dim + maha + tr1 - tr2))
+
+    def mean_and_cov(self, var_param):
+        mu, ls, B = self.unpack(to_dev(var_param))
+        return mu.cpu().numpy().copy(), (B @ B.T + torch.diag(torch.exp(2 * ls))).cpu().numpy()
+
+    def _pth_moment(self, var_param, p):
+        # sums of eigenvalue powers are traces: sum lambda = tr Sigma, sum lambda^2 = |Sigma|_F^2 (no eigensolver)
+        mu, ls, B = self.unpack(to_dev(var_param))
+        D2 = torch.exp(2 * ls)
+        tr = float(D2.sum() + (B * B).sum())
+        if p == 2:
+            return tr
+        fro2 = float((D2 * D2).sum() + 2 * (D2 * (B * B).sum(dim=1)).sum() + ((B.T @ B) ** 2).sum())
+        return 2 * fro2 + tr ** 2
+
+    def supports_pth_moment(self, p):
+        return p in [2, 4]

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 from ._tensor import F64, device, is_host, to_dev
-from .approximations import MultivariateT, _MeanField
+from .approximations import LRGaussian, MultivariateT, _MeanField
 from .models import GLMModel, Model
 from .parallel import broadcast_seed, is_distributed
 
@@ -120,6 +120,52 @@ def _mvt_objective(approx, model, S, objective, alpha, var_param, base=None, see
     return value, approx.pack_grad(gmu, Fbar)
 
 
+class _ModelLogDensity(torch.autograd.Function):
+    """f(theta) with the model plugin's own gradient kernels as the backward pass (no autograd inside the model)."""
+
+    @staticmethod
+    def forward(ctx, theta, model):
+        f, G = model.logp_and_grad(theta.detach().contiguous())
+        ctx.save_for_backward(G)
+        return f
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (G,) = ctx.saved_tensors
+        return grad_out[:, None] * G, None
+
+
+def _lr_objective(approx, model, S, objective, alpha, var_param, base=None, seed=None):
+    """ExclusiveKL (entropy / path-derivative) and AlphaDivergence for LRGaussian (objectives.py:154-164, :443-460 with
+    approximations.py:638-646).  The model's log density and gradient come from the plugin's kernels; the O(S d k)
+    reparameterisation and the k x k Woodbury algebra of log q / entropy are differentiated by torch autograd."""
+    vp = to_dev(var_param)
+    z, eps = approx.base_draws(S, seed) if base is None else (to_dev(base[0]), to_dev(base[1]))
+    approx.last_base = (z, eps)
+    S = eps.shape[0]
+    d = approx.dim
+    with torch.enable_grad():
+        lam = vp.detach().clone().requires_grad_(True)
+        mu, ls, B = approx.unpack(lam)
+        theta = mu + z @ B.T + torch.exp(ls) * eps
+        f = _ModelLogDensity.apply(theta, model)
+        if objective == _lib.OBJ_EXCLUSIVE_KL:
+            value = -(f.mean() + 0.5 * d * (np.log(2 * np.pi) + 1) + 0.5 * approx.log_det(ls, B))
+        elif objective == _lib.OBJ_EXCLUSIVE_KL_PATH:
+            mu0, ls0, B0 = approx.unpack(vp.detach())
+            value = -(f - approx.log_density_t(mu0, ls0, B0, theta)).mean()
+        else:
+            lw = f - approx.log_density_t(mu, ls, B, theta)
+            m = lw.max().detach()
+            sv = torch.exp(lw - m) ** alpha
+            # the reference's gradient is alpha * mean(sv.detach() * d lw) -- NOT divided by mean(sv) (SURVEY App. A.2)
+            surrogate = alpha * (sv.detach() * lw).mean()
+            (grad,) = torch.autograd.grad(surrogate, lam)
+            return (torch.log(sv.mean()) / alpha + m).detach(), grad
+        (grad,) = torch.autograd.grad(value, lam)
+    return value.detach(), grad
+
+
 def _to_host(value, grad):
     """(value, grad) -> (float, numpy) with ONE device-to-host copy when both are views of the same
     [1 + len(grad)] buffer (the layout _mf_objective produces), else one copy each."""
@@ -135,6 +181,8 @@ def _mf_objective(approx, model, S, objective, alpha, var_param, base=None, seed
     CUDA tensors (no host sync)."""
     if isinstance(approx, MultivariateT):
         return _mvt_objective(approx, model, S, objective, alpha, var_param, base=base, seed=seed)
+    if isinstance(approx, LRGaussian):
+        return _lr_objective(approx, model, S, objective, alpha, var_param, base=base, seed=seed)
     if not isinstance(approx, _MeanField):
         raise NotImplementedError('only mean-field families are supported by this objective path')
     d = approx.dim

@@ -427,9 +427,136 @@ class FASO(Optimizer):
             return ess, mcse
         return MCSE(iterates)
 
+    # -- fused path: graph-replayed steps between the checks, statistics on the device ring -------------
+    def _optimize_fused(self, n_iters, objective, init_param):
+        from ._mc_diagnostics import RingStats
+        from .approximations import MFGaussian
+        from .engine import FusedStep
+        sgo = self._sgo
+        diagnostics = sgo._diagnostics
+        host_init = np.array(init_param.detach().cpu().numpy() if isinstance(init_param, torch.Tensor)
+                             else init_param, dtype=np.float64)
+        P = host_init.size
+        eng = FusedStep(objective, sgo, ring=n_iters, hist_len=n_iters, want_grad_hist=True, want_dir_hist=diagnostics)
+        eng.set_param(host_init)
+        sgo._export_state(eng)
+        stats = RingStats(eng.param_hist, n_iters, P)
+        k_conv = k_stopped = k_Rhat = None
+        W_check = None
+        mcse = ess = None
+        hist = defaultdict(list)
+        iterate_average = host_init.copy()
+        if diagnostics:
+            hist['iterate_average_k_history'].append(0)
+            hist['iterate_average_history'].append(iterate_average)
+        opt_time = 0.0
+        progress = getattr(sgo, 'progress', True)
+        bar = tqdm.tqdm(total=n_iters, disable=not progress)
+        done = 0                               # iterations completed; the reference's k is done - 1
+        try:
+            while done < n_iters:
+                # run up to and including the next iteration at which the reference looks at the history
+                k_next = (done + self._k_check - 1) // self._k_check * self._k_check        # next multiple >= done
+                if k_conv is not None:
+                    k_next = min(k_next, max(k_conv + W_check, done))
+                k_next = min(k_next, n_iters - 1)
+                t0 = _time.perf_counter()
+                eng.run(k_next + 1 - done)
+                torch.cuda.current_stream().synchronize()
+                opt_time += _time.perf_counter() - t0
+                bar.update(k_next + 1 - done)
+                done = k_next + 1
+                k = k_next
+                if k_conv is None and k % self._k_check == 0:
+                    W_upper = int(0.95 * k)
+                    if W_upper > self._W_min:
+                        windows = np.linspace(self._W_min, W_upper, num=5, dtype=int)
+                        ok, best_W = stats.convergence_check(done, windows)
+                        iterate_average = stats.window_mean(done, best_W).cpu().numpy()
+                        if diagnostics:
+                            hist['iterate_average_k_history'].append(k)
+                            hist['iterate_average_history'].append(iterate_average)
+                        if ok:
+                            k_Rhat, k_conv, W_check = k, k - best_W, best_W
+                if k_conv is not None and k - k_conv == W_check:
+                    W = W_check
+                    t1 = _time.perf_counter()
+                    ess, mcse, mean = stats.mcse(done, W)
+                    iterate_average = mean
+                    if isinstance(objective.approx, MFGaussian):
+                        # MCSE(mu / sigma, log sigma), constant coordinates dropped (optimization.py:575-590); the
+                        # statistics are per column, so the reference's np.delete acts on the per-column vectors
+                        dim = int(P / 2)
+                        last2 = eng.last_rows(eng.param_hist, 2)
+                        still = (last2[0] == last2[1]).cpu().numpy()
+                        if np.any(still):
+                            drop = np.argwhere(still)
+                            ess, mcse, mean_kept = np.delete(ess, drop), np.delete(mcse, drop), np.delete(mean, drop)
+                        else:
+                            mean_kept = mean
+                        mcse = np.concatenate((mcse[:dim] / np.exp(mean_kept[-dim:]), mcse[-dim:]))
+                    mcse_time = _time.perf_counter() - t1
+                    if diagnostics:
+                        if k not in hist['iterate_average_k_history']:
+                            hist['iterate_average_k_history'].append(k)
+                            hist['iterate_average_history'].append(iterate_average)
+                        hist['ess_and_mcse_k_history'].append(k)
+                        hist['ess_history'].append(ess)
+                        hist['mcse_history'].append(mcse)
+                    if np.max(mcse) < self._mcse_threshold and np.min(ess) > self._ESS_min:
+                        k_stopped = k
+                        break
+                    ratio = (opt_time / max(k, 1)) / (mcse_time / W)
+                    W_check = int(max(1.05, 1 + 1 / np.sqrt(1 + ratio)) * W_check + 1)
+                if progress and k % self._k_check == 0:
+                    recent = eng.value_hist[max(0, k - 1000):k + 1]
+                    bar.set_description('average loss = {:,.5g} | R hat {}|'.format(
+                        float(recent.mean()), 'converged' if k_conv is not None else 'not converged'))
+        except (KeyboardInterrupt, StopIteration):  # pragma: no cover
+            pass
+        finally:
+            bar.close()
+        torch.cuda.current_stream().synchronize()
+        eng.check_comm()
+        sgo._import_state(eng)
+        self._report(k_stopped, k_conv, mcse, ess)
+        results = {'value_history': eng.value_hist[:done].cpu().numpy(),
+                   'grad_history': eng.last_rows(eng.grad_hist, done).cpu().numpy(),
+                   'variational_param_history': eng.last_rows(eng.param_hist, done).cpu().numpy()}
+        if diagnostics:
+            results['descent_dir_history'] = eng.last_rows(eng.dir_hist, done).cpu().numpy()
+        for key, v in hist.items():
+            results[key] = np.array(v)
+        results['k_conv'] = k_conv
+        results['k_Rhat'] = k_Rhat
+        results['k_stopped'] = k_stopped
+        results['opt_param'] = np.asarray(iterate_average)
+        return results
+
+    @staticmethod
+    def _report(k_stopped, k_conv, mcse, ess):
+        if k_stopped is None:
+            if k_conv is None:
+                print('WARNING: stationarity not reached after maximum number of iterations')
+                print('WARNING: try incresing the learning rate or the maximum number of iterations')
+            else:
+                print('WARNING: stationarity reached but MCSE too large and/or ESS too small')
+                if mcse is not None:
+                    print('WARNING: maximum MCSE = {:.3g}'.format(np.max(mcse)))
+                    print('WARNING: minimum ESS = {:.1f}'.format(np.min(ess)))
+        else:
+            print('Convergence reached at iteration', k_stopped)
+
     def optimize(self, n_iters, objective, init_param):
+        from .engine import fused_step_supported
         from .objectives import VariationalObjective
         sgo = self._sgo
+        if (n_iters > 0 and np.ndim(init_param) == 1 and fused_step_supported(objective, sgo)
+                and 3 * n_iters * np.size(init_param) * 8 < 8e9):
+            try:
+                return self._optimize_fused(n_iters, objective, init_param)
+            except NotImplementedError:
+                pass
         diagnostics = sgo._diagnostics
         k_conv = k_stopped = k_Rhat = None
         lr = sgo._learning_rate
@@ -507,16 +634,7 @@ class FASO(Optimizer):
             pass
         finally:
             bar.close()
-        if k_stopped is None:
-            if k_conv is None:
-                print('WARNING: stationarity not reached after maximum number of iterations')
-                print('WARNING: try incresing the learning rate or the maximum number of iterations')
-            else:
-                print('WARNING: stationarity reached but MCSE too large and/or ESS too small')
-                print('WARNING: maximum MCSE = {:.3g}'.format(np.max(mcse)))
-                print('WARNING: minimum ESS = {:.1f}'.format(np.min(ess)))
-        else:
-            print('Convergence reached at iteration', k_stopped)
+        self._report(k_stopped, k_conv, mcse, ess)
         results = _to_numpy_results(hist)
         results['k_conv'] = k_conv
         results['k_Rhat'] = k_Rhat
