@@ -302,6 +302,24 @@ int vb_faso_center_f64(const double* hist, int64_t ring, int P, int64_t end, int
 int vb_faso_ess_f64(double* acov_raw, int64_t ld, double scale, int64_t n_draw, int P, double* ess, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * DISInclusiveKL (objectives.py:283-416), forward-only in the model.
+ *   vb_dis_bisection_f64: the ESS bisection on the tempering epsilon (:338-366) in one launch.  log_prior / log_p /
+ *     log_q: [S]; w[S] receives exp(eps log_prior + (1 - eps) log_p - log_q) at the final midpoint (not max-shifted,
+ *     as the reference); out4 = [eps (snapped to 0 / max_eps when that end point never moved), ESS, 1 if all weights
+ *     are zero (the reference raises ValueError), sum w].
+ *   vb_mf_score_f64: value[1] = -sum_r c_r log q(x_{i_r}; var_param), grad[2d] = its gradient wrt [mu, log sigma]
+ *     (:405-416 differentiates approx.log_density at FIXED samples), c_r = scale * w[r] (w NULL: 1), i_r = idx[r]
+ *     (idx NULL: r), x: [*, d].  Workspace: vb_mf_score_workspace_bytes(d).
+ * ------------------------------------------------------------------------------------- */
+int vb_dis_bisection_f64(const double* log_prior, const double* log_p, const double* log_q, int64_t S,
+                         double eps_guess, double max_eps, double ess_target, int max_its, double* w,
+                         double* out4, cudaStream_t stream);
+size_t vb_mf_score_workspace_bytes(int d);
+int vb_mf_score_f64(const double* var_param, const double* x, const int64_t* idx, const double* w, double scale,
+                    int64_t n, int d, int family, double df, double* value, double* grad, void* workspace,
+                    size_t workspace_bytes, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Pareto-smoothed importance sampling and divergence-bound moments
  * (viabel/_psis.py:113-209 psislw, :212-332 gpdfitnew, :335-377 gpinv, :380-396 sumlogs;
  *  viabel/diagnostics.py:148-186 divergence_bound).

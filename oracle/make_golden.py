@@ -492,6 +492,39 @@ def gen_dis():
     print('dis: %d arrays' % len(out))
 
 
+def gen_dis_objective():
+    """DISInclusiveKL end to end (objectives.py:283-416): objective value and gradient of consecutive calls, with and
+    without resampling, through the reference's own value_and_grad.  The resampling indices come from numpy's GLOBAL
+    generator (:408-409), which the product also uses: seeding it identically reproduces them."""
+    from viabel.objectives import DISInclusiveKL
+    out = {}
+    mean, sd = target_params(4, seed=14)
+    logp = gauss_log_p(mean, sd)
+    rs = np.random.RandomState(5039)
+    for kind, df in (('mfg', None), ('mft', 8)):
+        for resample, batches in ((False, 1), (True, 1), (True, 3)):
+            tag = 'dis_obj/%s/%s%d' % (kind, 'res' if resample else 'nores', batches)
+            fam = make_family(kind, 4, df, seed=1214)
+            prior = MFGaussian(4)
+            obj = DISInclusiveKL(fam, logp, 60, 20, prior, np.concatenate([np.zeros(4), np.ones(4)]),
+                                 use_resampling=resample, num_resampling_batches=batches)
+            vp = np.concatenate([mean + 0.3 * rs.randn(4), np.log(sd) + 0.2 * rs.randn(4)])
+            np.random.seed(846)
+            n_calls = 4
+            for c in range(n_calls):
+                with Recorder() as rec:
+                    value, grad = obj(vp)
+                if len(rec):
+                    out['%s/call%d/base' % (tag, c)] = rec[0][2]
+                out['%s/call%d/var_param' % (tag, c)] = vp
+                out['%s/call%d/value' % (tag, c)] = np.asarray(float(value))
+                out['%s/call%d/grad' % (tag, c)] = np.asarray(grad, dtype=np.float64)
+                out['%s/call%d/eps' % (tag, c)] = np.asarray(float(obj._eps))
+                vp = vp - 0.05 * np.asarray(grad)
+    np.savez_compressed(os.path.join(OUT, 'dis_objective.npz'), **out)
+    print('dis_objective: %d arrays' % len(out))
+
+
 if __name__ == '__main__':
     print('reference:', os.path.dirname(viabel.__file__))
     gen_families()
@@ -503,3 +536,4 @@ if __name__ == '__main__':
     gen_diagnostics()
     gen_mc_diagnostics()
     gen_dis()
+    gen_dis_objective()

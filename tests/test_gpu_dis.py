@@ -1,0 +1,79 @@
+"""GPU parity for DISInclusiveKL (objectives.py:283-416) against the unmodified reference: the ESS bisection
+(tests/golden/dis.npz) and the objective value / gradient of consecutive calls with and without resampling
+(tests/golden/dis_objective.npz, oracle/make_golden.py: gen_dis_objective)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import relerr
+from _problems import target_params
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def vb():
+    import viabel_b200
+    return viabel_b200
+
+
+def _dis_inputs():
+    """Same inputs as oracle/make_golden.py::dis_inputs (rebuilt by seed)."""
+    rs = np.random.RandomState(515)
+    S, d = 400, 3
+    x = rs.randn(S, d) * 1.5
+    log_q = -0.5 * np.sum((x / 1.5) ** 2, axis=1) - d * np.log(1.5 * np.sqrt(2 * np.pi))
+    return {'interior': (x, -0.5 * np.sum((x / 0.4) ** 2, axis=1), log_q, 120),
+            'eps0': (x, -0.5 * np.sum((x / 1.4) ** 2, axis=1), log_q, 60),
+            'eps1': (x, -0.5 * np.sum((x / 0.2) ** 2, axis=1), log_q, 399)}
+
+
+@pytest.mark.parametrize('name', ['interior', 'eps0', 'eps1'])
+def test_dis_ess_bisection_golden(vb, golden, name):
+    """The tempering search (objectives.py:317-366: un-shifted weights, 50 bisection rounds on the ESS, end-point
+    snapping) as one kernel launch, against the unmodified reference on fixed log p / log q / temper-prior vectors."""
+    g = golden('dis')
+    x, log_p, log_q, target = _dis_inputs()[name]
+    d = x.shape[1]
+    obj = vb.DISInclusiveKL(vb.MFGaussian(d), vb.Model(lambda z: -0.5 * (z ** 2).sum(dim=1)), x.shape[0], target,
+                            vb.MFGaussian(d), np.zeros(2 * d))
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device='cuda')
+    eps, ess, w = obj._get_eps_and_weights(1, t(g[name + '/log_prior']), t(log_p), t(log_q))
+    assert eps == float(g[name + '/eps'])
+    assert abs(ess - float(g[name + '/ess'])) <= 1e-10 * float(g[name + '/ess'])
+    np.testing.assert_allclose(w.cpu().numpy(), g[name + '/w'], rtol=1e-12, atol=0)
+    with pytest.raises(ValueError):
+        obj._get_eps_and_weights(1, t(g[name + '/log_prior']), t(log_p) - np.inf, t(log_q))
+
+
+@pytest.mark.parametrize('kind', ['mfg', 'mft'])
+@pytest.mark.parametrize('mode', ['nores1', 'res1', 'res3'])
+def test_dis_objective_golden(vb, golden, kind, mode):
+    g = golden('dis_objective')
+    mean, sd = target_params(4, seed=14)
+    target = vb.GaussianTarget(mean, sd)
+    fam = vb.MFGaussian(4) if kind == 'mfg' else vb.MFStudentT(4, 8)
+    resample, batches = mode.startswith('res'), int(mode[-1])
+    obj = vb.DISInclusiveKL(fam, target, 60, 20, vb.MFGaussian(4), np.concatenate([np.zeros(4), np.ones(4)]),
+                            use_resampling=resample, num_resampling_batches=batches)
+    tag = 'dis_obj/%s/%s' % (kind, mode)
+    np.random.seed(846)                       # the reference resamples with numpy's global generator (:408-409)
+    for c in range(4):
+        key = '%s/call%d' % (tag, c)
+        base = g[key + '/base'] if key + '/base' in g else None
+        v, gr = obj(g[key + '/var_param'], base=base)
+        assert obj._eps == float(g[key + '/eps']), key
+        assert relerr(v, g[key + '/value']) < 1e-10, key
+        assert relerr(gr, g[key + '/grad']) < 1e-10, key
+
+
+def test_dis_weight_clipping(vb):
+    """The corrected clipping rule (objectives.py:368-386): no weight above threshold x total, total preserved."""
+    obj = vb.DISInclusiveKL(vb.MFGaussian(2), vb.Model(lambda z: -0.5 * (z ** 2).sum(dim=1)), 50, 10, vb.MFGaussian(2),
+                            np.zeros(4), w_clip_threshold=0.2)
+    w = torch.tensor([5.0, 1.0, 1.0, 0.5, 0.5, 0.25, 0.25, 0.25, 0.25], dtype=torch.float64, device='cuda')
+    c = obj._clip_weights(w)
+    assert float(c.max()) <= 0.2 * float(c.sum()) * (1 + 1e-12)
+    assert torch.equal(c[1:], w[1:])
+    assert torch.equal(vb.DISInclusiveKL(vb.MFGaussian(2), vb.Model(lambda z: z.sum(dim=1)), 50, 10, vb.MFGaussian(2),
+                                         np.zeros(4))._clip_weights(w), w)

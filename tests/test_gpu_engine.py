@@ -325,14 +325,18 @@ def test_faso_fused_matches_unfused(vb, monkeypatch, capsys):
         faso = vb.FASO(sgo, W_min=100, k_check=100, mcse_threshold=0.2)
         out[fused] = faso.optimize(3000, vb.ExclusiveKL(approx, model, S), approx.init_param())
     a, b = out[True], out[False]
-    assert a['k_Rhat'] == b['k_Rhat'] and a['k_conv'] == b['k_conv'] and a['k_stopped'] == b['k_stopped']
-    assert a['k_conv'] is not None
-    n = len(b['value_history'])
-    assert a['value_history'].shape == (n,) and a['variational_param_history'].shape == b['variational_param_history'].shape
-    assert relerr(a['value_history'], b['value_history']) < 1e-9
-    assert relerr(a['variational_param_history'], b['variational_param_history']) < 1e-9
-    assert relerr(a['grad_history'], b['grad_history']) < 1e-8
-    assert relerr(a['descent_dir_history'], b['descent_dir_history']) < 1e-8
-    assert relerr(a['opt_param'], b['opt_param']) < 1e-9
-    if 'mcse_history' in b and len(b['mcse_history']):
-        assert relerr(a['mcse_history'][-1], b['mcse_history'][-1]) < 1e-6
+    # the R-hat decisions are deterministic; where the MCSE re-checks fall afterwards depends on the measured
+    # optimisation / MCSE time ratio (optimization.py:599-605), so k_stopped may differ between the two loops
+    assert a['k_Rhat'] == b['k_Rhat'] and a['k_conv'] == b['k_conv'] and a['k_conv'] is not None
+    assert a['k_stopped'] is not None and b['k_stopped'] is not None
+    n = min(len(a['value_history']), len(b['value_history']))
+    assert a['variational_param_history'].shape[1:] == b['variational_param_history'].shape[1:]
+    assert relerr(a['value_history'][:n], b['value_history'][:n]) < 1e-9
+    assert relerr(a['variational_param_history'][:n], b['variational_param_history'][:n]) < 1e-9
+    assert relerr(a['grad_history'][:n], b['grad_history'][:n]) < 1e-8
+    assert relerr(a['descent_dir_history'][:n], b['descent_dir_history'][:n]) < 1e-8
+    # the first MCSE check happens at the same iteration over the same window in both loops
+    assert a['ess_and_mcse_k_history'][0] == b['ess_and_mcse_k_history'][0]
+    assert relerr(a['mcse_history'][0], b['mcse_history'][0]) < 1e-6
+    assert relerr(a['ess_history'][0], b['ess_history'][0]) < 1e-6
+    assert relerr(a['iterate_average_history'][1], b['iterate_average_history'][1]) < 1e-9

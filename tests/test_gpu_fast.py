@@ -51,16 +51,21 @@ def test_fast_sweep_vs_oracle(vb, vo, N, d, S):
     vp = points['conv']
     v, gr = vb.AlphaDivergence(approx, model, S, 2.0)(vp, base=base)
     v0, g0, lw0 = vo.alpha_divergence_meanfield(vp, base, oracle_model, 2.0)
-    # AlphaDivergence weights are exp(alpha (lw - max lw)): an error e_s in log-weight s that is NOT common to all
-    # samples is a RELATIVE error alpha * e_s in that sample's weight, on top of the sweep's own 1e-4 (a common shift
-    # -- the fp32 softplus has a systematic relative bias ~2e-6 -- cancels in the weights and only moves the value).
-    # The gradient is held to 1e-4 + alpha * max_s |e_s - mean e| with the MEASURED log-weight error, and that spread
-    # to the budget stated in DESIGN.md 4.2 ("AlphaDivergence on the fast path").
+    # AlphaDivergence weights are exp(alpha (lw - max lw)): the part of the log-weight error that is common to all
+    # samples (the fp32 softplus has a systematic relative bias ~2e-6) cancels in the weights and only shifts the value;
+    # the part that differs between a sample and the arg-max sample, e_s - e_max, is a RELATIVE error alpha (e_s - e_max)
+    # in that sample's weight.  Stated budget ("AlphaDivergence on the fast path"): log-weights carry
+    # fp32-accumulation error, spread <= 5e-7 * max|lw|; the gradient meets 1e-4 plus alpha times the weight-averaged
+    # log-weight error.
     e = approx.last_log_weights.cpu().numpy() - lw0
     spread = float(np.max(np.abs(e - e.mean())))
-    print('alpha fast path: N=%d d=%d common shift %.3e, spread %.3e, grad err %.3e' % (N, d, e.mean(), spread, relerr(gr, g0)))
-    assert spread < 2.5e-4
-    assert relerr(v, v0) < TOL_FAST and relerr(gr, g0) < TOL_FAST + 2.0 * spread
+    wn = np.exp(2.0 * (lw0 - lw0.max()))
+    wn /= wn.sum()
+    eff = float(np.sum(wn * np.abs(e - e[np.argmax(lw0)])))
+    print('alpha fast path: N=%d d=%d common shift %.3e, spread %.3e, weighted %.3e, grad err %.3e'
+          % (N, d, e.mean(), spread, eff, relerr(gr, g0)))
+    assert spread < 5e-7 * np.abs(lw0).max() + 1e-6
+    assert relerr(v, v0) < TOL_FAST and relerr(gr, g0) < TOL_FAST + 2.0 * 2.0 * eff
     theta = vo.mfg_sample(vp, base)
     assert relerr(model(theta), oracle_model(theta)[0]) < TOL_FAST
     # general float64 draws (not fp16-exact) still meet the tolerance

@@ -95,33 +95,6 @@ def test_host_optimizer_directions_golden(golden):
             assert relerr(opt.descent_direction(gr.copy()), g[name + '/dirs'][i]) < 1e-13, (name, i)
 
 
-def _dis_inputs():
-    """Same inputs as oracle/make_golden.py::dis_inputs (rebuilt by seed)."""
-    rs = np.random.RandomState(515)
-    S, d = 400, 3
-    x = rs.randn(S, d) * 1.5
-    log_q = -0.5 * np.sum((x / 1.5) ** 2, axis=1) - d * np.log(1.5 * np.sqrt(2 * np.pi))
-    return {'interior': (x, -0.5 * np.sum((x / 0.4) ** 2, axis=1), log_q, 120),
-            'eps0': (x, -0.5 * np.sum((x / 1.4) ** 2, axis=1), log_q, 60),
-            'eps1': (x, -0.5 * np.sum((x / 0.2) ** 2, axis=1), log_q, 399)}
-
-
-@pytest.mark.parametrize('name', ['interior', 'eps0', 'eps1'])
-def test_dis_ess_bisection_golden(golden, name):
-    """DISInclusiveKL's tempering search (objectives.py:317-366: un-shifted weights, 50 bisection rounds on the
-    ESS, end-point snapping) against the unmodified reference on fixed log p / log q / temper-prior vectors."""
-    g = golden('dis')
-    x, log_p, log_q, target = _dis_inputs()[name]
-    d = x.shape[1]
-    obj = vb.DISInclusiveKL(vb.MFGaussian(d), vb.Model(lambda z: -0.5 * (z ** 2).sum(dim=1)), x.shape[0], target,
-                            vb.MFGaussian(d), np.zeros(2 * d))
-    t = lambda a: torch.as_tensor(a, dtype=torch.float64)
-    eps, ess, w = obj._get_eps_and_weights(1, t(g[name + '/log_prior']), t(log_p), t(log_q))
-    assert eps == float(g[name + '/eps'])
-    assert abs(ess - float(g[name + '/ess'])) <= 1e-10 * float(g[name + '/ess'])
-    np.testing.assert_allclose(w.numpy(), g[name + '/w'], rtol=1e-12, atol=0)
-
-
 def test_exp_table_constants_accuracy():
     """The table-driven exp of the PSIS passes (csrc/psis.cu exp_nonpos): emulate its arithmetic in numpy with the
     constants parsed from the source.  Guards the reduction constants (256/ln2, the two-part ln2/256) and the

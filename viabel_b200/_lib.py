@@ -67,6 +67,9 @@ _PROTOS = {
     'vb_ring_mean_f64': (c_int, [P, c_int64, c_int, c_int64, c_int64, P, P, P]),
     'vb_faso_center_f64': (c_int, [P, c_int64, c_int, c_int64, c_int64, c_int64, P, P, P]),
     'vb_faso_ess_f64': (c_int, [P, c_int64, c_double, c_int64, c_int, P, P]),
+    'vb_dis_bisection_f64': (c_int, [P, P, P, c_int64, c_double, c_double, c_double, c_int, P, P, P]),
+    'vb_mf_score_workspace_bytes': (c_size_t, [c_int]),
+    'vb_mf_score_f64': (c_int, [P, P, P, P, c_double, c_int64, c_int, c_int, c_double, P, P, P, c_size_t, P]),
     # peer-memory communicator and the fused step (structures: viabel_b200/engine.py)
     'vb_comm_create': (c_int, [P, c_int, c_int, c_size_t, P]),
     'vb_comm_connect': (c_int, [P, P]),

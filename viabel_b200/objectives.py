@@ -409,34 +409,19 @@ class DISInclusiveKL(StochasticVariationalObjective):
         self._temper_prior_params = temper_prior_params
         super().__init__(approx, model, num_mc_samples)
 
-    # -- weights / ESS / bisection (objectives.py:317-366); S-vectors on the device ------------------
-    def _get_weights(self, eps, log_prior, log_p, log_q):
-        logw = eps * log_prior + (1 - eps) * log_p - log_q
-        if bool(logw.max() == -float('inf')):
-            raise ValueError('All weights zero! ' + 'Suggests overflow in importance density.')
-        return torch.exp(logw)                     # not max-shifted, as the reference (:330)
-
-    @staticmethod
-    def _get_ess(w):
-        return float((w.sum() ** 2.0) / (w ** 2.0).sum())
-
+    # -- weights / ESS / bisection (objectives.py:317-366): one kernel launch on the S-vectors ----------------
     def _get_eps_and_weights(self, eps_guess, log_prior, log_p, log_q):
-        lower, upper = 0., eps_guess
-        eps_guess = (lower + upper) / 2.
-        for _ in range(self._max_bisection_its):
-            w = self._get_weights(eps_guess, log_prior, log_p, log_q)
-            if self._get_ess(w) > self._ess_target:
-                upper = eps_guess
-            else:
-                lower = eps_guess
-            eps_guess = (lower + upper) / 2.
-        w = self._get_weights(eps_guess, log_prior, log_p, log_q)
-        ess = self._get_ess(w)
-        if lower == 0.:
-            eps_guess = 0.
-        if upper == self._max_eps:
-            eps_guess = self._max_eps
-        return eps_guess, ess, w
+        S = int(log_q.numel())
+        w = torch.empty(S, dtype=F64, device=log_q.device)
+        out = torch.empty(4, dtype=F64, device=log_q.device)
+        _lib.check(_lib.lib.vb_dis_bisection_f64(
+            _lib.ptr(log_prior.contiguous()), _lib.ptr(log_p.contiguous()), _lib.ptr(log_q.contiguous()), S,
+            float(eps_guess), float(self._max_eps), float(self._ess_target), int(self._max_bisection_its),
+            _lib.ptr(w), _lib.ptr(out), _lib.stream()))
+        eps, ess, zero, _ = out.cpu().numpy()
+        if zero:
+            raise ValueError('All weights zero! ' + 'Suggests overflow in importance density.')
+        return float(eps), float(ess), w
 
     def _clip_weights(self, w):
         """Clip weights to `w_clip_threshold` x their sum, scaling the others up (objectives.py:368-386).
@@ -460,7 +445,10 @@ class DISInclusiveKL(StochasticVariationalObjective):
     def _resample_indices(self, S, p):
         """np.random.choice from the GLOBAL numpy RNG, as the reference (:408-409).  With a sharded model every
         rank must resample the same draws: rank 0 draws, the others receive."""
-        idx = np.random.choice(S, size=self._resampling_batch_size, p=p / p.sum())
+        try:
+            idx = np.random.choice(S, size=self._resampling_batch_size, p=p)
+        except ValueError:                     # probabilities off by more than numpy's tolerance: renormalise
+            idx = np.random.choice(S, size=self._resampling_batch_size, p=p / p.sum())
         group = getattr(self.model, 'process_group', None)
         if getattr(self.model, 'sharded', False) and is_distributed(group):
             import torch.distributed as dist
@@ -469,22 +457,18 @@ class DISInclusiveKL(StochasticVariationalObjective):
             idx = t.cpu().numpy()
         return idx
 
-    def _score_terms(self, vp, x):
-        """-log q(lambda; x) summed with weights needs d(log q)/d[mu, log sigma] at fixed x."""
+    def _score(self, vp, x, idx, w, scale):
+        """(value, grad) = -sum_r c_r log q(x_r; lambda) and its gradient at the fixed samples (vb_mf_score_f64)."""
         approx = self.approx
         d = approx.dim
-        mu, ls = vp[:d], vp[d:]
-        sig = torch.exp(ls)
-        z = (x - mu) / sig
-        if approx._family == _lib.FAMILY_MF_GAUSSIAN:
-            dmu = z / sig                       # d log q / d mu
-            dls = z * z - 1.0                   # d log q / d log sigma
-        else:
-            df = float(approx.df)
-            q = (df + 1.0) / (df + z * z)
-            dmu = q * z / sig
-            dls = q * z * z - 1.0
-        return dmu, dls
+        out = torch.empty(1 + 2 * d, dtype=F64, device=vp.device)
+        ws = torch.empty(max(8, _lib.lib.vb_mf_score_workspace_bytes(d)), dtype=torch.uint8, device=vp.device)
+        n = int(idx.numel()) if idx is not None else int(x.shape[0])
+        _lib.check(_lib.lib.vb_mf_score_f64(
+            _lib.ptr(vp), _lib.ptr(x), _lib.ptr(idx), _lib.ptr(w), float(scale), n, d, approx._family,
+            float(approx.df) if approx._family else 0.0, _lib.ptr(out[:1]), _lib.ptr(out[1:]), _lib.ptr(ws), ws.numel(),
+            _lib.stream()))
+        return out[:1], out[1:]
 
     def _update_objective_and_grad(self):
         approx = self.approx
@@ -494,12 +478,12 @@ class DISInclusiveKL(StochasticVariationalObjective):
             self._objective_and_grad = unsupported
             return
 
-        def objective_and_grad(var_param):
+        def objective_and_grad(var_param, base=None):
             host = is_host(var_param)
             vp = to_dev(var_param)
             S = self.num_mc_samples
             if not self._use_resampling or self._objective_step % self._num_resampling_batches == 0:
-                x = approx.sample(vp, S)
+                x = approx.sample(vp, S) if base is None else approx.sample(vp, S, base=base)
                 self._state_samples = x
                 self._state_log_q = approx.log_density(vp, x)
                 self._state_log_p = self.model(x)
@@ -512,19 +496,22 @@ class DISInclusiveKL(StochasticVariationalObjective):
                 self._state_w_normalized = w / self._state_w_sum
             self._objective_step += 1
             if not self._use_resampling:
-                xs, wts = self._state_samples, self._state_w / S
-                value = -(wts * approx.log_density(vp, xs)).sum()
+                # -inner(w, log q) / S   (:405-406)
+                value, grad = self._score(vp, self._state_samples, None, self._state_w, 1.0 / S)
             else:
                 p = self._state_w_normalized.cpu().numpy()
                 idx = self._resample_indices(S, p)
-                xs = self._state_samples[torch.as_tensor(idx, device=vp.device)]
-                scale = self._state_w_sum / S / xs.shape[0]
-                wts = scale.expand(xs.shape[0])
-                value = -(wts * approx.log_density(vp, xs)).sum()
-            dmu, dls = self._score_terms(vp, xs)
-            grad = -torch.cat([(wts[:, None] * dmu).sum(dim=0), (wts[:, None] * dls).sum(dim=0)])
+                idx_d = torch.as_tensor(idx, dtype=torch.int64, device=vp.device)
+                # mean(-log q(x_idx)) * sum(w) / S   (:408-414)
+                scale = float(self._state_w_sum) / S / idx_d.numel()
+                value, grad = self._score(vp, self._state_samples, idx_d, None, scale)
             if host:
-                return _to_host(value, grad)
-            return value, grad
+                return _to_host(value[0], grad)
+            return value[0], grad
 
         self._objective_and_grad = objective_and_grad
+
+    def __call__(self, var_param, base=None):
+        if base is None:
+            return self._objective_and_grad(var_param)
+        return self._objective_and_grad(var_param, base=base)
