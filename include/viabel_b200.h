@@ -320,6 +320,18 @@ int vb_mf_score_f64(const double* var_param, const double* x, const int64_t* idx
                     size_t workspace_bytes, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Streaming log-weights for vi_diagnostics (convenience.py:136-179 samples_and_log_weights): for a mean-field
+ * family and a product target (target_kind 0: sum_j N(theta_j; loc_j, scale_j), 1: sum_j t_{target_df}(theta_j;
+ * loc_j, scale_j)) one kernel regenerates draw i = elements offset + i*d .. + d-1 of the family's Philox stream,
+ * reparameterises and writes lw[i] = log p(theta_i) - log q(theta_i).  theta_out (optional, [n,d]) also stores the
+ * samples; leave it NULL at scale (n = 1e8, d = 256 would be 204.8 GB).
+ * ------------------------------------------------------------------------------------- */
+int vb_mf_target_log_weights_f64(const double* var_param, int64_t n, int d, int family, double df, uint64_t seed,
+                                 uint64_t offset, int quantize, int target_kind, const double* target_loc,
+                                 const double* target_scale, double target_df, double* lw, double* theta_out,
+                                 cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Pareto-smoothed importance sampling and divergence-bound moments
  * (viabel/_psis.py:113-209 psislw, :212-332 gpdfitnew, :335-377 gpinv, :380-396 sumlogs;
  *  viabel/diagnostics.py:148-186 divergence_bound).

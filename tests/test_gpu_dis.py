@@ -62,7 +62,10 @@ def test_dis_objective_golden(vb, golden, kind, mode):
         key = '%s/call%d' % (tag, c)
         base = g[key + '/base'] if key + '/base' in g else None
         v, gr = obj(g[key + '/var_param'], base=base)
-        assert obj._eps == float(g[key + '/eps']), key
+        eps_ref = float(g[key + '/eps'])
+        # end-point snaps (0 or 1) are exact; an interior epsilon is the limit of 50 halvings whose late comparisons
+        # see ESS values that differ in the last bits between numpy's and the kernel's summation order
+        assert obj._eps == eps_ref if eps_ref in (0.0, 1.0) else abs(obj._eps - eps_ref) < 1e-12, key
         assert relerr(v, g[key + '/value']) < 1e-10, key
         assert relerr(gr, g[key + '/grad']) < 1e-10, key
 

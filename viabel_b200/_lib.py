@@ -70,6 +70,8 @@ _PROTOS = {
     'vb_dis_bisection_f64': (c_int, [P, P, P, c_int64, c_double, c_double, c_double, c_int, P, P, P]),
     'vb_mf_score_workspace_bytes': (c_size_t, [c_int]),
     'vb_mf_score_f64': (c_int, [P, P, P, P, c_double, c_int64, c_int, c_int, c_double, P, P, P, c_size_t, P]),
+    'vb_mf_target_log_weights_f64': (c_int, [P, c_int64, c_int, c_int, c_double, c_uint64, c_uint64, c_int, c_int, P, P,
+                                             c_double, P, P, P]),
     # peer-memory communicator and the fused step (structures: viabel_b200/engine.py)
     'vb_comm_create': (c_int, [P, c_int, c_int, c_size_t, P]),
     'vb_comm_connect': (c_int, [P, P]),
