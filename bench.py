@@ -364,6 +364,39 @@ def bench_psis_sharded(torch, dist, vb, args, rank, world, dev):
                          'algorithmic_bytes_per_draw': 24}}
 
 
+def bench_c5(torch, dist, vb, args, rank, world):
+    """BASELINE configs[4] END TO END: vi_diagnostics on n = 1e8 draws from a d = 256 Student-t target (df = 10) under
+    a mean-field Student-t proposal (df = 40): draw -> log p - log q (fused, streamed: samples[n,d] would be 204.8 GB)
+    -> draw-sharded PSIS -> 2-divergence / Wasserstein / error bounds.  ALU bound in the draw stage (2.56e10 Student-t
+    variates), so no HBM roofline claim: draws/s and the stage split are reported."""
+    import contextlib
+    import io
+    d, n = 256, args.psis_draws
+    rs = np.random.RandomState(20260119)
+    loc, scale = rs.randn(d), np.exp(0.25 * rs.randn(d))
+    vp = np.concatenate([loc + 0.05 * rs.randn(d), np.log(scale) + 0.02 * rs.randn(d)])
+    model = vb.StudentTTarget(loc, scale, 10.0)
+    approx = vb.MFStudentT(d, 40, seed=DRAW_SEED)
+    small = min(n, 2000000)
+    with contextlib.redirect_stdout(io.StringIO()):
+        vb.vi_diagnostics(vp, model=model, approx=approx, n_samples=small, keep_samples=False)      # warm-up
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rep = vb.vi_diagnostics(vp, model=model, approx=approx, n_samples=n, keep_samples=False)
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([sec], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    return {'metric': 'vi_diagnostics_draws_per_sec', 'value': n / sec, 'unit': 'draws/s', 'n_draws': n, 'dim': d,
+            'seconds': sec, 'khat': float(rep['khat']), 'd2': float(rep.get('d2', float('nan'))),
+            'W2': float(rep.get('W2', float('nan'))), 'variates_per_sec': n * d / sec,
+            'note': 'streamed (no samples[n,d]); draws sharded over %d rank(s); wall clock incl. the host read-backs' % world}
+
+
 def time_steps(torch, eng, steps, use_graph):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -474,13 +507,14 @@ def run_b200(args):
     torch.cuda.synchronize()
     sweep_sec = k0.elapsed_time(k1) * 1e-3 / reps
 
-    psis = None
+    psis = c5 = None
     if not args.no_psis:
         del eng
         if world > 1:
             psis = bench_psis_sharded(torch, dist, vb, args, rank, world, dev)
         elif rank == 0:
             psis = bench_psis(torch, vb, args)
+        c5 = bench_c5(torch, dist, vb, args, rank, world)
 
     if rank != 0:
         if world > 1:
@@ -564,6 +598,7 @@ def run_b200(args):
         'f64': f64_leg,
         'cpu_baseline': cpu_baseline,
         'psis': psis,
+        'c5_vi_diagnostics': c5,
     }
     print(json.dumps(line))
     if world > 1:

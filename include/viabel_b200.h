@@ -332,6 +332,54 @@ int vb_mf_target_log_weights_f64(const double* var_param, int64_t n, int d, int 
                                  cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Float64 GEMM on the FP64 tensor pipe with fused scalings (the building block of the full-rank path):
+ *   C[m,n] = ( alpha * sum_k A'(m,k) kscale[k] B'(k,n) ) * rowscale[m] / (divm[m] + divn[n]) + bias[n]
+ *   A'(m,k) = trans_a ? A[k*lda + m] : A[m*lda + k];  B'(k,n) = trans_b ? B[n*ldb + k] : B[k*ldb + n];
+ *   kscale / rowscale / bias / (divm, divn) are optional (NULL).
+ * ------------------------------------------------------------------------------------- */
+int vb_gemm_f64(int trans_a, int trans_b, int M, int N, int K, double alpha, const double* A, int64_t lda,
+                const double* B, int64_t ldb, double* C, int64_t ldc, const double* kscale, const double* rowscale,
+                const double* bias, const double* divm, const double* divn, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Full-rank MultivariateT (approximations.py:322-382, _distributions.py:7-38) and its objectives
+ * (objectives.py:154-164, :443-460).  var_param = [mu(d), row-major lower triangle of F], L = tril(F,-1) +
+ * diag(exp(diag F)), Sigma = L L^T.  The caller eigen-decomposes Sigma = V diag(w) V^T (cuSOLVER) between
+ * vb_mvt_sigma_f64 and the rest; V is row-major with eigenvectors in its COLUMNS.
+ *   vb_mvt_unpack_f64     L[d,d], half_logdet[1] = sum_i F_ii (= the entropy up to df-only constants, :351-354)
+ *   vb_mvt_sigma_f64      Sigma = scale * L L^T                                   (mean_and_cov :359-362 uses df/(df-2))
+ *   vb_mvt_transform_f64  P = (z / u) V, theta = mu + (P . sqrt(w)) V^T = mu + (z / u) sqrtm(Sigma), zu2[s] = |z_s/u_s|^2,
+ *                         u_s = sqrt(chi2_s / df)                                 (sample :342-349)
+ *   vb_mvt_objective_f64  value[1], grad[d + d(d+1)/2] of ExclusiveKL (entropy form) / AlphaDivergence from the
+ *                         model's f[S], G[S,d] at theta: the sqrtm / Cholesky-parameter VJPs as five GEMMs
+ *   vb_mvt_log_density_f64  multivariate_t_logpdf with the 1e-10 eigenvalue floor of the pseudo-inverse (:26-30)
+ * ------------------------------------------------------------------------------------- */
+int vb_mvt_unpack_f64(const double* var_param, int d, double* L, double* half_logdet, cudaStream_t stream);
+int vb_mvt_sigma_f64(const double* L, int d, double scale, double* Sigma, cudaStream_t stream);
+size_t vb_mvt_transform_workspace_bytes(int S, int d);
+int vb_mvt_transform_f64(const double* var_param, const double* z, const double* chi2, double df, int S, int d,
+                         const double* w, const double* V, double* P, double* theta, double* zu2, void* workspace,
+                         size_t workspace_bytes, cudaStream_t stream);
+size_t vb_mvt_objective_workspace_bytes(int S, int d);
+int vb_mvt_objective_f64(const double* L, const double* half_logdet, const double* w, const double* V,
+                         const double* P, const double* zu2, const double* f, const double* G, int S, int d,
+                         double df, int objective, double alpha, double* value, double* grad, void* workspace,
+                         size_t workspace_bytes, cudaStream_t stream);
+size_t vb_mvt_log_density_workspace_bytes(int64_t n, int d);
+int vb_mvt_log_density_f64(const double* var_param, const double* w, const double* V, const double* x, int64_t n, int d,
+                           double df, double* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Hierarchical linear regression plugin (BASELINE configs[3]) with per-sample gradients: a grouped contraction
+ * (no block-expanded design matrix).  X[N,p], y[N] sorted by group; goff[G+1] device int64 row offsets;
+ * theta[S,D], D = G p + p + 2 = [beta (group-major), m, log tau, log sigma]; p <= 32.
+ * ------------------------------------------------------------------------------------- */
+size_t vb_hier_workspace_bytes(int G, int S);
+int vb_hier_logp_grad_f64(const double* X, const double* y, const int64_t* goff, int64_t N, int p, int G,
+                          const double* theta, int S, double* out_lp, double* out_grad, void* workspace,
+                          size_t workspace_bytes, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Pareto-smoothed importance sampling and divergence-bound moments
  * (viabel/_psis.py:113-209 psislw, :212-332 gpdfitnew, :335-377 gpinv, :380-396 sumlogs;
  *  viabel/diagnostics.py:148-186 divergence_bound).

@@ -72,6 +72,17 @@ _PROTOS = {
     'vb_mf_score_f64': (c_int, [P, P, P, P, c_double, c_int64, c_int, c_int, c_double, P, P, P, c_size_t, P]),
     'vb_mf_target_log_weights_f64': (c_int, [P, c_int64, c_int, c_int, c_double, c_uint64, c_uint64, c_int, c_int, P, P,
                                              c_double, P, P, P]),
+    'vb_gemm_f64': (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, P, c_int64, P, c_int64, P, c_int64, P, P, P, P, P, P]),
+    'vb_mvt_unpack_f64': (c_int, [P, c_int, P, P, P]),
+    'vb_mvt_sigma_f64': (c_int, [P, c_int, c_double, P, P]),
+    'vb_mvt_transform_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'vb_mvt_transform_f64': (c_int, [P, P, P, c_double, c_int, c_int, P, P, P, P, P, P, c_size_t, P]),
+    'vb_mvt_objective_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'vb_mvt_objective_f64': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_double, c_int, c_double, P, P, P, c_size_t, P]),
+    'vb_mvt_log_density_workspace_bytes': (c_size_t, [c_int64, c_int]),
+    'vb_mvt_log_density_f64': (c_int, [P, P, P, P, c_int64, c_int, c_double, P, P, c_size_t, P]),
+    'vb_hier_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'vb_hier_logp_grad_f64': (c_int, [P, P, P, c_int64, c_int, c_int, P, c_int, P, P, P, c_size_t, P]),
     # peer-memory communicator and the fused step (structures: viabel_b200/engine.py)
     'vb_comm_create': (c_int, [P, c_int, c_int, c_size_t, P]),
     'vb_comm_connect': (c_int, [P, P]),

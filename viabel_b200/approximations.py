@@ -236,10 +236,13 @@ class MultivariateT(ApproximationFamily):
 
     var_param = [mu(d), row-major lower triangle of F] with L = tril(F,-1) + diag(exp(diag F)) and
     Sigma = L L^T (paragami PSDSymmetricMatrixPattern, approximations.py:315-319).  Samples use the
-    SYMMETRIC square root of Sigma, as the reference does (:348).  The d x d algebra (eigh, GEMMs)
-    is replicated on every rank and runs in cuSOLVER / cuBLAS through torch; the base draws and the
-    O(n d) reductions are this package's kernels.  Entropy is sum(log L_ii) -- the reference's
-    0.5*log(det(Sigma)) (:354) overflows for large d but is the same number."""
+    SYMMETRIC square root of Sigma, as the reference does (:348).  The d x d algebra is replicated on every rank.
+    Entropy is sum(log L_ii) -- the reference's 0.5*log(det(Sigma)) (:354) overflows for large d but is
+    the same number.
+
+    Device path (csrc/mvt.cu + csrc/gemm_f64.cu): the Cholesky-vector unpack, Sigma = L L^T, the reparameterisation
+    through the eigenbasis and every cotangent GEMM are this package's float64 tensor-core kernels; the symmetric
+    eigen-decomposition is the one library call (cuSOLVER via torch.linalg.eigh)."""
 
     def __init__(self, dim, df, seed=1):
         if df <= 2:
@@ -248,7 +251,6 @@ class MultivariateT(ApproximationFamily):
         self._seed = int(seed)
         self._offset = 0
         self.last_base = None
-        self._tril = None
         super().__init__(dim, dim + dim * (dim + 1) // 2, True, False)
 
     @property
@@ -262,45 +264,55 @@ class MultivariateT(ApproximationFamily):
         F[np.diag_indices(d)] = 0.5 * np.log(10.0)
         return np.concatenate([np.zeros(d), F[np.tril_indices(d)]])
 
-    # -- parameter unpacking on the device ---------------------------------------------------------
-    def _tril_idx(self, dev):
-        if self._tril is None or self._tril[0].device != dev:
-            r, c = np.tril_indices(self.dim)
-            self._tril = (torch.as_tensor(r, device=dev), torch.as_tensor(c, device=dev))
-        return self._tril
-
+    # -- device pieces (csrc/mvt.cu) ------------------------------------------------------------------
     def unpack(self, vp):
-        """(mu[d], F[d,d], L[d,d]) as CUDA tensors."""
+        """(mu[d] view, L[d,d], half_logdet[1] = sum_i F_ii) as CUDA tensors (vb_mvt_unpack_f64)."""
         d = self.dim
         if vp.numel() != self.var_param_dim:
             raise ValueError('var_param has the wrong length')
-        r, c = self._tril_idx(vp.device)
-        F = torch.zeros(d, d, dtype=F64, device=vp.device)
-        F[r, c] = vp[d:]
-        L = torch.tril(F, -1) + torch.diag(torch.exp(torch.diagonal(F)))
-        return vp[:d], F, L
+        L = torch.empty(d, d, dtype=F64, device=vp.device)
+        hl = torch.empty(1, dtype=F64, device=vp.device)
+        _lib.check(_lib.lib.vb_mvt_unpack_f64(_lib.ptr(vp), d, _lib.ptr(L), _lib.ptr(hl), _lib.stream()))
+        return vp[:d], L, hl
 
-    def pack_grad(self, gmu, Fbar):
-        r, c = self._tril_idx(Fbar.device)
-        return torch.cat([gmu, Fbar[r, c]])
+    def sigma(self, L, scale=1.0):
+        """scale * L L^T through the float64 tensor-core GEMM."""
+        d = self.dim
+        Sigma = torch.empty(d, d, dtype=F64, device=L.device)
+        _lib.check(_lib.lib.vb_mvt_sigma_f64(_lib.ptr(L), d, float(scale), _lib.ptr(Sigma), _lib.stream()))
+        return Sigma
 
     @staticmethod
     def _eigh(Sigma):
-        """Symmetric eigendecomposition on the device.  cuSOLVER's divide-and-conquer can refuse a large
-        matrix whose eigenvalues are all equal (e.g. the reference's init Sigma = 10 I at d = 2048); the
-        degeneracy is then broken by a relative 1e-13 ramp on the diagonal, far below the 1e-10 tolerance."""
+        """Symmetric eigendecomposition on the device -- the ONE library call of this path (cuSOLVER through
+        torch.linalg.eigh).  cuSOLVER's divide-and-conquer can refuse a large matrix whose eigenvalues are all equal
+        (e.g. the reference's init Sigma = 10 I at d = 2048); the degeneracy is then broken by a relative 1e-13 ramp on
+        the diagonal, far below the 1e-10 tolerance.  Returns (w, V) with V contiguous, eigenvectors in columns."""
         try:
-            return torch.linalg.eigh(Sigma)
+            w, V = torch.linalg.eigh(Sigma)
         except torch.linalg.LinAlgError:
             d = Sigma.shape[0]
             ramp = torch.arange(d, dtype=Sigma.dtype, device=Sigma.device) / d
-            return torch.linalg.eigh(Sigma + torch.diag(1e-13 * torch.diagonal(Sigma).abs().mean() * ramp))
+            w, V = torch.linalg.eigh(Sigma + torch.diag(1e-13 * torch.diagonal(Sigma).abs().mean() * ramp))
+        return w.contiguous(), V.contiguous()
 
-    @classmethod
-    def sym_sqrt(cls, Sigma):
-        """(A, w, V) with A = V diag(sqrt w) V^T, the PSD square root scipy.linalg.sqrtm returns."""
-        w, V = cls._eigh(Sigma)
-        return (V * torch.sqrt(torch.clamp(w, min=0.0))) @ V.T, w, V
+    def decompose(self, vp):
+        """(L, half_logdet, w, V) of var_param: unpack -> Sigma = L L^T -> eigh."""
+        _, L, hl = self.unpack(vp)
+        w, V = self._eigh(self.sigma(L))
+        return L, hl, w, V
+
+    def transform(self, vp, chi2, z, w, V):
+        """(theta[S,d], P[S,d], zu2[S]): theta = mu + (z / u) sqrtm(Sigma) without forming the square root."""
+        S, d = int(z.shape[0]), self.dim
+        P = torch.empty(S, d, dtype=F64, device=z.device)
+        theta = torch.empty(S, d, dtype=F64, device=z.device)
+        zu2 = torch.empty(S, dtype=F64, device=z.device)
+        ws = torch.empty(_lib.lib.vb_mvt_transform_workspace_bytes(S, d), dtype=torch.uint8, device=z.device)
+        _lib.check(_lib.lib.vb_mvt_transform_f64(_lib.ptr(vp), _lib.ptr(z), _lib.ptr(chi2), float(self._df), S, d, _lib.ptr(w),
+                                                 _lib.ptr(V), _lib.ptr(P), _lib.ptr(theta), _lib.ptr(zu2), _lib.ptr(ws),
+                                                 ws.numel(), _lib.stream()))
+        return theta, P, zu2
 
     # -- base draws: chi-square FIRST, then normals, as the reference (:345-347) -------------------
     def base_draws(self, n_samples, seed=None):
@@ -319,11 +331,10 @@ class MultivariateT(ApproximationFamily):
     def sample(self, var_param, n_samples, seed=None, base=None):
         host = is_host(var_param)
         vp = to_dev(var_param)
-        mu, _, L = self.unpack(vp)
-        chi2, z = self.base_draws(n_samples, seed) if base is None else (to_dev(base[0]), to_dev(base[1]))
+        chi2, z = self.base_draws(n_samples, seed) if base is None else (to_dev(base[0]).reshape(-1), to_dev(base[1]))
         self.last_base = (chi2, z)
-        A, _, _ = self.sym_sqrt(L @ L.T)
-        theta = mu + (z @ A) / torch.sqrt(chi2 / self._df)[:, None]
+        _, _, w, V = self.decompose(vp)
+        theta, _, _ = self.transform(vp, chi2, z, w, V)
         return like_input(theta, host)
 
     def entropy(self, var_param):
@@ -337,15 +348,14 @@ class MultivariateT(ApproximationFamily):
         """multivariate_t_logpdf (_distributions.py:7-38) on CUDA tensors: eigen-decomposition of Sigma,
         eigenvalues <= 1e-10 get a zero inverse but still enter the log pseudo-determinant."""
         d = self.dim
-        df = float(self._df)
-        mu, _, L = self.unpack(vp)
-        w, V = self._eigh(L @ L.T)
-        winv = torch.where(w.abs() <= 1e-10, torch.zeros_like(w), 1.0 / w)
-        U = V * torch.sqrt(winv)
-        maha = (((x - mu) @ U) ** 2).sum(dim=-1)
-        const = (torch.lgamma(torch.tensor(0.5 * (df + d), dtype=F64)) - torch.lgamma(torch.tensor(0.5 * df, dtype=F64))
-                 - 0.5 * d * np.log(np.pi * df)).item()
-        return const - 0.5 * torch.log(w).sum() - 0.5 * (df + d) * torch.log(1.0 + maha / df)
+        _, _, w, V = self.decompose(vp)
+        x = x.contiguous()
+        n = int(x.shape[0])
+        out = torch.empty(n, dtype=F64, device=x.device)
+        ws = torch.empty(_lib.lib.vb_mvt_log_density_workspace_bytes(n, d), dtype=torch.uint8, device=x.device)
+        _lib.check(_lib.lib.vb_mvt_log_density_f64(_lib.ptr(vp), _lib.ptr(w), _lib.ptr(V), _lib.ptr(x), n, d, float(self._df),
+                                                   _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream()))
+        return out
 
     def log_density(self, var_param, x):
         host = is_host(x)
@@ -356,20 +366,23 @@ class MultivariateT(ApproximationFamily):
 
     def mean_and_cov(self, var_param):
         vp = to_dev(var_param)
-        mu, _, L = self.unpack(vp)
+        mu, L, _ = self.unpack(vp)
         df = self._df
-        return mu.cpu().numpy().copy(), (df / (df - 2.) * (L @ L.T)).cpu().numpy()
+        return mu.cpu().numpy().copy(), self.sigma(L, df / (df - 2.)).cpu().numpy()
 
     def _pth_moment(self, var_param, p):
+        # sums of powers of the eigenvalues of Sigma are traces (approximations.py:364-374 calls eigvalsh):
+        # sum lambda = |L|_F^2, sum lambda^2 = |Sigma|_F^2
         df = self._df
         if df <= p:
             raise ValueError('df must be greater than p')
-        _, _, L = self.unpack(to_dev(var_param))
-        sq = torch.linalg.eigvalsh(L @ L.T).cpu().numpy()
+        _, L, _ = self.unpack(to_dev(var_param))
         c = df / (df - 2)
+        tr = float((L * L).sum())
         if p == 2:
-            return c * np.sum(sq)
-        return c ** 2 * (2 * (df - 1) / (df - 4) * np.sum(sq ** 2) + np.sum(sq) ** 2)
+            return c * tr
+        Sigma = self.sigma(L)
+        return c ** 2 * (2 * (df - 1) / (df - 4) * float((Sigma * Sigma).sum()) + tr ** 2)
 
     def supports_pth_moment(self, p):
         return p in [2, 4] and p < self._df

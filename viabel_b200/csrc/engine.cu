@@ -356,74 +356,52 @@ __global__ void __launch_bounds__(32 * kPostGroups) mf_post_kernel(StepCfg c, St
   }
   const unsigned long long step = p.counters[0];
   const double invS = 1.0 / (double)S;
-  // value (objectives.py:161-164): -(mean_s f(theta_s) + H), or -(mean_s (f - log q)) for the path-derivative form
-  {
-    double a = 0.0, b = 0.0, h = 0.0;
-    for (int s = threadIdx.x; s < S; s += blockDim.x) {
-      double sq = 0.0, lq = 0.0;
-      for (int k = 0; k < c.chunks; ++k) {
-        sq += __ldcg(p.sq_part + s * c.chunks + k);
-        if (path) lq += __ldcg(p.lq_part + s * c.chunks + k);
-      }
-      const double f = __ldcg(p.vec + s) + (-0.5 * sq * c.inv_tau2 + c.prior_const);
-      if (p.logp) p.logp[s] = f;
-      a += f;
-      b += lq;
-    }
-    if (!path)
-      for (int j = threadIdx.x; j < d; j += blockDim.x) h += p.vp[d + j];
-    a = block_sum(a, red);
-    b = block_sum(b, red);
-    h = block_sum(h, red);
-    if (!path && c.family == VB_FAMILY_MF_GAUSSIAN) h += 0.5 * d * (1.0 + kLog2Pi);     // approximations.py:218-220
-    const double v = path ? -((a - b) * invS) : -(a * invS + h);
-    if (threadIdx.x == 0) {
-      p.value[0] = v;
-      if (p.value_hist && (long long)step < p.hist_len) p.value_hist[step] = v;
-    }
-  }
-  __syncthreads();
-  // gradient; every read of var_param happens before the barrier, every write after it
-  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) {
-    const int j = i < d ? i : i - d;
-    const double sig = exp(p.vp[d + j]);
-    double g;
-    if (i < d) {
-      const double a = __ldcg(p.vec + S + j) - __ldcg(p.aux + j) * c.inv_tau2;              // sum_s g_s[j]
-      g = path ? -invS * (a + __ldcg(p.aux + 2 * d + j) / sig) : -invS * a;
-    } else {
-      const double b = __ldcg(p.vec + S + d + j) - __ldcg(p.aux + d + j) * c.inv_tau2;      // sum_s g_s[j] e_s[j]
-      g = path ? -invS * (b * sig + __ldcg(p.aux + 3 * d + j)) : -invS * b * sig - 1.0;
-    }
-    p.grad[i] = g;
-    if (p.grad_hist && p.ring > 0) p.grad_hist[(size_t)(step % (unsigned long long)p.ring) * (2 * d) + i] = g;
-  }
-  __syncthreads();
-  // optimiser step (optimization.py:188-197, :308-326) fused with the update (objectives.py:57-59)
   const int first = p.counters[1] == 0;
-  if (c.optimizer != 0) {
-    for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) {
-      const double g = p.grad[i];
+  // One pass, no barriers inside: thread j owns BOTH entries of coordinate j (mu_j and log sigma_j), so it reads the
+  // old parameter values before it writes the new ones and no other thread touches them; the threads beyond d (and
+  // all threads again, strided) accumulate the per-sample terms of the value.  All loads of a thread are independent.
+  double va = 0.0, vb_ = 0.0, vh = 0.0;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    const double mu_old = p.vp[j], ls_old = p.vp[d + j];
+    const double sig = exp(ls_old);
+    const double a = __ldcg(p.vec + S + j) - __ldcg(p.aux + j) * c.inv_tau2;              // sum_s g_s[j]
+    const double b = __ldcg(p.vec + S + d + j) - __ldcg(p.aux + d + j) * c.inv_tau2;      // sum_s g_s[j] e_s[j]
+    double g[2];
+    if (path) {
+      g[0] = -invS * (a + __ldcg(p.aux + 2 * d + j) / sig);
+      g[1] = -invS * (b * sig + __ldcg(p.aux + 3 * d + j));
+    } else {
+      g[0] = -invS * a;
+      g[1] = -invS * b * sig - 1.0;
+      vh += ls_old;                                                                        // entropy: sum_j log sigma_j
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = u * d + j;
+      const double gi = g[u];
+      p.grad[i] = gi;
+      if (p.grad_hist && p.ring > 0) p.grad_hist[(size_t)(step % (unsigned long long)p.ring) * (2 * d) + i] = gi;
+      if (c.optimizer == 0) continue;
       double dd;
-      if (c.optimizer == 1) {                    // RMSProp: nu starts at grad**2
-        const double g2 = g * g;
+      if (c.optimizer == 1) {                    // RMSProp: nu starts at grad**2 (optimization.py:189-190)
+        const double g2 = gi * gi;
         double v = first ? g2 : p.opt_nu[i];
         v = v * c.beta1;
         v += (1.0 - c.beta1) * g2;
         p.opt_nu[i] = v;
-        dd = g / sqrt(c.jitter + v);
-      } else {                                   // Adam, incl. the first-step aliasing of `momentum = grad`
+        dd = gi / sqrt(c.jitter + v);
+      } else {                                   // Adam, incl. the first-step aliasing of `momentum = grad` (:314-320)
         double mi, vi;
         if (first) {
-          const double gs = g * c.beta1;
+          const double gs = gi * c.beta1;
           mi = gs + (1.0 - c.beta1) * gs;
-          vi = (g * g) * c.beta2;
+          vi = (gi * gi) * c.beta2;
           vi += (1.0 - c.beta2) * (mi * mi);
         } else {
           mi = p.opt_m[i] * c.beta1;
-          mi += (1.0 - c.beta1) * g;
+          mi += (1.0 - c.beta1) * gi;
           vi = p.opt_nu[i] * c.beta2;
-          vi += (1.0 - c.beta2) * (g * g);
+          vi += (1.0 - c.beta2) * (gi * gi);
         }
         p.opt_m[i] = mi;
         p.opt_nu[i] = vi;
@@ -431,10 +409,32 @@ __global__ void __launch_bounds__(32 * kPostGroups) mf_post_kernel(StepCfg c, St
       }
       if (p.direction) p.direction[i] = dd;
       if (p.dir_hist && p.ring > 0) p.dir_hist[(size_t)(step % (unsigned long long)p.ring) * (2 * d) + i] = dd;
-      const double nv = p.vp[i] - c.lr * dd;
+      const double nv = (u == 0 ? mu_old : ls_old) - c.lr * dd;     // objectives.py:57-59
       p.vp[i] = nv;
       if (p.param_hist && p.ring > 0) p.param_hist[(size_t)(step % (unsigned long long)p.ring) * (2 * d) + i] = nv;
     }
+  }
+  // value (objectives.py:161-164): -(mean_s f(theta_s) + H), or -(mean_s (f - log q)) for the path-derivative form;
+  // samples are taken from the top of the block so that they overlap the coordinate work above
+  for (int s = (int)blockDim.x - 1 - (int)threadIdx.x; s < S; s += blockDim.x) {
+    double sq = 0.0, lq = 0.0;
+    for (int k = 0; k < c.chunks; ++k) {
+      sq += __ldcg(p.sq_part + s * c.chunks + k);
+      if (path) lq += __ldcg(p.lq_part + s * c.chunks + k);
+    }
+    const double f = __ldcg(p.vec + s) + (-0.5 * sq * c.inv_tau2 + c.prior_const);
+    if (p.logp) p.logp[s] = f;
+    va += f;
+    vb_ += lq;
+  }
+  va = block_sum(va, red);
+  vb_ = block_sum(vb_, red);
+  vh = block_sum(vh, red);
+  if (threadIdx.x == 0) {
+    if (!path && c.family == VB_FAMILY_MF_GAUSSIAN) vh += 0.5 * d * (1.0 + kLog2Pi);     // approximations.py:218-220
+    const double v = path ? -((va - vb_) * invS) : -(va * invS + vh);
+    p.value[0] = v;
+    if (p.value_hist && (long long)step < p.hist_len) p.value_hist[step] = v;
   }
   __syncthreads();
   if (threadIdx.x == 0) {

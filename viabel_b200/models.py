@@ -288,40 +288,37 @@ class HierarchicalLinearRegression(Model):
         y_i ~ N(x_i . beta_{g(i)}, sigma),  beta_g ~ N(m, tau I),  m ~ N(0, 10 I),
         log tau ~ N(0,1),  log sigma ~ N(0,1);   theta = [beta (G*p, group-major), m (p), log tau, log sigma].
 
-    The likelihood contraction is a dense GEMM against the block-expanded design matrix
-    X_exp[N, G*p] (cuBLAS fp64 through torch); the gradient is written out analytically."""
+    Log density and PER-SAMPLE gradients (what the full-rank families need) through vb_hier_logp_grad_f64: the
+    observations are kept sorted by group and the likelihood is a grouped contraction -- one CTA per (group, 128
+    samples) -- not a dense GEMM against a block-expanded [N, G*p] design matrix."""
 
     def __init__(self, X, y, group, n_groups):
         Xd = to_dev(X)
-        self.y = to_dev(y).reshape(-1)
+        yd = to_dev(y).reshape(-1)
         g = torch.as_tensor(np.asarray(group), dtype=torch.int64, device=Xd.device)
         self.N, self.p = int(Xd.shape[0]), int(Xd.shape[1])
         self.G = int(n_groups)
+        if self.p > 32:
+            raise NotImplementedError('at most 32 coefficients per group')
         self.dim = self.G * self.p + self.p + 2
-        Xe = torch.zeros(self.N, self.G, self.p, dtype=F64, device=Xd.device)
-        Xe[torch.arange(self.N, device=Xd.device), g] = Xd
-        self.Xe = Xe.reshape(self.N, self.G * self.p)
-        super().__init__(lambda th: self.logp_and_grad(th)[0], lambda th: self.logp_and_grad(th)[1])
+        order = torch.argsort(g, stable=True)
+        self.X = Xd[order].contiguous()
+        self.y = yd[order].contiguous()
+        counts = torch.bincount(g, minlength=self.G)
+        self.goff = torch.cat([torch.zeros(1, dtype=torch.int64, device=Xd.device), torch.cumsum(counts, 0)]).contiguous()
+        super().__init__(lambda th: self.logp_and_grad(th, want_grad=False)[0], lambda th: self.logp_and_grad(th)[1])
 
-    def logp_and_grad(self, theta):
-        G, p, N = self.G, self.p, self.N
-        S = theta.shape[0]
-        c = 0.5 * np.log(2 * np.pi)
-        beta = theta[:, :G * p]
-        m = theta[:, G * p:G * p + p]
-        ltau, lsig = theta[:, -2], theta[:, -1]
-        inv_sig, inv_tau = torch.exp(-lsig), torch.exp(-ltau)
-        res = (self.y[None, :] - beta @ self.Xe.T) * inv_sig[:, None]              # [S, N]
-        db = (beta.reshape(S, G, p) - m[:, None, :]) * inv_tau[:, None, None]      # [S, G, p]
-        ssr, ssb = (res * res).sum(dim=1), (db * db).sum(dim=(1, 2))
-        lp = (-0.5 * ssr - N * (lsig + c) - 0.5 * ssb - G * p * (ltau + c)
-              - 0.5 * ((m / 10.0) ** 2).sum(dim=1) - p * (np.log(10.0) + c)
-              - 0.5 * ltau ** 2 - c - 0.5 * lsig ** 2 - c)
-        grad = torch.empty_like(theta)
-        grad[:, :G * p] = ((res * inv_sig[:, None]) @ self.Xe) - (db * inv_tau[:, None, None]).reshape(S, G * p)
-        grad[:, G * p:G * p + p] = db.sum(dim=1) * inv_tau[:, None] - m / 100.0
-        grad[:, -2] = ssb - G * p - ltau
-        grad[:, -1] = ssr - N - lsig
+    def logp_and_grad(self, theta, want_grad=True):
+        theta = theta.contiguous()
+        S = int(theta.shape[0])
+        if theta.shape[1] != self.dim:
+            raise ValueError('theta must be [S, %d]' % self.dim)
+        lp = torch.empty(S, dtype=F64, device=theta.device)
+        grad = torch.empty(S, self.dim, dtype=F64, device=theta.device) if want_grad else None
+        ws = torch.empty(_lib.lib.vb_hier_workspace_bytes(self.G, S), dtype=torch.uint8, device=theta.device)
+        _lib.check(_lib.lib.vb_hier_logp_grad_f64(_lib.ptr(self.X), _lib.ptr(self.y), _lib.ptr(self.goff), self.N, self.p,
+                                                  self.G, _lib.ptr(theta), S, _lib.ptr(lp), _lib.ptr(grad), _lib.ptr(ws),
+                                                  ws.numel(), _lib.stream()))
         return lp, grad
 
 

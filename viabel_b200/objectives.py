@@ -81,43 +81,25 @@ class StochasticVariationalObjective(VariationalObjective):
 def _mvt_objective(approx, model, S, objective, alpha, var_param, base=None, seed=None):
     """ExclusiveKL (entropy branch) / AlphaDivergence for the full-rank MultivariateT family
     (objectives.py:154-164, :443-460 with approximations.py:342-357; gradient per SURVEY.md App. A.3).
-    The d x d algebra is replicated dense linear algebra (cuSOLVER eigh + cuBLAS GEMMs via torch)."""
+    unpack -> Sigma -> [cuSOLVER eigh] -> reparameterise -> model plugin -> vb_mvt_objective_f64: everything except
+    the eigensolver is this package's kernels (csrc/mvt.cu, float64 tensor-core GEMMs of csrc/gemm_f64.cu)."""
     if objective == _lib.OBJ_EXCLUSIVE_KL_PATH:
         raise NotImplementedError('path-derivative estimator is not available for MultivariateT')
     vp = to_dev(var_param)
     d, df = approx.dim, float(approx.df)
-    mu, F, L = approx.unpack(vp)
-    chi2, z = approx.base_draws(S, seed) if base is None else (to_dev(base[0]), to_dev(base[1]))
+    chi2, z = approx.base_draws(S, seed) if base is None else (to_dev(base[0]).reshape(-1), to_dev(base[1]))
     approx.last_base = (chi2, z)
-    S = z.shape[0]
-    A, w, V = approx.sym_sqrt(L @ L.T)
-    zu = z / torch.sqrt(chi2 / df)[:, None]
-    theta = (mu + zu @ A).contiguous()
+    S = int(z.shape[0])
+    L, hl, w, V = approx.decompose(vp)
+    theta, P, zu2 = approx.transform(vp, chi2, z, w, V)
     f, G = model.logp_and_grad(theta)
-    if objective == _lib.OBJ_EXCLUSIVE_KL:
-        value = -(f.mean() + torch.diagonal(F).sum())
-        gmu = -G.mean(dim=0)
-        Abar = -(zu.T @ G) / S
-        diag_add = -1.0
-    else:
-        # log q at the sampled points: theta - mu = (z/u) A and A Sigma^-1 A = I, so the Mahalanobis term is
-        # |z/u|^2 exactly (no second eigen-decomposition); log det Sigma = 2 sum F_ii
-        import math
-        const = math.lgamma(0.5 * (df + d)) - math.lgamma(0.5 * df) - 0.5 * d * math.log(math.pi * df)
-        logq = const - torch.diagonal(F).sum() - 0.5 * (df + d) * torch.log1p((zu * zu).sum(dim=1) / df)
-        lw = f - logq
-        m = lw.max()
-        sv = torch.exp(lw - m) ** alpha
-        value = torch.log(sv.mean()) / alpha + m
-        gmu = alpha / S * (sv @ G)
-        Abar = alpha / S * (zu.T @ (sv[:, None] * G))
-        diag_add = alpha / S * sv.sum()
-    rw = torch.sqrt(w)
-    M = V.T @ Abar @ V
-    Sbar = V @ (M / (rw[:, None] + rw[None, :])) @ V.T
-    Lbar = (Sbar + Sbar.T) @ L
-    Fbar = torch.tril(Lbar, -1) + torch.diag(torch.diagonal(Lbar) * torch.diagonal(L) + diag_add)
-    return value, approx.pack_grad(gmu, Fbar)
+    out = torch.empty(1 + vp.numel(), dtype=F64, device=vp.device)
+    ws = torch.empty(_lib.lib.vb_mvt_objective_workspace_bytes(S, d), dtype=torch.uint8, device=vp.device)
+    _lib.check(_lib.lib.vb_mvt_objective_f64(
+        _lib.ptr(L), _lib.ptr(hl), _lib.ptr(w), _lib.ptr(V), _lib.ptr(P), _lib.ptr(zu2), _lib.ptr(f.contiguous()),
+        _lib.ptr(G.contiguous()), S, d, df, objective, float(alpha), _lib.ptr(out[:1]), _lib.ptr(out[1:]), _lib.ptr(ws),
+        ws.numel(), _lib.stream()))
+    return out[0], out[1:]
 
 
 class _ModelLogDensity(torch.autograd.Function):
