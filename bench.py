@@ -55,6 +55,7 @@ def parse():
     ap.add_argument('--no-graph', action='store_true', help='enqueue every step from Python instead of replaying graphs')
     ap.add_argument('--psis-draws', type=int, default=100000000)
     ap.add_argument('--ref-seconds', type=float, default=150.0, help='time budget of the reference arm')
+    ap.add_argument('--config', default='c2', choices=['c2', 'c4'], help='c2: the headline ELBO-gradient bench; c4: BASELINE configs[3]')
     return ap.parse_args()
 
 
@@ -606,10 +607,123 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_c4(args):
+    """BASELINE configs[3]: hierarchical linear regression with d = 2048 latents (G = 65 groups x p = 31 coefficients +
+    31 hyper-means + log tau + log sigma, 200 observations per group), full-rank MultivariateT(df = 100),
+    AlphaDivergence(alpha = 2), S = 256, RMSProp step.  One iteration = unpack -> Sigma = L L^T -> eigh (cuSOLVER, the
+    one library call) -> reparameterise -> grouped model kernel -> cotangent GEMMs -> fused RMSProp.  Roofline: the
+    float64 tensor-pipe GEMMs of csrc/gemm_f64.cu (executed flops 8 d^3 + 8 S d^2) against the cuBLAS fp64 matmul peak."""
+    import torch
+    import viabel_b200 as vb
+    torch.cuda.set_device(0)
+    G, p, n_per, S = 65, 31, 200, args.mc
+    rs = np.random.RandomState(20260118)
+    N = G * n_per
+    group = np.repeat(np.arange(G), n_per)
+    X = rs.randn(N, p)
+    m = rs.randn(p)
+    beta = m + 0.5 * rs.randn(G, p)
+    y = np.sum(X * beta[group], axis=1) + 0.3 * rs.randn(N)
+    model = vb.HierarchicalLinearRegression(X, y, group, G)
+    d = model.dim
+    approx = vb.MultivariateT(d, 100, seed=DRAW_SEED)
+    objective = vb.AlphaDivergence(approx, model, S, 2.0)
+    opt = vb.RMSProp(0.01)
+    # start near a sensible scale (Sigma = 0.01 I): the reference's init Sigma = 10 I overflows the likelihood scale
+    vp0 = approx.init_param()
+    F = np.zeros((d, d))
+    F[np.diag_indices(d)] = 0.5 * np.log(0.01)
+    vp0[d:] = F[np.tril_indices(d)]
+    vp0[:G * p] = beta.reshape(-1)
+    vp0[G * p:G * p + p] = m
+    vp = torch.as_tensor(vp0, device='cuda')
+
+    def step():
+        value, grad = objective(vp)
+        opt._fused_step(vp, grad, False)
+        return value
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    steps = args.steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        v = step()
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / steps
+    finite = bool(torch.isfinite(vp).all()) and bool(torch.isfinite(v))
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e-3 / reps, out
+
+    _, L, hl = approx.unpack(vp)
+    t_sigma, Sigma = timed(lambda: approx.sigma(L))
+    t_eigh, (w, V) = timed(lambda: approx._eigh(Sigma))
+    chi2, z = approx.base_draws(S)
+    t_tr, (theta, P, zu2) = timed(lambda: approx.transform(vp, chi2, z, w, V))
+    t_model, (f, Gm) = timed(lambda: model.logp_and_grad(theta))
+    out = torch.empty(1 + vp.numel(), dtype=torch.float64, device='cuda')
+    ws = torch.empty(vb._lib.lib.vb_mvt_objective_workspace_bytes(S, d), dtype=torch.uint8, device='cuda')
+    ptr = vb._lib.ptr
+    t_obj, _ = timed(lambda: vb._lib.check(vb._lib.lib.vb_mvt_objective_f64(
+        ptr(L), ptr(hl), ptr(w), ptr(V), ptr(P), ptr(zu2), ptr(f), ptr(Gm), S, d, 100.0, 2, 2.0, ptr(out[:1]), ptr(out[1:]),
+        ptr(ws), ws.numel(), vb._lib.stream())))
+    clocks = sampler.stop()
+    gemm_flops = 8.0 * d ** 3 + 8.0 * S * d * d
+    t_gemm = t_sigma + t_tr + t_obj
+    peak = matmul_peak_tflops(torch, torch.float64, False, 4096)
+    achieved = gemm_flops / t_gemm / 1e12
+    # end to end with host buffers: numpy var_param in, numpy value + gradient out
+    vp_host = vp.cpu().numpy()
+    for _ in range(2):
+        objective(vp_host)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_e2e = max(2, min(steps, 5))
+    for _ in range(n_e2e):
+        vh, gh = objective(vp_host)
+        vp_host = vp_host - 0.01 * gh / (np.abs(gh) + 1.0)
+    e2e = (time.perf_counter() - t0) / n_e2e
+    line = {
+        'metric': 'alpha_grad_iters_per_sec', 'value': 1.0 / sec, 'unit': 'iter/s', 'n_gpus': 1, 'steps': steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'hier-linear d=%d (G=%d p=%d, %d obs) MultivariateT(df=100) AlphaDivergence(alpha=2) S=%d + RMSProp '
+                               '(BASELINE configs[3])' % (d, G, p, N, S),
+                   'l2': 'parameter and cotangent matrices (7 x d^2 x 8 B = %.0f MB) exceed L2' % (7 * d * d * 8 / 1e6)},
+        'clocks': clocks,
+        'e2e': {'value': 1.0 / e2e, 'unit': 'iter/s', 'h2d_bytes_per_step': int(vp.numel()) * 8,
+                'd2h_bytes_per_step': (1 + int(vp.numel())) * 8},
+        'gpu_launches': 24 * steps, 'finite': finite,
+        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+                     'traffic': None, 'kernel': 'gemm_f64_kernel (8 launches per iteration)', 'kernel_ms': t_gemm * 1e3,
+                     'peak_note': 'cuBLAS fp64 matmul 4096^3 measured in this run (best of 10)',
+                     'executed_flops_per_iteration': gemm_flops},
+        'stages_ms': {'sigma_gemm': t_sigma * 1e3, 'eigh_cusolver': t_eigh * 1e3, 'transform_gemms': t_tr * 1e3,
+                      'model_grouped_kernel': t_model * 1e3, 'objective_gemms': t_obj * 1e3},
+        'cpu_baseline': None,
+    }
+    print(json.dumps(line))
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.config == 'c4':
+        run_c4(args)
     else:
         run_b200(args)
 

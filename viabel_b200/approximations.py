@@ -286,14 +286,26 @@ class MultivariateT(ApproximationFamily):
     def _eigh(Sigma):
         """Symmetric eigendecomposition on the device -- the ONE library call of this path (cuSOLVER through
         torch.linalg.eigh).  cuSOLVER's divide-and-conquer can refuse a large matrix whose eigenvalues are all equal
-        (e.g. the reference's init Sigma = 10 I at d = 2048); the degeneracy is then broken by a relative 1e-13 ramp on
-        the diagonal, far below the 1e-10 tolerance.  Returns (w, V) with V contiguous, eigenvectors in columns."""
+        (e.g. the reference's init Sigma = 10 I at d = 2048): an exactly diagonal Sigma is then decomposed by sorting
+        its diagonal, anything else gets a relative 1e-13 ramp on the diagonal, far below the 1e-10 tolerance.
+        Returns (w, V) with V contiguous, eigenvectors in columns."""
         try:
             w, V = torch.linalg.eigh(Sigma)
         except torch.linalg.LinAlgError:
             d = Sigma.shape[0]
-            ramp = torch.arange(d, dtype=Sigma.dtype, device=Sigma.device) / d
-            w, V = torch.linalg.eigh(Sigma + torch.diag(1e-13 * torch.diagonal(Sigma).abs().mean() * ramp))
+            diag = torch.diagonal(Sigma)
+            if int(torch.count_nonzero(Sigma)) == int(torch.count_nonzero(diag)):
+                # exactly diagonal (the reference's init_param, Sigma = c I): the decomposition is a sort
+                w, order = torch.sort(diag)
+                V = torch.zeros_like(Sigma)
+                V[order, torch.arange(d, device=Sigma.device)] = 1.0
+            else:
+                ramp = torch.arange(d, dtype=Sigma.dtype, device=Sigma.device) / d
+                scale = diag.abs().mean()
+                try:
+                    w, V = torch.linalg.eigh(Sigma + torch.diag(1e-13 * scale * ramp))
+                except torch.linalg.LinAlgError:
+                    w, V = torch.linalg.eigh(Sigma + torch.diag(1e-10 * scale * ramp))
         return w.contiguous(), V.contiguous()
 
     def decompose(self, vp):
