@@ -628,7 +628,9 @@ def run_c4(args):
     d = model.dim
     approx = vb.MultivariateT(d, 100, seed=DRAW_SEED)
     objective = vb.AlphaDivergence(approx, model, S, 2.0)
-    opt = vb.RMSProp(0.01)
+    # 2.1 M free parameters: RMSProp's first steps move every Cholesky entry by the learning rate, and a unit-lower-
+    # triangular factor with +-lr/0.1 below the diagonal stays well conditioned only for small lr
+    opt = vb.RMSProp(0.0005)
     # start near a sensible scale (Sigma = 0.01 I): the reference's init Sigma = 10 I overflows the likelihood scale
     vp0 = approx.init_param()
     F = np.zeros((d, d))
