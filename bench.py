@@ -229,8 +229,10 @@ def measured_peak(name, fallback):
         return fallback, 'fallback (B200_PROFILING.md)'
 
 
-def matmul_peak_tflops(torch, dtype, tf32, n):
-    """Same method as MEASURED_PEAKS.json's `how` (torch.matmul n^3, 2 n^3 flop, best of 10, CUDA events)."""
+def matmul_peak_tflops(torch, dtype, tf32, n, sustained=False):
+    """Same method as MEASURED_PEAKS.json's `how`: torch.matmul n^3 (2 n^3 flop) with CUDA events -- best of 10
+    (burst), or, with sustained=True, back to back for ~0.7 s and then the mean of 10 more (the figure to hold a
+    kernel timed inside a long step against: the boxes of this pool power-cap after a few hundred ms of load)."""
     torch.backends.cuda.matmul.allow_tf32 = tf32
     a = torch.randn(n, n, device='cuda', dtype=dtype)
     b = torch.randn(n, n, device='cuda', dtype=dtype)
@@ -243,6 +245,17 @@ def matmul_peak_tflops(torch, dtype, tf32, n):
         torch.cuda.synchronize()
         if i >= 2:
             best = min(best, e0.elapsed_time(e1) * 1e-3)
+    if sustained:
+        reps = max(10, int(0.7 / best))
+        for _ in range(reps):
+            torch.matmul(a, b)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = e0.elapsed_time(e1) * 1e-3 / 10
     torch.backends.cuda.matmul.allow_tf32 = False
     return 2.0 * n ** 3 / best / 1e12
 
@@ -375,7 +388,9 @@ def bench_c5(torch, dist, vb, args, rank, world):
     d, n = 256, args.psis_draws
     rs = np.random.RandomState(20260119)
     loc, scale = rs.randn(d), np.exp(0.25 * rs.randn(d))
-    vp = np.concatenate([loc + 0.05 * rs.randn(d), np.log(scale) + 0.02 * rs.randn(d)])
+    # the proposal is 10 % wider than the target per coordinate: its lighter tails (df 40 vs 10) are then covered and
+    # k-hat stays below 0.7, so the whole pipeline (PSIS -> bounds) runs
+    vp = np.concatenate([loc + 0.05 * rs.randn(d), np.log(scale) + 0.10 + 0.02 * rs.randn(d)])
     model = vb.StudentTTarget(loc, scale, 10.0)
     approx = vb.MFStudentT(d, 40, seed=DRAW_SEED)
     small = min(n, 2000000)
@@ -450,27 +465,31 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
     eng.run(max(args.warmup, 3), use_graph=use_graph)
     eng.run(16, use_graph=use_graph)      # untimed: both graph shapes (8-step and 1-step) are captured before the clock starts
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    elapsed = time_steps(torch, eng, args.steps, use_graph)
+    # (1) burst: the first K steps after the warm-up, GPU clocks still at their idle-boost state
+    burst = max_over_ranks(time_steps(torch, eng, args.steps, use_graph))
     barrier()
-    if world > 1:
-        t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed = float(t.item())
-    ms_per_step = elapsed / args.steps * 1e3
-    # sustained: the same step for >= 1 s (the power cap needs a few hundred ms to bite; nvidia-smi samples every
-    # 100 ms).  The same count on every rank -- the step contains the exchange.
-    n_sus = max(args.steps, min(20000, int(1.2 / max(elapsed / args.steps, 1e-5))))
+    # (2) settle: the same step for >= 1.2 s, untimed for `value` but reported as `sustained`.  These boxes reach their
+    # steady clocks only after a few hundred ms of load (one busy GPU is power-capped DOWN, eight lightly loaded ones
+    # clock UP), so a number taken in the first 20 ms describes neither.  Same count on every rank: the step
+    # contains the exchange.
+    n_sus = max(args.steps, min(20000, int(1.2 / max(burst / args.steps, 1e-5))))
     n_sus = (n_sus + 7) // 8 * 8
-    sus = time_steps(torch, eng, n_sus, use_graph)
+    sus = max_over_ranks(time_steps(torch, eng, n_sus, use_graph))
+    # (3) the K timed steps, in the steady state, back to back with the settle phase (no idle gap)
+    elapsed = max_over_ranks(time_steps(torch, eng, args.steps, use_graph))
     barrier()
-    if world > 1:
-        t = torch.tensor([sus], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sus = float(t.item())
+    ms_per_step = elapsed / args.steps * 1e3
     clocks = sampler.stop() if sampler else None
     eng.check_comm()
     finite = bool(torch.isfinite(eng.vp).all())
@@ -493,14 +512,14 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_sec = float(t.item())
 
-    # ---- dominant kernel alone (the sweep through the C ABI), CUDA events on the launching stream --------
+    # ---- dominant kernel alone (the sweep through the C ABI), CUDA events on the launching stream, in the same
+    #      steady state: back to back for ~0.5 s, then the mean of the next launches --------
     theta = approx.sample(torch.as_tensor(approx.init_param(), device=dev), S)
     base = approx.last_base
-    for _ in range(2):
+    for _ in range(max(3, int(0.5 / max(elapsed / args.steps, 1e-5)))):
         model.sweep(theta, base, None, True)
-    torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = max(3, min(args.steps, 10))
+    reps = max(10, min(args.steps, 50))
     k0.record()
     for _ in range(reps):
         model.sweep(theta, base, None, True)
@@ -530,9 +549,11 @@ def run_b200(args):
         peak = matmul_peak_tflops(torch, torch.float64, False, 4096)
         peak_note = 'cuBLAS fp64 matmul 4096^3 measured in this run (torch.matmul, 2 n^3 flop, best of 10, CUDA events)'
     else:
-        peak = matmul_peak_tflops(torch, torch.float32, True, 8192)
-        peak_note = ('cuBLAS tf32 matmul 8192^3 measured in this run with the method of MEASURED_PEAKS.json '
-                     '(torch.matmul, 2 n^3 flop, best of 10, CUDA events); SURVEY 8(d) names this denominator')
+        peak = matmul_peak_tflops(torch, torch.float32, True, 8192, sustained=True)
+        peak_burst = matmul_peak_tflops(torch, torch.float32, True, 8192)
+        peak_note = ('cuBLAS tf32 matmul 8192^3 measured in this run with the method of MEASURED_PEAKS.json (torch.matmul, '
+                     '2 n^3 flop, CUDA events): SUSTAINED figure (back to back for 0.7 s, then the mean of 10), because the '
+                     'kernel is timed inside a long run; burst (best of 10) = %.1f.  SURVEY 8(d) names this denominator' % peak_burst)
     achieved = flops / sweep_sec / 1e12
     traffic = None
     if path == 'fast' and world == 1 and (N, d, S) == (1000000, 512, 256):
@@ -541,8 +562,9 @@ def run_b200(args):
                 'frac': achieved / peak, 'traffic': traffic, 'kernel': 'glm_sweep_%s' % path,
                 'kernel_ms': sweep_sec * 1e3, 'peak_note': peak_note,
                 'bf16_peak_tflops': bf16_peak, 'bf16_peak_source': how,
-                'frac_bf16_algorithmic': achieved / bf16_peak,
-                'frac_bf16_executed': (2.0 * achieved / bf16_peak) if path == 'fast' else None,
+                'bf16_peak_sustained_tflops': bf16_sus,
+                'frac_bf16_algorithmic': achieved / bf16_sus,
+                'frac_bf16_executed': (2.0 * achieved / bf16_sus) if path == 'fast' else None,
                 'executed_note': 'fp16 hi/lo operand splits: 3 + 1 tensor passes = 2x the algorithmic flops',
                 'algorithmic_flops_per_launch': flops, 'algorithmic_bytes_per_launch': (hi - lo) * d * 4.0 if path == 'fast'
                 else (hi - lo) * d * 8.0}
@@ -580,6 +602,7 @@ def run_b200(args):
     line = {
         'metric': 'elbo_grad_iters_per_sec', 'value': 1e3 / ms_per_step, 'unit': 'iter/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
+        'settle_steps': 16 + args.steps + n_sus,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f64' if path == 'f64' else 'f16x2-split/f32',
         'data': 'synthetic',
@@ -589,6 +612,9 @@ def run_b200(args):
                    'step': 'CUDA graph replay of 3 kernels (pre | sweep | post)' if use_graph else '3 kernels enqueued from Python',
                    'exchange': 'in-kernel one-shot all-reduce over peer memory' if world > 1 else 'none',
                    'draws': 'fp16-exact Philox normals (enable_fast_path sets quantize_draws=2)' if path == 'fast' else 'fp64 Philox normals'},
+        'timing': 'K steps timed in the steady state: after W warm-up steps, K burst steps and a %d-step settle phase' % n_sus,
+        'burst': {'value': args.steps / burst, 'unit': 'iter/s', 'ms_per_step': burst / args.steps * 1e3, 'steps': args.steps,
+                  'note': 'the first K steps after the warm-up (the round-1 definition of `value`)'},
         'sustained': {'value': n_sus / sus, 'unit': 'iter/s', 'ms_per_step': sus / n_sus * 1e3, 'steps': n_sus},
         'clocks': clocks,
         'e2e': {'value': 1.0 / e2e_sec, 'unit': 'iter/s', 'h2d_bytes_per_step': 2 * d * 8,
