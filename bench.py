@@ -279,10 +279,14 @@ def bench_psis(torch, vb, args):
     n = args.psis_draws
     lw = psis_draws(torch, n, 'cuda', DATA_SEED + 5)
     out = torch.empty_like(lw)
-    for _ in range(3):
+    # its own steady state: let the GPU leave the power-capped state of the tensor-core legs (1 s idle), then run the
+    # PSIS pipeline back to back for ~0.3 s before the timed repetitions
+    torch.cuda.synchronize()
+    time.sleep(1.0)
+    for _ in range(600):
         vb.psislw_device(lw, out)
     torch.cuda.synchronize()
-    reps = 10
+    reps = 20
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
