@@ -9,6 +9,7 @@ per-rank sums are exchanged inside that kernel through the peer-memory communica
 (parallel.Communicator) -- no NCCL call on the hot path.
 """
 import ctypes
+import gc
 from ctypes import c_double, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 import numpy as np
@@ -254,8 +255,16 @@ class FusedStep(object):
             self._restore(snap)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                body()
+            # no garbage collection inside the capture: a collected object that owns device resources (an old
+            # graph, a model handle) would call cudaFree / cudaGraphExecDestroy, which a global-mode capture forbids
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                    body()
+            finally:
+                if gc_was_on:
+                    gc.enable()
             self._graphs[key] = g
         return g
 
