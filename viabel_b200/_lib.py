@@ -9,7 +9,8 @@ import os
 from ctypes import c_char_p, c_double, c_int, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libviabel_b200.so')
+# VIABEL_B200_LIB points at another build of the same library (A/B runs of kernel variants)
+LIB_PATH = os.environ.get('VIABEL_B200_LIB') or os.path.join(_HERE, 'libviabel_b200.so')
 
 VB_OK = 0
 VB_ERR_INVALID_ARG, VB_ERR_UNSUPPORTED, VB_ERR_CUDA, VB_ERR_WORKSPACE, VB_ERR_NUMERIC = -1, -2, -3, -4, -5
