@@ -149,20 +149,21 @@ __global__ void __launch_bounds__(kSweepThreads, 1) glm_sweep_f64_kernel(SweepAr
       __syncthreads();   // previous tile's readers of Xs / rbar are done
       // ---- stage the X tile (zero padded) ----------------------------------------------
       if (vec_ok) {
+        // asynchronous 16-byte copies, zero filled beyond N / d: every copy of the tile is in flight at once, so the
+        // HBM latency is paid once per tile (a load -> store loop paid it once per iteration: 11 % of the sweep)
         const int half = a.P >> 1;
         for (int idx = tid; idx < BM * half; idx += kSweepThreads) {
           const int r = idx / half, c2 = idx - r * half;
           const int64_t n = n0 + r;
-          double2 v = make_double2(0.0, 0.0);
-          if (n < a.N) {
-            const int j = 2 * c2;
-            if (j + 1 < a.d)
-              v = *reinterpret_cast<const double2*>(a.X + n * a.ldx + j);
-            else if (j < a.d)
-              v.x = a.X[n * a.ldx + j];
-          }
-          *reinterpret_cast<double2*>(Xs + (size_t)r * a.P + 2 * c2) = v;
+          const int j = 2 * c2;
+          const bool row_ok = n < a.N;
+          const uint32_t bytes = (row_ok && j + 1 < a.d) ? 16u : ((row_ok && j < a.d) ? 8u : 0u);
+          const double* src = bytes ? a.X + n * a.ldx + j : a.X;
+          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Xs + (size_t)r * a.P + 2 * c2);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
       } else {
         for (int idx = tid; idx < BM * a.P; idx += kSweepThreads) {
           const int r = idx / a.P, c = idx - r * a.P;
@@ -198,13 +199,16 @@ __global__ void __launch_bounds__(kSweepThreads, 1) glm_sweep_f64_kernel(SweepAr
 #pragma unroll
           for (int i = 0; i < MT; ++i)
             af[i] = *reinterpret_cast<const double2*>(Xs + (size_t)(8 * i + g) * a.P + 8 * kg + 2 * t);
+          // the two k-halves of a tile update the same accumulators: issue all 4 MT tiles of the first half
+          // before the second, so that a DMMA never waits for the one issued just before it
 #pragma unroll
           for (int i = 0; i < MT; ++i)
 #pragma unroll
-            for (int jn = 0; jn < 4; ++jn) {
-              dmma884(acc[i][jn][0], acc[i][jn][1], af[i].x, bcur[jn].x);
-              dmma884(acc[i][jn][0], acc[i][jn][1], af[i].y, bcur[jn].y);
-            }
+            for (int jn = 0; jn < 4; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], af[i].x, bcur[jn].x);
+#pragma unroll
+          for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int jn = 0; jn < 4; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], af[i].y, bcur[jn].y);
 #pragma unroll
           for (int jn = 0; jn < 4; ++jn) bcur[jn] = bnxt[jn];
         }
@@ -262,18 +266,23 @@ __global__ void __launch_bounds__(kSweepThreads, 1) glm_sweep_f64_kernel(SweepAr
               for (int jn = 0; jn < 4; ++jn) enxt[jn] = bp[jn * sbStride + (size_t)(jb + 1) * 32];
             }
             double p0 = 0.0, p1 = 0.0;
+            double t0[MT], t1[MT];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) t0[i] = t1[i] = 0.0;
+            // MT independent accumulation chains, interleaved (a chain's next DMMA is MT instructions away)
+#pragma unroll
+            for (int jn = 0; jn < 4; ++jn) {
+#pragma unroll
+              for (int i = 0; i < MT; ++i) dmma884(t0[i], t1[i], acc[i][jn][0], ecur[jn].x);
+#pragma unroll
+              for (int i = 0; i < MT; ++i) dmma884(t0[i], t1[i], acc[i][jn][1], ecur[jn].y);
+            }
 #pragma unroll
             for (int i = 0; i < MT; ++i) {
-              double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-              for (int jn = 0; jn < 4; ++jn) {
-                dmma884(t0, t1, acc[i][jn][0], ecur[jn].x);
-                dmma884(t0, t1, acc[i][jn][1], ecur[jn].y);
-              }
               const double2 xv =
                   *reinterpret_cast<const double2*>(Xs + (size_t)(8 * i + g) * a.P + 8 * jb + 2 * t);
-              p0 += xv.x * t0;
-              p1 += xv.y * t1;
+              p0 += xv.x * t0[i];
+              p1 += xv.y * t1[i];
             }
 #pragma unroll
             for (int o = 4; o < 32; o <<= 1) {
