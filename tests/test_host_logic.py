@@ -98,7 +98,7 @@ def test_host_optimizer_directions_golden(golden):
 def test_exp_table_constants_accuracy():
     """The table-driven exp of the PSIS passes (csrc/psis.cu exp_nonpos): emulate its arithmetic in numpy with the
     constants parsed from the source.  Guards the reduction constants (256/ln2, the two-part ln2/256) and the
-    degree-4 polynomial: a wrong digit shows up as an error far above the ~2 ulp of the float64 emulation."""
+    degree-4 polynomial (and the 7-operation variant of the streaming sums): a wrong digit shows up as an error far above the ~2 ulp of the float64 emulation."""
     import os
     import re
     src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'viabel_b200', 'csrc', 'psis.cu')).read()
@@ -124,6 +124,16 @@ def test_exp_table_constants_accuracy():
     val = np.ldexp(p * tab[ni & (ntab - 1)], (ni >> shift_bits).astype(np.int64))
     rel = np.abs(val - np.exp(x)) / np.exp(x)
     assert rel.max() < 1e-15, rel.max()
+    # exp_stream (the two streaming sums): one-step reduction with the correctly rounded -ln2/ntab, degree 3
+    assert c[7] == -np.log(2.0) / ntab
+    r = n * c[7] + x
+    p = c[5]
+    p = p * r + c[6]
+    p = p * r + 1.0
+    p = p * r + 1.0
+    val = np.ldexp(p * tab[ni & (ntab - 1)], (ni >> shift_bits).astype(np.int64))
+    rel = (val - np.exp(x)) / np.exp(x)
+    assert np.abs(rel).max() < 3e-13 and abs(rel.mean()) < 5e-14, (np.abs(rel).max(), rel.mean())
 
 
 def test_fast_path_numerics_scheme_emulated():
