@@ -117,6 +117,13 @@ def cpu_iterations(n_rows, d, S, steps, warmup, budget_s=None):
     """(seconds per iteration, iterations timed) of the oracle on n_rows observations."""
     from oracle import viabel_oracle as vo
     X, y = host_problem(n_rows, d, DATA_SEED)
+    # one BLAS thread per pool worker (the workers already cover every core; nested BLAS threading oversubscribes the
+    # host 16-fold and was measured 6x slower).  The --impl reference arm sets the same through the environment.
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=1)
+    except Exception:
+        pass
     it = CpuIteration(X, y, os.cpu_count() or 1)
     rs = np.random.RandomState(DRAW_SEED)
     vp = vo.mfg_init_param(d)
