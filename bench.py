@@ -381,7 +381,29 @@ def bench_psis_sharded(torch, dist, vb, args, rank, world, dev):
     sec = float(t.item())
     hbm, how = measured_peak('hbm_gbs', 6650.0)
     achieved = 24.0 * n / sec / 1e9
+    # weak scaling beside it: the same pipeline with n draws PER RANK (the replicated select / GPD stages and the
+    # exchange are a fixed ~0.3 ms, which a 0.5 ms job cannot hide when split; a world x larger job can)
+    del lw, out
+    lw = psis_draws(torch, n, dev, DATA_SEED + 5 + 1000 * rank)
+    out = torch.empty_like(lw)
+    sizes_w = [n] * world
+    for _ in range(3):
+        vb.psislw_sharded(lw, out=out, sizes=sizes_w)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        _, khat_w, res_w = vb.psislw_sharded(lw, out=out, sizes=sizes_w)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3 / reps], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec_w = float(t.item())
+    weak = {'value': n * world / sec_w, 'unit': 'draws/s', 'n_draws': n * world, 'ms': sec_w * 1e3, 'khat': float(khat_w),
+            'frac_of_hbm_x_ranks': 24.0 * n * world / sec_w / 1e9 / (hbm * world)}
+    del lw, out
     return {'metric': 'psis_draws_per_sec', 'value': n / sec, 'unit': 'draws/s', 'n_draws': n, 'ms': sec * 1e3,
+            'weak_scaling': weak,
             'sharding': 'draws over %d ranks (strong scaling of the 1e8-draw column, includes the status read-back)' % world,
             'khat': float(khat), 'n_tail': int(res[2]),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm * world, 'unit': 'GB/s',
