@@ -525,6 +525,71 @@ def gen_dis_objective():
     print('dis_objective: %d arrays' % len(out))
 
 
+def nvp_masks(dim, n_pairs):
+    """Alternating half masks of the reference's own NVP test (tests/test_approximations.py:131-139)."""
+    half, halfplus = dim // 2, dim - dim // 2
+    m1 = np.hstack([[0] * half, [1] * halfplus])
+    m2 = np.hstack([[1] * half, [0] * halfplus])
+    return np.array(list(np.vstack([m1, m2])) * n_pairs)
+
+
+def gen_flows():
+    """NeuralNet.forward (approximations.py:414-429) and NVPFlow (:452-550): g / f / log_density / sample with the
+    prior's recorded draws, then ExclusiveKL(use_path_deriv=True) and AlphaDivergence on the flow (the only two
+    objectives the reference can evaluate on a family without entropy: its plain ExclusiveKL branch calls
+    approx.log_density(samples) without var_param, objectives.py:163)."""
+    from viabel.approximations import NeuralNet, NVPFlow
+    out = {}
+    rs = np.random.RandomState(1639)
+    for dim, hidden in ((1, 4), (3, 10), (6, 8)):
+        tag = 'nn_d%d' % dim
+        nn = NeuralNet([[dim, hidden], [hidden, hidden], [hidden, dim]])
+        flat = rs.randn(nn.var_param_dim) / 3
+        x = rs.randn(9, dim)
+        y, ldj = nn.forward(nn._pattern.fold(flat), x)
+        out[tag + '/flat'] = flat
+        out[tag + '/x'] = x
+        out[tag + '/y'] = np.asarray(y)
+        out[tag + '/log_det_J'] = np.asarray(ldj)
+    for dim, hidden, pairs, prior_kind in ((1, 5, 2, 'mfg'), (3, 10, 3, 'mfg'), (6, 7, 2, 'mft')):
+        tag = 'nvp_d%d' % dim
+        layers = [[dim, hidden], [hidden, dim]]
+        mask = nvp_masks(dim, pairs)
+        prior = MFGaussian(dim) if prior_kind == 'mfg' else MFStudentT(dim, 7)
+        prior_param = np.concatenate([0.2 * rs.randn(dim), 0.1 * rs.randn(dim)])
+        fam = NVPFlow(layers, layers, mask, prior, prior_param, dim)
+        vp = rs.randn(fam.var_param_dim) / 4
+        with Recorder() as rec:
+            x = fam.sample(vp, 11, seed=341)
+        z0 = prior_param[:dim] + np.exp(prior_param[dim:]) * rec[0][2]
+        out[tag + '/prior_param'] = prior_param
+        out[tag + '/mask'] = mask.astype(np.float64)
+        out[tag + '/var_param'] = vp
+        out[tag + '/base'] = rec[0][2]
+        out[tag + '/z0'] = z0
+        out[tag + '/sample'] = np.asarray(x)
+        zb, ld = fam.f(vp, x)
+        out[tag + '/f_z'] = np.asarray(zb)
+        out[tag + '/f_logdet'] = np.asarray(ld)
+        out[tag + '/log_density'] = np.asarray(fam.log_density(vp, x))
+        mean, sd = target_params(dim, seed=14 + dim)
+        logp = gauss_log_p(mean, sd)
+        objs = {'ekl_path': lambda: ExclusiveKL(fam, logp, 8, use_path_deriv=True),
+                'alpha2': lambda: AlphaDivergence(fam, logp, 8, 2.0)}
+        for oname, mk in objs.items():
+            otag = '%s/obj/%s' % (tag, oname)
+            np.random.seed(5039)
+            with Recorder() as rec:
+                value, grad = mk()(vp)
+            out[otag + '/base'] = rec[0][2]
+            out[otag + '/value'] = np.asarray(float(value))
+            out[otag + '/grad'] = np.asarray(grad, dtype=np.float64)
+        out[tag + '/target_mean'] = mean
+        out[tag + '/target_sd'] = sd
+    np.savez_compressed(os.path.join(OUT, 'flows.npz'), **out)
+    print('flows: %d arrays' % len(out))
+
+
 if __name__ == '__main__':
     print('reference:', os.path.dirname(viabel.__file__))
     gen_families()
@@ -537,3 +602,4 @@ if __name__ == '__main__':
     gen_mc_diagnostics()
     gen_dis()
     gen_dis_objective()
+    gen_flows()

@@ -88,8 +88,24 @@ def shape(a):
     return tuple(a.shape)
 
 
+class _Acc(_np.ndarray):
+    """ndarray whose in-place add accepts a Box: `acc = np.zeros(n); acc += traced` (the accumulator pattern of
+    NeuralNet.forward / NVPFlow.f, approximations.py:419-428, :520-529) rebinds `acc` to the traced sum, as real
+    autograd's ArrayBox arithmetic does.  Everything else behaves as a plain ndarray."""
+
+    def __iadd__(self, other):
+        if isinstance(other, Box):
+            return other + _np.asarray(self)
+        return _np.ndarray.__iadd__(self, other)
+
+    def __isub__(self, other):
+        if isinstance(other, Box):
+            return (-other) + _np.asarray(self)
+        return _np.ndarray.__isub__(self, other)
+
+
 def zeros(*a, **k):
-    return _np.zeros(*a, **k)
+    return _np.zeros(*a, **k).view(_Acc)
 
 
 def ones(*a, **k):

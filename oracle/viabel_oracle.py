@@ -636,6 +636,81 @@ def lr_objective(var_param, z, eps, model, kind, alpha=None):
 
 # --------------------------------------------------------------------------
 # PSIS (_psis.py:113-396) -- selection restatement (no full argsort)
+
+# ---------------------------------------------------------------------------------------------
+# NeuralNet / NVPFlow (approximations.py:385-550), forward functions; tanh hidden activations
+# ---------------------------------------------------------------------------------------------
+def nn_fold(flat, shapes):
+    """PatternDict order (:404-407): W0 (C-order), b0, W1, b1, ..."""
+    out, off = [], 0
+    for a, b in shapes:
+        W = flat[off:off + a * b].reshape(a, b)
+        off += a * b
+        out.append((W, flat[off:off + b]))
+        off += b
+    assert off == flat.size
+    return out
+
+
+def nn_forward(flat, shapes, x, last='tanh'):
+    """NeuralNet.forward (:414-429): tanh layers, `last` in {'tanh', 'identity'}; the log-det term is the
+    reference's log|sum_j (f'(out) W^T)_j| with the derivative evaluated at the layer OUTPUT."""
+    layers = nn_fold(np.asarray(flat, dtype=np.float64), shapes)
+    log_det = np.zeros(x.shape[0])
+    for i, (W, b) in enumerate(layers):
+        ident = (i + 1 == len(layers)) and last == 'identity'
+        x = x @ W + b
+        if not ident:
+            x = np.tanh(x)
+        d = np.ones_like(x) if ident else 1.0 - np.tanh(x) ** 2
+        log_det = log_det + np.log(np.abs((d @ W.T).sum(axis=1)))
+    return x, log_det
+
+
+def nvp_split(var_param, shapes_t, shapes_s, n_layers):
+    """Flat NVPFlow parameter -> [(t_flat, s_flat)] ("it" before "is", :487-489)."""
+    nt = sum(a * b + b for a, b in shapes_t)
+    ns = sum(a * b + b for a, b in shapes_s)
+    out, off = [], 0
+    for _ in range(n_layers):
+        out.append((var_param[off:off + nt], var_param[off + nt:off + nt + ns]))
+        off += nt + ns
+    assert off == var_param.size
+    return out
+
+
+def nvp_g(var_param, shapes_t, shapes_s, mask, z):
+    """NVPFlow.g (:493-511)."""
+    x = z
+    for (tf, sf), m in zip(nvp_split(var_param, shapes_t, shapes_s, len(mask)), mask):
+        x_ = x * m
+        s = nn_forward(sf, shapes_s, x_, 'tanh')[0] * (1 - m)
+        t = nn_forward(tf, shapes_t, x_, 'identity')[0] * (1 - m)
+        x = x_ + (1 - m) * (x * np.exp(s) + t)
+    return x
+
+
+def nvp_f(var_param, shapes_t, shapes_s, mask, x):
+    """NVPFlow.f (:513-531): (z, log_det_J)."""
+    parts = nvp_split(var_param, shapes_t, shapes_s, len(mask))
+    log_det, z = np.zeros(x.shape[0]), x
+    for i in reversed(range(len(mask))):
+        tf, sf = parts[i]
+        m = mask[i]
+        z_ = m * z
+        s = nn_forward(sf, shapes_s, z_, 'tanh')[0] * (1 - m)
+        t = nn_forward(tf, shapes_t, z_, 'identity')[0] * (1 - m)
+        z = (1 - m) * (z - t) * np.exp(-s) + z_
+        log_det = log_det - s.sum(axis=1)
+    return z, log_det
+
+
+def nvp_log_density(var_param, shapes_t, shapes_s, mask, x, prior_param, prior_df=None):
+    """NVPFlow.log_density (:533-535) over an MFGaussian (prior_df None) or MFStudentT prior."""
+    z, ld = nvp_f(var_param, shapes_t, shapes_s, mask, x)
+    lp = mfg_log_density(prior_param, z) if prior_df is None else mft_log_density(prior_param, z, prior_df)
+    return lp + ld
+
 # --------------------------------------------------------------------------
 def psis_tail_len(n, Reff=1.0):
     """_psis.py:158: M such that cutoff_ind = -M-1."""

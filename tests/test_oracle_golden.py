@@ -369,3 +369,26 @@ def test_lr_gaussian(golden):
         assert relerr(gr, g[t + '/grad']) < 1e-9, t
         n += 1
     assert n == 12
+
+
+FLOW_NN = ((1, 4), (3, 10), (6, 8))
+FLOW_NVP = ((1, 5, None), (3, 10, None), (6, 7, 7))
+
+
+def test_flow_forward_functions(golden):
+    """NeuralNet.forward and NVPFlow g / f / log_density (approximations.py:414-429, :493-535) against the reference."""
+    g = golden('flows')
+    for dim, hidden in FLOW_NN:
+        t = 'nn_d%d' % dim
+        y, ld = vo.nn_forward(g[t + '/flat'], [(dim, hidden), (hidden, hidden), (hidden, dim)], g[t + '/x'])
+        assert relerr(y, g[t + '/y']) < TOL and relerr(ld, g[t + '/log_det_J']) < TOL
+    for dim, hidden, df in FLOW_NVP:
+        t = 'nvp_d%d' % dim
+        sh = [(dim, hidden), (hidden, dim)]
+        vp, mask = g[t + '/var_param'], g[t + '/mask']
+        assert relerr(vo.nvp_g(vp, sh, sh, mask, g[t + '/z0']), g[t + '/sample']) < TOL
+        z, ld = vo.nvp_f(vp, sh, sh, mask, g[t + '/sample'])
+        assert relerr(z, g[t + '/f_z']) < TOL and relerr(ld, g[t + '/f_logdet']) < TOL
+        assert relerr(z, g[t + '/z0']) < 1e-12                        # f inverts g
+        lq = vo.nvp_log_density(vp, sh, sh, mask, g[t + '/sample'], g[t + '/prior_param'], df)
+        assert relerr(lq, g[t + '/log_density']) < TOL

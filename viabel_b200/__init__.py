@@ -8,6 +8,7 @@ from ._psis import *  # noqa: F401,F403
 from .approximations import *  # noqa: F401,F403
 from .convenience import *  # noqa: F401,F403
 from .diagnostics import *  # noqa: F401,F403
+from .flows import *  # noqa: F401,F403
 from .models import *  # noqa: F401,F403
 from .objectives import *  # noqa: F401,F403
 from .optimization import *  # noqa: F401,F403

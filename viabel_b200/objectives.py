@@ -13,6 +13,7 @@ import torch
 from . import _lib
 from ._tensor import F64, device, is_host, to_dev
 from .approximations import LRGaussian, MultivariateT, _MeanField
+from .flows import NVPFlow
 from .models import GLMModel, Model
 from .parallel import broadcast_seed, is_distributed
 
@@ -148,6 +149,34 @@ def _lr_objective(approx, model, S, objective, alpha, var_param, base=None, seed
     return value.detach(), grad
 
 
+def _flow_objective(approx, model, S, objective, alpha, var_param, base=None, seed=None):
+    """ExclusiveKL (path-derivative form) and AlphaDivergence for NVPFlow (objectives.py:154-164, :443-460 with
+    approximations.py:493-539).  z_0 comes from the prior's Philox stream (or `base`: the prior's base draws), the
+    coupling networks and the prior's log density are differentiated by torch autograd, the model's log density and
+    gradient come from the plugin.  The family has no entropy, and the reference's plain ExclusiveKL branch cannot
+    evaluate it either (it calls approx.log_density(samples) without var_param, objectives.py:163 -> TypeError)."""
+    if objective == _lib.OBJ_EXCLUSIVE_KL:
+        raise NotImplementedError('NVPFlow has no entropy: use ExclusiveKL(..., use_path_deriv=True) or AlphaDivergence '
+                                  '(the reference raises a TypeError on this branch, objectives.py:163)')
+    vp = to_dev(var_param)
+    z0 = approx.prior_draws(S, seed=seed, base=base)
+    with torch.enable_grad():
+        lam = vp.detach().clone().requires_grad_(True)
+        x = approx.g_t(lam, z0)
+        f = _ModelLogDensity.apply(x, model)
+        if objective == _lib.OBJ_EXCLUSIVE_KL_PATH:
+            value = -(f - approx.log_density_t(vp.detach(), x)).mean()
+            (grad,) = torch.autograd.grad(value, lam)
+            return value.detach(), grad
+        lw = f - approx.log_density_t(lam, x)
+        m = lw.max().detach()
+        sv = torch.exp(lw - m) ** alpha
+        surrogate = alpha * (sv.detach() * lw).mean()                  # unnormalised, as the reference (App. A.2)
+        (grad,) = torch.autograd.grad(surrogate, lam)
+        approx.last_log_weights = lw.detach()
+        return (torch.log(sv.mean()) / alpha + m).detach(), grad
+
+
 def _to_host(value, grad):
     """(value, grad) -> (float, numpy) with ONE device-to-host copy when both are views of the same
     [1 + len(grad)] buffer (the layout _mf_objective produces), else one copy each."""
@@ -165,6 +194,8 @@ def _mf_objective(approx, model, S, objective, alpha, var_param, base=None, seed
         return _mvt_objective(approx, model, S, objective, alpha, var_param, base=base, seed=seed)
     if isinstance(approx, LRGaussian):
         return _lr_objective(approx, model, S, objective, alpha, var_param, base=base, seed=seed)
+    if isinstance(approx, NVPFlow):
+        return _flow_objective(approx, model, S, objective, alpha, var_param, base=base, seed=seed)
     if not isinstance(approx, _MeanField):
         raise NotImplementedError('only mean-field families are supported by this objective path')
     d = approx.dim
