@@ -320,6 +320,16 @@ int vb_mf_score_f64(const double* var_param, const double* x, const int64_t* idx
                     size_t workspace_bytes, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Product-target model plugins (north_star: "Gaussian/Student-t targets"): log density and per-sample gradient of
+ * kind 0: sum_j N(theta_j; loc_j, scale_j), kind 1: sum_j t_df(theta_j; loc_j, scale_j) at theta[S,d].  In the
+ * reference these are user Python log densities under autograd (models.py:27-39; tests/test_objectives.py:18-19).
+ * log_norm_const is the theta-independent part (the caller's closed form); grad may be NULL (forward only, as
+ * DISInclusiveKL needs).  logp[S], grad[S,d].
+ * ------------------------------------------------------------------------------------- */
+int vb_target_logp_grad_f64(const double* theta, int64_t S, int d, int kind, const double* loc, const double* scale,
+                            double df, double log_norm_const, double* logp, double* grad, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Streaming log-weights for vi_diagnostics (convenience.py:136-179 samples_and_log_weights): for a mean-field
  * family and a product target (target_kind 0: sum_j N(theta_j; loc_j, scale_j), 1: sum_j t_{target_df}(theta_j;
  * loc_j, scale_j)) one kernel regenerates draw i = elements offset + i*d .. + d-1 of the family's Philox stream,

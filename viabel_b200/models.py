@@ -322,6 +322,21 @@ class HierarchicalLinearRegression(Model):
         return lp, grad
 
 
+def _target_logp_grad(theta, kind, loc, scale, df, const):
+    """(log p[S], grad[S,d]) of a product target through vb_target_logp_grad_f64 (csrc/targets.cu)."""
+    th = theta.contiguous()
+    if th.dim() == 1:
+        th = th[None, :]
+    S, d = int(th.shape[0]), int(th.shape[1])
+    if d != loc.numel():
+        raise ValueError('theta has the wrong dimension')
+    lp = torch.empty(S, dtype=F64, device=th.device)
+    G = torch.empty(S, d, dtype=F64, device=th.device)
+    _lib.check(_lib.lib.vb_target_logp_grad_f64(_lib.ptr(th), S, d, kind, _lib.ptr(loc), _lib.ptr(scale), float(df),
+                                               float(const), _lib.ptr(lp), _lib.ptr(G), _lib.stream()))
+    return lp, G
+
+
 class GaussianTarget(Model):
     """Independent Gaussian target sum_j N(theta_j; mean_j, sd_j) (the reference tests' target,
     tests/test_objectives.py:18-19) with its analytic gradient."""
@@ -333,8 +348,7 @@ class GaussianTarget(Model):
         super().__init__(lambda th: self.logp_and_grad(th)[0], lambda th: self.logp_and_grad(th)[1])
 
     def logp_and_grad(self, theta):
-        z = (theta - self.mean) / self.sd
-        return -0.5 * (z * z).sum(dim=1) + self._const, -z / self.sd
+        return _target_logp_grad(theta, 0, self.mean, self.sd, 0.0, self._const)
 
     def point_derivatives(self, m, V=None, want_hessian=False):
         h = -1.0 / (self.sd * self.sd)                    # diagonal Hessian
@@ -355,10 +369,7 @@ class StudentTTarget(Model):
         super().__init__(lambda th: self.logp_and_grad(th)[0], lambda th: self.logp_and_grad(th)[1])
 
     def logp_and_grad(self, theta):
-        df = self.df
-        z = (theta - self.loc) / self.scale
-        lp = -0.5 * (df + 1.0) * torch.log1p(z * z / df).sum(dim=1) + self._const
-        return lp, -(df + 1.0) * z / ((df + z * z) * self.scale)
+        return _target_logp_grad(theta, 1, self.loc, self.scale, self.df, self._const)
 
     def point_derivatives(self, m, V=None, want_hessian=False):
         df = self.df
