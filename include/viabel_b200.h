@@ -320,6 +320,15 @@ int vb_mf_score_f64(const double* var_param, const double* x, const int64_t* idx
                     size_t workspace_bytes, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * GLM plugin, PER-SAMPLE gradients (full-rank / low-rank / flow families: models.py:27-39 under autograd in the
+ * reference).  The two GEMMs are vb_gemm_f64; this is the link step between them on a row chunk A[Nc,S] = y.(X_c
+ * Theta^T): ll_accum[s] += sum_n loglik(A[n,s]) (deterministic), A[n,s] <- y_n dloglik/da in place.
+ * ------------------------------------------------------------------------------------- */
+size_t vb_glm_link_workspace_bytes(int64_t Nc, int S);
+int vb_glm_link_f64(double* A, const double* y, int64_t Nc, int S, int link, double* ll_accum, void* workspace,
+                    size_t workspace_bytes, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Product-target model plugins (north_star: "Gaussian/Student-t targets"): log density and per-sample gradient of
  * kind 0: sum_j N(theta_j; loc_j, scale_j), kind 1: sum_j t_df(theta_j; loc_j, scale_j) at theta[S,d].  In the
  * reference these are user Python log densities under autograd (models.py:27-39; tests/test_objectives.py:18-19).

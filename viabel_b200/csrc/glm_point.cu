@@ -209,3 +209,75 @@ extern "C" int vb_glm_point_f64(const double* X, int64_t ldx, const double* y, i
   }
   return VB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-sample GLM gradients (full-rank / low-rank / flow families need grad f(theta_s) for EVERY sample: their
+// cotangents are not sums over s).  G[S,d] = sum_n y_n r[n,s] x_n is a GEMM with K = N, so the path is
+//   A[Nc,S] = y . (X_c Theta^T)      vb_gemm_f64 (row scaling fused)
+//   link     (this kernel)           ll[s] += sum_n loglik(A[n,s]);  A[n,s] <- y_n dloglik/da
+//   G       += A^T X_c               vb_gemm_f64 (transposed A)
+// over row chunks (the reference runs the user's numpy log density under autograd: models.py:27-39).  The link kernel
+// is elementwise over the chunk with deterministic column sums: block = 32 columns x 8 row groups, per-block partials,
+// a finishing kernel adds them in block order.
+// ---------------------------------------------------------------------------------------------------------------
+namespace vb {
+
+constexpr int kLinkRowsPerBlock = 512;
+
+__global__ void __launch_bounds__(256) glm_link_kernel(double* __restrict__ A, const double* __restrict__ y, int64_t Nc, int S,
+                                                       int link, double* __restrict__ part) {
+  __shared__ double red[8][33];
+  const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int s = blockIdx.x * 32 + cx;
+  const int64_t r0 = (int64_t)blockIdx.y * kLinkRowsPerBlock;
+  const int64_t r1 = r0 + kLinkRowsPerBlock < Nc ? r0 + kLinkRowsPerBlock : Nc;
+  double acc = 0.0;
+  if (s < S) {
+    for (int64_t r = r0 + rg; r < r1; r += 8) {
+      const double a = A[r * S + s];
+      double ll, dl;
+      if (link == VB_LINK_LOGISTIC) link_logistic(a, ll, dl);
+      else link_probit(a, ll, dl);
+      acc += ll;
+      A[r * S + s] = y[r] * dl;
+    }
+  }
+  red[rg][cx] = acc;
+  __syncthreads();
+  if (rg == 0 && s < S) {
+    double t = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][cx];
+    part[(size_t)blockIdx.y * S + s] = t;
+  }
+}
+
+__global__ void glm_link_finish_kernel(const double* __restrict__ part, int nblk, int S, double* __restrict__ ll) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double t = 0.0;
+  for (int b = 0; b < nblk; ++b) t += part[(size_t)b * S + s];
+  ll[s] += t;
+}
+
+}  // namespace vb
+
+extern "C" size_t vb_glm_link_workspace_bytes(int64_t Nc, int S) {
+  if (Nc <= 0 || S <= 0) return 0;
+  return (size_t)((Nc + vb::kLinkRowsPerBlock - 1) / vb::kLinkRowsPerBlock) * S * sizeof(double);
+}
+
+extern "C" int vb_glm_link_f64(double* A, const double* y, int64_t Nc, int S, int link, double* ll_accum, void* workspace,
+                               size_t workspace_bytes, cudaStream_t stream) {
+  using namespace vb;
+  if (!A || !y || !ll_accum || Nc <= 0 || S <= 0) return set_error(VB_ERR_INVALID_ARG, "glm_link: bad arguments");
+  if (link != VB_LINK_LOGISTIC && link != VB_LINK_PROBIT) return set_error(VB_ERR_UNSUPPORTED, "glm_link: logistic or probit");
+  if (!workspace || workspace_bytes < vb_glm_link_workspace_bytes(Nc, S)) return set_error(VB_ERR_WORKSPACE, "glm_link: workspace too small");
+  const int nblk = (int)((Nc + kLinkRowsPerBlock - 1) / kLinkRowsPerBlock);
+  double* part = static_cast<double*>(workspace);
+  glm_link_kernel<<<dim3((S + 31) / 32, nblk), 256, 0, stream>>>(A, y, Nc, S, link, part);
+  VB_CHECK_LAUNCH();
+  glm_link_finish_kernel<<<(S + 127) / 128, 128, 0, stream>>>(part, nblk, S, ll_accum);
+  VB_CHECK_LAUNCH();
+  return VB_OK;
+}

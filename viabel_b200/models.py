@@ -202,24 +202,29 @@ class GLMModel(Model):
         return ll, None, None
 
     def logp_and_grad(self, theta, chunk=65536):
-        """Per-sample log density [S] and gradient [S,d] (needed by full-rank families, whose d x d
-        cotangent uses every sample's gradient).  The S x d gradient accumulator does not fit on chip,
-        so this is X.Theta^T and R^T.X as library GEMMs (cuBLAS fp64) over row chunks; the fused
-        sweep above is the mean-field hot path."""
-        S = theta.shape[0]
+        """Per-sample log density [S] and gradient [S,d] (needed by full-rank / low-rank / flow families, whose
+        cotangents use every sample's gradient).  The S x d accumulator does not fit on chip, so this is two GEMMs on
+        the package's float64 DMMA kernel (vb_gemm_f64: A = y.(X_c Theta^T) with the row scaling fused, then
+        G += A^T X_c) with the link step between them (vb_glm_link_f64), over row chunks; the fused sweep above is
+        the mean-field hot path."""
+        theta = theta.contiguous()
+        S, d = int(theta.shape[0]), int(theta.shape[1])
+        lib, ptr, st = _lib.lib, _lib.ptr, _lib.stream()
         ll = torch.zeros(S, dtype=F64, device=theta.device)
         G = torch.zeros_like(theta)
-        for lo in range(0, self.N, chunk):
-            Xc, yc = self.X[lo:lo + chunk], self.y[lo:lo + chunk]
-            a = (Xc @ theta.T) * yc[:, None]
-            if self.link == _lib.LINK_LOGISTIC:
-                ll += torch.nn.functional.logsigmoid(a).sum(dim=0)
-                R = torch.sigmoid(-a)
-            else:
-                lc = torch.special.log_ndtr(a)
-                ll += lc.sum(dim=0)
-                R = torch.exp(-0.5 * a * a - 0.5 * np.log(2 * np.pi) - lc)
-            G += (R * yc[:, None]).T @ Xc
+        rows = min(int(chunk), self.N)
+        A = torch.empty(rows, S, dtype=F64, device=theta.device)
+        Gc = torch.empty_like(theta)
+        ws = torch.empty(max(8, lib.vb_glm_link_workspace_bytes(rows, S)), dtype=torch.uint8, device=theta.device)
+        ldx = self.X.stride(0)
+        for lo in range(0, self.N, rows):
+            nc = min(rows, self.N - lo)
+            Xc, yc = self.X[lo:lo + nc], self.y[lo:lo + nc]
+            _lib.check(lib.vb_gemm_f64(0, 1, nc, S, d, 1.0, ptr(Xc), ldx, ptr(theta), d, ptr(A), S, None, ptr(yc), None, None,
+                                       None, st))
+            _lib.check(lib.vb_glm_link_f64(ptr(A), ptr(yc), nc, S, self.link, ptr(ll), ptr(ws), ws.numel(), st))
+            _lib.check(lib.vb_gemm_f64(1, 0, S, d, nc, 1.0, ptr(A), S, ptr(Xc), ldx, ptr(Gc), d, None, None, None, None, None, st))
+            G += Gc
         buf = torch.cat([ll, G.reshape(-1)])
         self._allreduce(buf)
         ll, G = buf[:S], buf[S:].view_as(theta)
