@@ -320,6 +320,15 @@ int vb_mf_score_f64(const double* var_param, const double* x, const int64_t* idx
                     size_t workspace_bytes, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Mean-field families on a plugin WITHOUT a fused sweep (targets, hierarchical regression, user models): reduce the
+ * per-sample model gradients G[S,d] to gmu[j] = sum_s w_s G[s,j] and ge[j] = sum_s w_s G[s,j] base[s,j] (w NULL: 1) --
+ * the inputs of vb_mf_objective_finish_f64; in the reference this is autograd's reverse sweep through
+ * mu + sigma * eps (approximations.py:212-216 under objectives.py:161-167).
+ * ------------------------------------------------------------------------------------- */
+int vb_mf_reduce_grads_f64(const double* G, const double* w, const double* base, int64_t S, int d, double* gmu, double* ge,
+                           cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * GLM plugin, PER-SAMPLE gradients (full-rank / low-rank / flow families: models.py:27-39 under autograd in the
  * reference).  The two GEMMs are vb_gemm_f64; this is the link step between them on a row chunk A[Nc,S] = y.(X_c
  * Theta^T): ll_accum[s] += sum_n loglik(A[n,s]) (deterministic), A[n,s] <- y_n dloglik/da in place.

@@ -59,6 +59,7 @@ _PROTOS = {
     'vb_psis_dist_global': (c_int, [P, c_int64, c_int64, c_double, c_int, P, P, c_size_t, P]),
     'vb_psis_dist_apply': (c_int, [P, P, c_int64, c_int64, c_int64, c_double, c_int, c_int, P, P, c_size_t, P]),
     'vb_divergence_moments_f64': (c_int, [P, c_int64, c_double, P, P]),
+    'vb_mf_reduce_grads_f64': (c_int, [P, P, P, c_int64, c_int, P, P, P]),
     'vb_glm_link_workspace_bytes': (c_size_t, [c_int64, c_int]),
     'vb_glm_link_f64': (c_int, [P, P, c_int64, c_int, c_int, P, P, c_size_t, P]),
     'vb_target_logp_grad_f64': (c_int, [P, c_int64, c_int, c_int, P, P, c_double, c_double, P, P, P]),

@@ -284,3 +284,50 @@ extern "C" int vb_mf_objective_finish_f64(const double* var_param, const double*
   }
   return VB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Reduction of PER-SAMPLE model gradients G[S,d] (a plugin without a fused sweep: targets, hierarchical regression,
+// user models) to the two vectors the mean-field gradient assembly needs:
+//   gmu[j] = sum_s w_s G[s,j],   ge[j] = sum_s w_s G[s,j] e[s,j]          (w = 1 when NULL)
+// -- the reverse sweep autograd performs through `mu + sigma * eps` in the reference (approximations.py:212-216 under
+// objectives.py:161-167).  One block per 32 columns walks all S rows (8 row groups, fixed-order combination):
+// deterministic, coalesced 256-byte row segments.
+// ---------------------------------------------------------------------------------------------------------------
+namespace vb {
+__global__ void __launch_bounds__(256) mf_reduce_grads_kernel(const double* __restrict__ G, const double* __restrict__ w,
+                                                              const double* __restrict__ e, int64_t S, int d,
+                                                              double* __restrict__ gmu, double* __restrict__ ge) {
+  __shared__ double r0[8][33], r1[8][33];
+  const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + cx;
+  double a = 0.0, b = 0.0;
+  if (j < d) {
+    for (int64_t s = rg; s < S; s += 8) {
+      const double g = (w ? w[s] : 1.0) * G[s * d + j];
+      a += g;
+      b = fma(g, e[s * d + j], b);
+    }
+  }
+  r0[rg][cx] = a;
+  r1[rg][cx] = b;
+  __syncthreads();
+  if (rg == 0 && j < d) {
+    double ta = 0.0, tb = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      ta += r0[g][cx];
+      tb += r1[g][cx];
+    }
+    gmu[j] = ta;
+    ge[j] = tb;
+  }
+}
+}  // namespace vb
+
+extern "C" int vb_mf_reduce_grads_f64(const double* G, const double* w, const double* base, int64_t S, int d, double* gmu,
+                                      double* ge, cudaStream_t stream) {
+  if (!G || !base || !gmu || !ge || S <= 0 || d <= 0) return set_error(VB_ERR_INVALID_ARG, "mf_reduce_grads: bad arguments");
+  mf_reduce_grads_kernel<<<(d + 31) / 32, 256, 0, stream>>>(G, w, base, S, d, gmu, ge);
+  VB_CHECK_LAUNCH();
+  return VB_OK;
+}

@@ -222,8 +222,10 @@ def _mf_objective(approx, model, S, objective, alpha, var_param, base=None, seed
             total_only = objective == _lib.OBJ_EXCLUSIVE_KL and not want_logp
             return model.sweep(theta, e, w, True, ll_total_only=total_only)
         f, G = model.logp_and_grad(theta)
-        Gw = G if w is None else G * w[:, None]
-        return f.contiguous(), Gw.sum(dim=0).contiguous(), (Gw * e).sum(dim=0).contiguous()
+        G = G.to(F64).contiguous()
+        gv = torch.empty(2 * d, dtype=F64, device=dev)
+        _lib.check(lib.vb_mf_reduce_grads_f64(ptr(G), ptr(w), ptr(e), S, d, ptr(gv[:d]), ptr(gv[d:]), st))
+        return f.contiguous(), gv[:d], gv[d:]
 
     w = None
     if objective == _lib.OBJ_ALPHA:
