@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from conftest import relerr
-from _problems import logistic_problem
+from _problems import logistic_problem, target_params
 
 pytestmark = pytest.mark.gpu
 TOL64 = 1e-10
@@ -340,3 +340,30 @@ def test_faso_fused_matches_unfused(vb, monkeypatch, capsys):
     assert relerr(a['mcse_history'][0], b['mcse_history'][0]) < 1e-6
     assert relerr(a['ess_history'][0], b['ess_history'][0]) < 1e-6
     assert relerr(a['iterate_average_history'][1], b['iterate_average_history'][1]) < 1e-9
+
+
+@pytest.mark.parametrize('family', ['mfg', 'mft'])
+def test_faso_device_ring_matches_host_lists(vb, family):
+    """The general (unfused) FASO loop keeps its iterate history in a device ring and runs split-R-hat / ESS / MCSE on
+    it (csrc/faso.cu); with the ring disabled it falls back to the reference's host lists and numpy statistics
+    (optimization.py:546-605, _mc_diagnostics.py).  Same draws -> same decisions and the same iterate average."""
+    d = 5
+    mean, sd = target_params(d, seed=23)
+    model = vb.GaussianTarget(mean, sd)
+    out = {}
+    for ring in (True, False):
+        approx = vb.MFGaussian(d, seed=29) if family == 'mfg' else vb.MFStudentT(d, 9, seed=29)
+        sgo = vb.RMSProp(0.05, diagnostics=True)
+        sgo.progress = False
+        faso = vb.FASO(sgo, W_min=100, k_check=100, mcse_threshold=0.2)
+        if not ring:
+            faso._device_ring_bytes = 0
+        out[ring] = faso.optimize(2500, vb.ExclusiveKL(approx, model, 10), approx.init_param())
+    a, b = out[True], out[False]
+    assert a['k_Rhat'] == b['k_Rhat'] and a['k_conv'] == b['k_conv'] and a['k_conv'] is not None
+    n = min(len(a['value_history']), len(b['value_history']))
+    assert relerr(a['variational_param_history'][:n], b['variational_param_history'][:n]) < 1e-12
+    assert a['ess_and_mcse_k_history'][0] == b['ess_and_mcse_k_history'][0]
+    assert relerr(a['mcse_history'][0], b['mcse_history'][0]) < 1e-6
+    assert relerr(a['ess_history'][0], b['ess_history'][0]) < 1e-6
+    assert relerr(a['iterate_average_history'][1], b['iterate_average_history'][1]) < 1e-10

@@ -395,6 +395,9 @@ def _window(hist, W):
 class FASO(Optimizer):
     """Fixed-learning-rate stochastic optimisation with R-hat / MCSE stopping (:479-633)."""
 
+    #: device memory the iterate ring of the general (unfused) loop may take; 0 forces the reference's host lists
+    _device_ring_bytes = 48e9
+
     def __init__(self, sgo, *, mcse_threshold=0.1, W_min=200, ESS_min=None, k_check=None):
         if not isinstance(sgo, StochasticGradientOptimizer):
             raise ValueError('sgo must be a subclass of StochasticGradientOptimizer')
@@ -573,8 +576,19 @@ class FASO(Optimizer):
         opt_time = 0.0
         mcse = ess = None
         W_check = None
+        # Iterate history: a device ring [n_iters, P] with the batched device statistics (csrc/faso.cu) whenever it
+        # fits -- the reference's host lists + per-parameter MCSE loop (optimization.py:546, _mc_diagnostics.py:119)
+        # cannot work at BASELINE configs[3]'s 2.1 M parameters; host lists remain the fallback for huge n_iters * P
+        from ._mc_diagnostics import RingStats
+        from .approximations import MFGaussian
+        P = host_init.size
+        ring = stats = None
+        if n_iters > 0 and n_iters * P * 8 <= self._device_ring_bytes:
+            ring = torch.empty(n_iters, P, dtype=F64, device=vp.device)
+            stats = RingStats(ring, n_iters, P)
         progress = getattr(sgo, 'progress', True)
         bar = tqdm.trange(n_iters, disable=not progress)
+        done = 0
         try:
             for k in bar:
                 t0 = _time.perf_counter()
@@ -589,7 +603,11 @@ class FASO(Optimizer):
                 else:
                     direction = sgo.descent_direction(grad)
                     vp = to_dev(objective.update(vp, lr * direction))
-                hist['variational_param_history'].append(vp.clone())
+                if ring is not None:
+                    ring[k].copy_(vp.reshape(-1))
+                else:
+                    hist['variational_param_history'].append(vp.clone())
+                done = k + 1
                 if diagnostics:
                     hist['descent_dir_history'].append(direction.clone())
                 opt_time += _time.perf_counter() - t0
@@ -598,9 +616,13 @@ class FASO(Optimizer):
                     W_upper = int(0.95 * k)
                     if W_upper > self._W_min:
                         windows = np.linspace(self._W_min, W_upper, num=5, dtype=int)
-                        recent = _window(hist['variational_param_history'], W_upper)
-                        ok, best_W = R_hat_convergence_check(recent, windows)
-                        iterate_average = np.mean(recent[-best_W:], axis=0)
+                        if stats is not None:
+                            ok, best_W = stats.convergence_check(done, windows)
+                            iterate_average = stats.window_mean(done, best_W).cpu().numpy()
+                        else:
+                            recent = _window(hist['variational_param_history'], W_upper)
+                            ok, best_W = R_hat_convergence_check(recent, windows)
+                            iterate_average = np.mean(recent[-best_W:], axis=0)
                         if diagnostics:
                             hist['iterate_average_k_history'].append(k)
                             hist['iterate_average_history'].append(iterate_average)
@@ -609,14 +631,28 @@ class FASO(Optimizer):
 
                 if k_conv is not None and k - k_conv == W_check:
                     W = W_check
-                    iterates = _window(hist['variational_param_history'], W)
-                    iterate_average = np.mean(iterates, axis=0)
+                    if stats is not None:
+                        t1 = _time.perf_counter()
+                        ess, mcse, iterate_average = stats.mcse(done, W)
+                        if isinstance(objective.approx, MFGaussian):
+                            # MCSE(mu / sigma, log sigma), constant coordinates dropped (optimization.py:575-590)
+                            dim = int(P / 2)
+                            still = (ring[k - 1] == ring[k]).cpu().numpy()
+                            mean_kept = iterate_average
+                            if np.any(still):
+                                drop = np.argwhere(still)
+                                ess, mcse, mean_kept = np.delete(ess, drop), np.delete(mcse, drop), np.delete(mean_kept, drop)
+                            mcse = np.concatenate((mcse[:dim] / np.exp(mean_kept[-dim:]), mcse[-dim:]))
+                        mcse_time = _time.perf_counter() - t1
+                    else:
+                        iterates = _window(hist['variational_param_history'], W)
+                        iterate_average = np.mean(iterates, axis=0)
+                        t1 = _time.perf_counter()
+                        ess, mcse = self._mcse_of_window(iterates, objective, host_init.size)
+                        mcse_time = _time.perf_counter() - t1
                     if diagnostics and k not in hist['iterate_average_k_history']:
                         hist['iterate_average_k_history'].append(k)
                         hist['iterate_average_history'].append(iterate_average)
-                    t1 = _time.perf_counter()
-                    ess, mcse = self._mcse_of_window(iterates, objective, host_init.size)
-                    mcse_time = _time.perf_counter() - t1
                     if diagnostics:
                         hist['ess_and_mcse_k_history'].append(k)
                         hist['ess_history'].append(ess)
@@ -636,6 +672,8 @@ class FASO(Optimizer):
             bar.close()
         self._report(k_stopped, k_conv, mcse, ess)
         results = _to_numpy_results(hist)
+        if ring is not None:
+            results['variational_param_history'] = ring[:done].cpu().numpy()
         results['k_conv'] = k_conv
         results['k_Rhat'] = k_Rhat
         results['k_stopped'] = k_stopped
