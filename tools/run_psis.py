@@ -32,3 +32,22 @@ for _ in range(10):
 ts.sort()
 print('psislw n=%d: median %.4f ms  min %.4f ms  -> %.3e draws/s, %.1f%% of 6543.7 GB/s at 24 B/draw'
       % (n, ts[len(ts) // 2], ts[0], n / ts[len(ts) // 2] * 1e3, 100 * 24.0 * n / ts[len(ts) // 2] * 1e3 / 6543.7e9))
+
+# k-hat / moments only (no output array): 16 B/draw algorithmic
+_, res0, _, _ = vb.psislw_device(lw, None)
+torch.cuda.synchronize()
+print('moments-only result', res0.cpu().numpy())
+r_full, r_mom = res.cpu().numpy(), res0.cpu().numpy()
+for name, i in (('khat', 0), ('lse', 4), ('sumv', 7), ('sumexp2v', 8)):
+    print('  %-9s full %.17g  moments-only %.17g  rel diff %.2e'
+          % (name, r_full[i], r_mom[i], abs(r_full[i] - r_mom[i]) / max(abs(r_full[i]), 1e-300)))
+ts = []
+for _ in range(10):
+    e0.record()
+    vb.psislw_device(lw, None)
+    e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1))
+ts.sort()
+print('moments-only n=%d: median %.4f ms  min %.4f ms  -> %.1f%% of 6543.7 GB/s at 16 B/draw'
+      % (n, ts[len(ts) // 2], ts[0], 100 * 16.0 * n / ts[len(ts) // 2] * 1e3 / 6543.7e9))

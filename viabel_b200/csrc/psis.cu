@@ -29,7 +29,8 @@ constexpr int kDigitBits = 11;
 constexpr int kBins = 1 << kDigitBits;
 constexpr int kGather = 8192;            // boundary-bucket members selected in shared memory
 constexpr int kVBins = 8192;             // linear bins on the shifted tail values
-constexpr int kGpdSplit = 8;             // CTAs per quadrature point
+constexpr int kGpdJ = 8;                 // quadrature points per CTA of the GPD grid kernel
+constexpr int kGpdChunk = 2048;          // tail values per CTA of the GPD grid kernel (256 threads x 8, held in registers)
 
 // result[] slots (doubles, device memory)
 enum { R_KHAT = 0, R_SIGMA, R_N2, R_CUTOFF, R_LSE, R_MAX, R_STATUS, R_SUMV, R_SUMEXP2V, R_M, R_NCAND, R_SMOOTHED,
@@ -60,6 +61,12 @@ struct PsisScalars {           // device-resident control block
   unsigned int gcount;         // keys gathered from it
   unsigned long long prefix;   // exact-mode radix state
   unsigned long long kth;
+  double hist_hi;              // upper end of the candidate histogram's linear bins (sample maximum / merged maximum)
+  double tbase;                // base of pass A's exponentials: t0, or the next double above it in exact mode
+  double below_sv, below_se2;  // one-pass moments: sum (x - tbase), sum exp(2 (x - tbase)) over x below the threshold
+  double cand_sv, cand_se2;    // one-pass moments: sum v, sum exp(2 v) over candidates that are not tail
+  long long n_local;           // draws this control block's pass A covered
+  int onepass;                 // moments-only mode: no pass B, the bound moments come out of pass A
   unsigned int gpd_done;       // blocks of the GPD grid kernel that have finished
   unsigned int gather_done, count_done, values_done, select_done;      // same for the kernels whose last block runs the next (single-CTA) step
 };
@@ -207,8 +214,11 @@ __device__ unsigned long long cta_select_kth_largest(const unsigned long long* k
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void psis_init_kernel(PsisScalars* sc, int M, unsigned int* hist, unsigned int* vhist) {
+__global__ void psis_init_kernel(PsisScalars* sc, int M, unsigned int* hist, unsigned int* vhist, int onepass,
+                                 long long n_local) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
+    sc->hist_hi = -INFINITY; sc->tbase = -INFINITY; sc->below_sv = 0; sc->below_se2 = 0; sc->cand_sv = 0; sc->cand_se2 = 0;
+    sc->onepass = onepass; sc->n_local = n_local;
     sc->maxkey = 0; sc->t0key = 0; sc->cutkey = 0; sc->ncand = 0; sc->ntail = 0; sc->status = 0; sc->strict = 0;
     sc->gpd_done = 0; sc->gather_done = 0; sc->count_done = 0; sc->values_done = 0; sc->select_done = 0;
     sc->t0 = -INFINITY; sc->maxv = 0; sc->cutoff = 0; sc->expcut = 0; sc->body_below = 0; sc->body_cand = 0;
@@ -251,6 +261,26 @@ __device__ unsigned long long reg_select_kth_largest(const unsigned long long (&
   return prefix;
 }
 
+// maximum of the sample (all threads of one CTA call this): the upper end of the candidate histogram's bins
+__device__ __forceinline__ void sample_max(PsisScalars* sc, unsigned long long km, unsigned long long* smaxk /*[32]*/) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long v = __shfl_xor_sync(0xffffffffu, km, o);
+    km = v > km ? v : km;
+  }
+  if ((threadIdx.x & 31) == 0) smaxk[threadIdx.x >> 5] = km;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    km = threadIdx.x < (blockDim.x >> 5) ? smaxk[threadIdx.x] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long v = __shfl_xor_sync(0xffffffffu, km, o);
+      km = v > km ? v : km;
+    }
+    if (threadIdx.x == 0) sc->hist_hi = dkey_inv(km);
+  }
+}
+
 // candidate threshold t0 from a strided sample of m <= 16384 keys (16 per thread, in registers).
 // R <= 256: the R-th largest of the 1024 per-thread maxima, which is <= the R-th largest of the whole
 // sample (a subset's order statistic), i.e. errs on the side of a few more candidates and needs one key
@@ -262,6 +292,7 @@ __global__ void __launch_bounds__(kSelThreads) psis_sample_select_kernel(const d
   __shared__ unsigned long long sh[2];
   __shared__ unsigned int wtot[32];
   __shared__ unsigned int last;
+  __shared__ unsigned long long smaxk[32];
   if (R >= (unsigned)m) {
     if (blockIdx.x == 0 && threadIdx.x == 0) { sc->t0key = 0; sc->t0 = -INFINITY; }
     return;
@@ -287,6 +318,7 @@ __global__ void __launch_bounds__(kSelThreads) psis_sample_select_kernel(const d
     unsigned long long kmax[1] = {__ldcg(gmax + threadIdx.x)};
     // sign + exponent + 21 mantissa bits (3 digit passes) decide the threshold: relative resolution 5e-7
     key = reg_select_kth_largest<1>(kmax, R, hist, sh, wtot, 31);
+    sample_max(sc, kmax[0], smaxk);
   } else {
     unsigned long long kreg[16];
 #pragma unroll
@@ -294,10 +326,11 @@ __global__ void __launch_bounds__(kSelThreads) psis_sample_select_kernel(const d
       const int i = u * kSelThreads + threadIdx.x;
       kreg[u] = i < m ? dkey(lw[(int64_t)i * stride]) : 0ull;          // key 0 = below everything
     }
-    if (R <= 256) {
-      unsigned long long kmax[1] = {0ull};
+    unsigned long long kmax[1] = {0ull};
 #pragma unroll
-      for (int u = 0; u < 16; ++u) kmax[0] = kreg[u] > kmax[0] ? kreg[u] : kmax[0];
+    for (int u = 0; u < 16; ++u) kmax[0] = kreg[u] > kmax[0] ? kreg[u] : kmax[0];
+    sample_max(sc, kmax[0], smaxk);
+    if (R <= 256) {
       key = reg_select_kth_largest<1>(kmax, R, hist, sh, wtot);
     } else {
       key = reg_select_kth_largest<16>(kreg, R, hist, sh, wtot);
@@ -326,6 +359,7 @@ __global__ void __launch_bounds__(256) psis_pass_a_kernel(const double* __restri
   const bool all = !(t0 > -INFINITY);       // threshold -inf: everything is a candidate
   // single comparison x >= thr: in exact mode candidates are STRICTLY above t0
   const double thr = all ? -INFINITY : (sc->strict ? nextafter(t0, INFINITY) : t0);
+  if (blockIdx.x == 0 && threadIdx.x == 0) sc->tbase = t0;         // this version's sums are relative to t0 itself
   double mx = -INFINITY, acc0 = 0.0, acc1 = 0.0;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -446,20 +480,237 @@ __global__ void __launch_bounds__(256) psis_pass_a_kernel(const double* __restri
     }
 }
 
-// ---- cutoff among the candidates: one histogram pass on LINEAR value bins over [t0, max] (monotone in x,
-// so every entry of a higher bin is larger than every entry of a lower one), then an exact key select
-// of the boundary bin in shared memory
+// linear value bins of the candidate histogram over [t0, hist_hi] (monotone in x)
 __device__ __forceinline__ unsigned int cbin(double x, double lo, double scale) {
   const double f = (x - lo) * scale;
   const int b = (int)f;
   return b < 0 ? 0u : (b >= kBins ? (unsigned)(kBins - 1) : (unsigned)b);
 }
 __device__ __forceinline__ double cand_scale(const PsisScalars* sc, double& lo) {
-  const double hi = dkey_inv(sc->maxkey);
+  const double hi = sc->hist_hi;               // values above it (the sample maximum) share the top bin
   lo = sc->t0;
   return (lo > -INFINITY && hi > lo) ? (double)kBins / (hi - lo) : 0.0;      // 0: everything in bin 0
 }
 
+// exp(d) for -707.75 < d <= ~0 WITHOUT the underflow select (the caller screens the sign/exponent word of d):
+// the 7-operation form of exp_stream.  Its relative error (<= 1.4e-13 truncation, <= 1e-14 from the one-step
+// reduction for every term that matters) enters a sum whose budget is 1e-10.
+__device__ __forceinline__ double exp_core(double d, uint32_t tab) {
+  const double t = fma(d, c_expk[0], c_expk[1]);
+  const int n = __double2loint(t);
+  const double kf = t - c_expk[1];
+  const double r = fma(kf, c_expk[7], d);
+  double p = c_expk[5];
+  p = fma(p, r, c_expk[6]);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  double tj;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab + ((uint32_t)(n & (kExpTab - 1)) << 3)));
+  const double v = p * tj;                           // in [1, 2.001)
+  return __hiloint2double(__double2hiint(v) + ((n & ~(kExpTab - 1)) << 12), __double2loint(v));
+}
+
+// pass A, lean form.  What the profile of the first version showed: 150 instructions per 4 draws of which only 52
+// are double-precision arithmetic -- the rest were the two selects per draw (candidate, underflow), the -inf
+// initialisation of predicated loads, register copies of the software pipeline and 64-bit index arithmetic.  Here
+// the main loop covers only iterations in which every thread has a full quad (no predication), is unrolled by two so
+// that the prefetched quads alternate between two register sets, and accumulates all four exponentials
+// unconditionally; ONE integer test per draw on the high word of d = x - tbase (d >= 0: candidate, d < -707.75:
+// underflow; as a signed integer both are "hi >= 0xC0861E00") and one warp vote send the rare iterations that hold a
+// candidate or an underflowing term to a slow path that zeroes those terms and stages the candidates.
+// kMom: also sum d and exp(2 d) (moments-only PSIS: the CUBO / ELBO sums without a second pass over the draws).
+constexpr int kHiSpecial = (int)0xC0861E00;
+template <bool kMom>
+__global__ void __launch_bounds__(256, 4) psis_pass_a_lean_kernel(const double* __restrict__ lw, int64_t n, int64_t idx_off,
+                                                               PsisScalars* sc, double* __restrict__ cand_x,
+                                                               int64_t* __restrict__ cand_i, unsigned int cap,
+                                                               double* __restrict__ blk_sum, double* __restrict__ blk_mom,
+                                                               unsigned int* __restrict__ ghist) {
+  __shared__ double red[32];
+  __shared__ unsigned long long redk[32];
+  __shared__ double etab_s[kExpTab];
+  __shared__ double sx[8][kStage];
+  __shared__ long long si[8][kStage];
+  __shared__ unsigned int wcnt[8], cta_base;
+  const uint32_t etab = load_exp_table(etab_s);
+  const double t0 = sc->t0;
+  const bool all = !(t0 > -INFINITY);       // threshold -inf: everything is a candidate
+  // candidates are x >= tb; in exact mode (candidates STRICTLY above t0) tb is the next double above t0
+  const double tb = all ? -INFINITY : (sc->strict ? nextafter(t0, INFINITY) : t0);
+  if (blockIdx.x == 0 && threadIdx.x == 0) sc->tbase = tb;
+  // the candidate histogram (linear bins over [t0, sample maximum]) is filled here, from the slow path: one global
+  // atomic per candidate spread over 2048 bins and the whole pass (the separate histogram kernel cost 7 us)
+  double hlo;
+  const double hscale = cand_scale(sc, hlo);
+  double mx = -INFINITY, acc0 = 0.0, acc1 = 0.0, s1 = 0.0, s3 = 0.0;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  unsigned int staged = 0;                  // warp-uniform number of staged candidates
+  auto flush_warp = [&]() {
+    unsigned int base = 0;
+    if (lane == 0) base = atomicAdd(&sc->ncand, staged);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (unsigned int i = lane; i < staged; i += 32)
+      if (base + i < cap) {
+        cand_x[base + i] = sx[w][i];
+        cand_i[base + i] = si[w][i];
+      }
+    __syncwarp();
+    staged = 0;
+  };
+  auto push = [&](double x, int64_t i, bool is_cand) {
+    const unsigned int ball = __ballot_sync(0xffffffffu, is_cand);
+    if (ball) {
+      if (staged + 32 > kStage) flush_warp();
+      if (is_cand) {
+        mx = fmax(mx, x);
+        if (hscale > 0.0) atomicAdd(&ghist[cbin(x, hlo, hscale)], 1u);
+        else if (lane == __ffs(ball) - 1) atomicAdd(&ghist[0], (unsigned int)__popc(ball));    // degenerate range: one bin
+        const unsigned int slot = staged + __popc(ball & ((1u << lane) - 1));
+        sx[w][slot] = x;
+        si[w][slot] = i + idx_off;      // global draw index (idx_off = this rank's first draw)
+      }
+      staged += __popc(ball);
+    }
+  };
+  // one quad of draws; q = index of the quad
+  auto quad = [&](const double2 a, const double2 b, const int64_t q) {
+    double d0 = a.x - tb, d1 = a.y - tb, d2 = b.x - tb, d3 = b.y - tb;
+    double e0 = exp_core(d0, etab), e1 = exp_core(d1, etab), e2 = exp_core(d2, etab), e3 = exp_core(d3, etab);
+    const int h0 = __double2hiint(d0), h1 = __double2hiint(d1), h2 = __double2hiint(d2), h3 = __double2hiint(d3);
+    const bool special = (h0 >= kHiSpecial) | (h1 >= kHiSpecial) | (h2 >= kHiSpecial) | (h3 >= kHiSpecial);
+    if (__any_sync(0xffffffffu, special)) {
+      const bool c0 = a.x >= tb, c1 = a.y >= tb, c2 = b.x >= tb, c3 = b.y >= tb;
+      e0 = h0 >= kHiSpecial ? 0.0 : e0;
+      e1 = h1 >= kHiSpecial ? 0.0 : e1;
+      e2 = h2 >= kHiSpecial ? 0.0 : e2;
+      e3 = h3 >= kHiSpecial ? 0.0 : e3;
+      if (kMom) {
+        d0 = c0 ? 0.0 : d0;
+        d1 = c1 ? 0.0 : d1;
+        d2 = c2 ? 0.0 : d2;
+        d3 = c3 ? 0.0 : d3;
+      }
+      push(a.x, 4 * q, c0);
+      push(a.y, 4 * q + 1, c1);
+      push(b.x, 4 * q + 2, c2);
+      push(b.y, 4 * q + 3, c3);
+    }
+    acc0 += e0 + e2;
+    acc1 += e1 + e3;
+    if (kMom) {
+      s1 += (d0 + d1) + (d2 + d3);
+      s3 = fma(e0, e0, s3);
+      s3 = fma(e1, e1, s3);
+      s3 = fma(e2, e2, s3);
+      s3 = fma(e3, e3, s3);
+    }
+  };
+  int64_t done = 0;
+  if ((reinterpret_cast<uintptr_t>(lw) & 31) == 0 && !all) {
+    const int64_t full = (n / 4) / nthreads;          // iterations in which EVERY thread owns a quad
+    if (full > 0) {
+      const double2* p = reinterpret_cast<const double2*>(lw) + 2 * tid;
+      const int64_t st = 2 * nthreads;
+      double2 a = __ldcs(p), b = __ldcs(p + 1);
+      int64_t q = tid, it = 0;
+      for (; it + 2 <= full; it += 2) {
+        const double2 c = __ldcs(p + st), d = __ldcs(p + st + 1);
+        quad(a, b, q);
+        p += 2 * st;
+        if (it + 2 < full) {
+          a = __ldcs(p);
+          b = __ldcs(p + 1);
+        }
+        quad(c, d, q + nthreads);
+        q += 2 * nthreads;
+      }
+      if (it < full) quad(a, b, q);
+    }
+    done = full * nthreads * 4;
+  }
+  {   // the rest (< 4 draws per thread), or the whole array when unaligned / when everything is a candidate
+    const int64_t rest = n - done;
+    const int64_t iters = (rest + nthreads - 1) / nthreads;
+    for (int64_t it = 0; it < iters; ++it) {
+      const int64_t i = done + it * nthreads + tid;
+      const bool v = i < n;
+      const double x = v ? lw[i] : -INFINITY;
+      const bool c = v && (all || x >= tb);
+      if (v && !c) {
+        const double d = x - tb;
+        const double e = (unsigned int)__double2hiint(d) >= 0xC0861E00u ? 0.0 : exp_core(d, etab);
+        acc0 += e;
+        if (kMom) {
+          s1 += d;
+          s3 = fma(e, e, s3);
+        }
+      }
+      push(x, i, c);
+    }
+  }
+  // block reductions and the single per-CTA flush of the staged candidates
+  double acc = warp_sum(acc0 + acc1);
+  if (kMom) {
+    s1 = warp_sum(s1);
+    s3 = warp_sum(s3);
+  }
+  unsigned long long mk = dkey(mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(0xffffffffu, mk, o);
+    mk = t > mk ? t : mk;
+  }
+  if (lane == 0) {
+    red[w] = acc;
+    redk[w] = mk;
+    wcnt[w] = staged;
+    if (kMom) {
+      red[8 + w] = s1;
+      red[16 + w] = s3;
+    }
+  }
+  __syncthreads();
+  if (w == 0) {
+    double a = lane < 8 ? red[lane] : 0.0;
+    unsigned long long k = lane < 8 ? redk[lane] : 0ull;
+    unsigned int c = lane < 8 ? wcnt[lane] : 0u;
+    a = warp_sum(a);
+    double m1 = 0.0, m3 = 0.0;
+    if (kMom) {
+      m1 = warp_sum(lane < 8 ? red[8 + lane] : 0.0);
+      m3 = warp_sum(lane < 8 ? red[16 + lane] : 0.0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long t = __shfl_xor_sync(0xffffffffu, k, o);
+      k = t > k ? t : k;
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) {
+      blk_sum[blockIdx.x] = a;
+      if (kMom) {
+        blk_mom[2 * blockIdx.x] = m1;
+        blk_mom[2 * blockIdx.x + 1] = m3;
+      }
+      if (k > dkey(-INFINITY)) atomicMax(&sc->maxkey, k);
+      cta_base = c ? atomicAdd(&sc->ncand, c) : 0u;
+    }
+  }
+  __syncthreads();
+  unsigned int base = cta_base;
+  for (int u = 0; u < w; ++u) base += wcnt[u];
+  for (unsigned int i = lane; i < staged; i += 32)
+    if (base + i < cap) {
+      cand_x[base + i] = sx[w][i];
+      cand_i[base + i] = si[w][i];
+    }
+}
+
+// ---- cutoff among the candidates: one histogram pass on LINEAR value bins over [t0, max] (monotone in x,
+// so every entry of a higher bin is larger than every entry of a lower one), then an exact key select
+// of the boundary bin in shared memory
 __global__ void __launch_bounds__(256) psis_cand_hist_kernel(PsisScalars* sc, const double* __restrict__ cand_x,
                                                              unsigned int cap, unsigned int* __restrict__ ghist) {
   PDL_SYNC();
@@ -486,13 +737,23 @@ __global__ void __launch_bounds__(256) psis_cand_hist_kernel(PsisScalars* sc, co
 // that bin into a small global buffer
 // cutoff = (M+1)-th largest candidate (one CTA of kSelThreads threads; run by the last block of the gather kernel)
 __device__ __forceinline__ void cutoff_block(PsisScalars* sc, const double* cand_x, unsigned int cap,
-                                             const unsigned long long* gbuf, const double* blk_sum, int nblk,
+                                             const unsigned long long* gbuf, const double* blk_sum,
+                                             const double* blk_mom, int nblk,
                                              unsigned int* hist, unsigned long long* sh, unsigned int* wtot, double* red) {
   const unsigned int C = sc->ncand;
   const int M = sc->M;
   double s = 0.0;
   for (int b = threadIdx.x; b < nblk; b += blockDim.x) s += blk_sum[b];
   s = block_sum(s, red);
+  double m1 = 0.0, m3 = 0.0;
+  if (sc->onepass) {            // one-pass moments: pass A's per-CTA sums of d and exp(2 d)
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+      m1 += blk_mom[2 * b];
+      m3 += blk_mom[2 * b + 1];
+    }
+    m1 = block_sum(m1, red);
+    m3 = block_sum(m3, red);
+  }
   // exact mode collects only values strictly above t0: when there are none the maximum is t0 itself
   const unsigned long long maxkey = (sc->strict && sc->maxkey < sc->t0key) ? sc->t0key : sc->maxkey;
   const double maxv = dkey_inv(maxkey);
@@ -507,7 +768,23 @@ __device__ __forceinline__ void cutoff_block(PsisScalars* sc, const double* cand
     }
     const unsigned int bstar = sc->bstar, members = sc->members;
     const unsigned long long need = sc->need;
-    if (members <= kGather) {
+    if (members <= kSelThreads) {
+      // the usual case (a boundary bin of 1 / 2048 of the candidate range holds a few hundred keys): one key per
+      // thread, rank by counting against the others in shared memory -- one step instead of six radix passes
+      unsigned long long* sk = reinterpret_cast<unsigned long long*>(hist);      // kBins x 4 bytes = 1024 keys
+      const unsigned long long key = threadIdx.x < members ? gbuf[threadIdx.x] : 0ull;
+      sk[threadIdx.x] = key;
+      __syncthreads();
+      unsigned int gt = 0, ge = 0;
+      for (unsigned int j = 0; j < members; ++j) {
+        const unsigned long long o = sk[j];
+        gt += o > key;
+        ge += o >= key;
+      }
+      if (threadIdx.x < members && gt < need && need <= ge) sh[0] = key;         // ties write the same key
+      __syncthreads();
+      cutkey = sh[0];
+    } else if (members <= kGather) {
       // exact 64-bit radix select over the gathered boundary bin (<= 8192 keys, L2 resident)
       cutkey = cta_select_kth_largest(gbuf, members, need, hist, sh, wtot);
     } else {
@@ -550,15 +827,19 @@ __device__ __forceinline__ void cutoff_block(PsisScalars* sc, const double* cand
     sc->cutoff = cutoff;
     sc->expcut = exp(cutoff);
     sc->body_below = s;
+    sc->below_sv = m1;
+    sc->below_se2 = m3;
     sc->vscale = (cutoff < 0.0) ? (double)kVBins / (-cutoff) : 0.0;
   }
 }
 
 __global__ void __launch_bounds__(kSelThreads) psis_cand_gather_kernel(PsisScalars* sc, const double* __restrict__ cand_x,
                                                                         unsigned int cap, const unsigned int* __restrict__ ghist,
-                                                                        unsigned long long* gbuf, const double* blk_sum, int nblk) {
+                                                                        unsigned long long* gbuf, const double* blk_sum,
+                                                                        const double* blk_mom, int nblk) {
   PDL_SYNC();
-  __shared__ unsigned int hist[kBins];
+  __shared__ __align__(8) unsigned int hist[kBins];      // cutoff_block reuses it as 1024 64-bit keys
+  static_assert(kBins * sizeof(unsigned int) >= kSelThreads * sizeof(unsigned long long), "key buffer");
   __shared__ unsigned long long sh[2];
   __shared__ unsigned int wtot[32];
   __shared__ double red[32];
@@ -594,7 +875,7 @@ __global__ void __launch_bounds__(kSelThreads) psis_cand_gather_kernel(PsisScala
   __syncthreads();
   if (last) {
     __threadfence();
-    cutoff_block(sc, cand_x, cap, gbuf, blk_sum, nblk, hist, sh, wtot, red);
+    cutoff_block(sc, cand_x, cap, gbuf, blk_sum, blk_mom, nblk, hist, sh, wtot, red);
   }
 }
 
@@ -651,17 +932,29 @@ __global__ void __launch_bounds__(kSelThreads) psis_tail_count_kernel(PsisScalar
   if (sc->status) return;
   const unsigned int C = sc->ncand;
   const double maxv = sc->maxv, cutoff = sc->cutoff, vscale = sc->vscale;
-  double acc = 0.0;
+  const bool onepass = sc->onepass != 0;
+  double acc = 0.0, accv = 0.0, acc2 = 0.0;
   for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < C; i += gridDim.x * blockDim.x) {
     const double v = cand_x[i] - maxv;
     if (v > cutoff) {
       atomicAdd(&vhist[vbin(v, cutoff, vscale)], 1u);
     } else {
-      acc += exp(v);
+      const double e = exp(v);
+      acc += e;
+      accv += v;
+      acc2 = fma(e, e, acc2);
     }
   }
   acc = block_sum(acc, red);
   if (threadIdx.x == 0 && acc != 0.0) atomicAdd(&sc->body_cand, acc);
+  if (onepass) {
+    accv = block_sum(accv, red);
+    acc2 = block_sum(acc2, red);
+    if (threadIdx.x == 0) {
+      atomicAdd(&sc->cand_sv, accv);
+      atomicAdd(&sc->cand_se2, acc2);
+    }
+  }
   // the last block to finish scans the bin counts into offsets (saves a single-CTA launch)
   __threadfence();
   __syncthreads();
@@ -753,12 +1046,11 @@ __global__ void __launch_bounds__(256) psis_tail_index_order_kernel(PsisScalars*
 }
 
 // profile likelihood weights -> posterior mean of b (:288-312)
-__device__ __forceinline__ void gpd_weights(PsisScalars* sc, const double* bs, const double* part, double* Ls, int N, int m,
-                                            double* red) {
+__device__ __forceinline__ void gpd_weights(PsisScalars* sc, const double* bs, const double* part, int nparts, double* Ls,
+                                            int N, int m, double* red) {
   for (int j = threadIdx.x; j < m; j += blockDim.x) {
     double ksum = 0.0;
-#pragma unroll
-    for (int u = 0; u < kGpdSplit; ++u) ksum += __ldcg(part + j * kGpdSplit + u);     // written by other blocks
+    for (int u = 0; u < nparts; ++u) ksum += __ldcg(part + j * nparts + u);     // written by other blocks
     const double kj = ksum / (double)N;
     double L = __ldcg(bs + j) / kj;
     L = log(-L);
@@ -809,39 +1101,64 @@ struct LogProd {
 };
 
 // ---- generalised Pareto fit (_psis.py:212-332), split so that no stage is a long serial loop --------
-// partial sums of log1p(-b_j x_i): grid = (m, kGpdSplit)
+// partial sums of log1p(-b_j x_i).  grid = (ceil(mgrid / kGpdJ), ceil(tail_cap / kGpdChunk)): a CTA keeps 2048 tail
+// values in registers (8 per thread, one batch of independent loads) and evaluates kGpdJ quadrature points on them, so
+// the tail array crosses L2 -> SM m / 8 times instead of m times (the first version -- one CTA per (j, eighth of the
+// tail) -- moved 49 MB through L2 and ran in two waves: 25 us; this form 6 MB, one wave).  Each thread's 8 terms of
+// one quadrature point become ONE log of their product (see LogProd).
 __global__ void __launch_bounds__(256) psis_gpd_grid_kernel(PsisScalars* sc, const double* __restrict__ sorted_x,
                                                             double* __restrict__ bs, double* __restrict__ part,
                                                             double* __restrict__ Ls) {
   PDL_SYNC();
   __shared__ double red[32];
+  __shared__ double wpart[8][kGpdJ];
+  __shared__ unsigned int last;
   if (sc->status) return;
   const int N = (int)sc->ntail;
   if (N <= 4) return;
   const int m = 30 + (int)sqrt((double)N);
-  const int j = blockIdx.x;
-  if (j >= m) return;
+  const int nparts = gridDim.y;
+  const int j0 = blockIdx.x * kGpdJ;
+  if (j0 >= m) return;                                   // (mgrid is sized for the largest possible tail)
+  const int jgroups = (m + kGpdJ - 1) / kGpdJ;
   const double xq = sorted_x[(int)(N / 4.0 + 0.5) - 1];
   const double xmax = sorted_x[N - 1];
-  double b = 1.0 - sqrt((double)m / ((double)(j + 1) - 0.5));
-  b /= 3.0 * xq;
-  b += 1.0 / xmax;
-  const double nb = -b;
-  double acc = 0.0;
-  LogProd lp;
-  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < N; i += gridDim.y * blockDim.x) lp.add(nb, sorted_x[i]);
-  acc = block_sum(lp.result(), red);
-  __shared__ unsigned int last;
-  if (threadIdx.x == 0) {
-    part[j * kGpdSplit + blockIdx.y] = acc;
-    if (blockIdx.y == 0) bs[j] = b;
-    __threadfence();
-    last = atomicAdd(&sc->gpd_done, 1u) == (unsigned)(m * kGpdSplit) - 1u;
+  const int base = blockIdx.y * kGpdChunk;
+  double x[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int i = base + u * 256 + (int)threadIdx.x;
+    x[u] = i < N ? sorted_x[i] : 0.0;                    // a term 1 + nb * 0 = 1 leaves the product alone
   }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int jj = 0; jj < kGpdJ; ++jj) {
+    const int j = j0 + jj;
+    double b = 1.0 - sqrt((double)m / ((double)(j + 1) - 0.5));
+    b /= 3.0 * xq;
+    b += 1.0 / xmax;
+    if (blockIdx.y == 0 && threadIdx.x == 0 && j < m) bs[j] = b;
+    const double nb = j < m ? -b : 0.0;
+    double prod = fma(nb, x[0], 1.0);
+#pragma unroll
+    for (int u = 1; u < 8; ++u) prod *= fma(nb, x[u], 1.0);
+    const double v = warp_sum(log(prod));
+    if (lane == 0) wpart[w][jj] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kGpdJ && j0 + (int)threadIdx.x < m) {
+    double a = 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a += wpart[u][threadIdx.x];
+    part[(j0 + threadIdx.x) * nparts + blockIdx.y] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&sc->gpd_done, 1u) == (unsigned)(jgroups * nparts) - 1u;
   __syncthreads();
   if (last) {              // every partial sum is visible: the last block turns them into the posterior mean of b
     __threadfence();
-    gpd_weights(sc, bs, part, Ls, N, m, red);
+    gpd_weights(sc, bs, part, nparts, Ls, N, m, red);
   }
 }
 
@@ -889,8 +1206,15 @@ __device__ __forceinline__ void lse_warp(PsisScalars* sc, const double* part3, i
   sv = warp_sum(sv);
   se = warp_sum(se);
   if (threadIdx.x != 0) return;
-  const double below = sc->body_below > 0.0 ? sc->body_below * exp(sc->t0 - sc->maxv) : 0.0;
+  const double below = sc->body_below > 0.0 ? sc->body_below * exp(sc->tbase - sc->maxv) : 0.0;
   const double total = below + sc->body_cand + ts;
+  if (sc->onepass) {
+    // moments of v = x - max over ALL draws from pass A's sums (relative to tbase), the candidate list and the tail
+    const double nbelow = (double)(sc->n_local - (long long)sc->ncand);
+    const double shift = sc->tbase - sc->maxv;
+    result[R_SUMV] = (nbelow > 0.0 ? sc->below_sv + nbelow * shift : 0.0) + sc->cand_sv + sv;
+    result[R_SUMEXP2V] = (sc->below_se2 > 0.0 ? sc->below_se2 * exp(2.0 * shift) : 0.0) + sc->cand_se2 + se;
+  }
   sc->tail_sum = ts;
   sc->sumv = sv;
   sc->sumexp2v = se;
@@ -928,6 +1252,7 @@ __global__ void __launch_bounds__(256) psis_tail_values_kernel(PsisScalars* sc, 
     k = k * (double)N / ((double)N + 10.0) + 5.0 / ((double)N + 10.0);
   }
   const bool smooth = (k >= 1.0 / 3.0) && !isinf(k);
+  const bool onepass = sc->onepass != 0;
   const double expcut = sc->expcut;
   double ts = 0.0, sv = 0.0, se = 0.0;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x) {
@@ -940,7 +1265,7 @@ __global__ void __launch_bounds__(256) psis_tail_values_kernel(PsisScalars* sc, 
     }
     tail_out[r] = v;
     ts += exp(v);
-    if (smooth) {          // moments of the smoothed tail (pass B covers everything it writes itself)
+    if (smooth || onepass) {          // moments of the tail (pass B covers everything it writes itself)
       sv += v;
       se += exp(2.0 * v);
     }
@@ -1221,7 +1546,7 @@ __global__ void __launch_bounds__(256) dbound_sum_kernel(const double* __restric
 
 // ---------------------------------------------------------------------------------------------
 struct PsisPlan {
-  int M, m_sample, grid, tail_cap, mgrid, kparts, vparts;
+  int M, m_sample, grid, tail_cap, mgrid, gchunks, kparts, vparts;
   unsigned int cap, cap_local, R;
   int64_t stride;
   size_t off_sc, off_candx, off_candi, off_blk, off_tmpv, off_tmpi, off_tmpb, off_tailv, off_taili, off_tailout,
@@ -1271,7 +1596,8 @@ static void psis_plan(int64_t n, double reff, PsisPlan& p, int64_t n_global = 0,
   p.off_idxsorted = take(sizeof(int64_t) * p.tail_cap);
   p.off_orderrank = take(sizeof(int) * p.tail_cap);
   p.off_bs = take(sizeof(double) * p.mgrid);
-  p.off_part = take(sizeof(double) * p.mgrid * kGpdSplit);
+  p.gchunks = (p.tail_cap + kGpdChunk - 1) / kGpdChunk;
+  p.off_part = take(sizeof(double) * (p.mgrid + kGpdJ) * p.gchunks);
   p.off_Ls = take(sizeof(double) * p.mgrid);
   p.off_kpart = take(sizeof(double) * p.kparts);
   p.off_part3 = take(sizeof(double) * 3 * p.vparts);
@@ -1354,9 +1680,15 @@ static void psis_ptrs(char* ws, const PsisPlan& p, PsisPtrs& q) {
 }
 
 // stage 1 (per rank): threshold, pass A over this rank's draws
+// VB_PSIS_PASS_A=v1 selects the first version of the kernel (A/B timing)
+static bool pass_a_v1() {
+  static const bool v1 = [] { const char* e = getenv("VB_PSIS_PASS_A"); return e && e[0] == 'v' && e[1] == '1'; }();
+  return v1;
+}
+
 static int psis_stage_local(const double* lw, int64_t n, int64_t idx_off, int exact, const PsisPlan& p, PsisPtrs& q,
-                            cudaStream_t stream) {
-  psis_init_kernel<<<8, 1024, 0, stream>>>(q.sc, p.M, q.ghist, q.vhist);
+                            cudaStream_t stream, int onepass = 0) {
+  psis_init_kernel<<<8, 1024, 0, stream>>>(q.sc, p.M, q.ghist, q.vhist, onepass, (long long)n);
   VB_CHECK_LAUNCH();
   if (!exact) {
     psis_sample_select_kernel<<<(p.R <= 256 && p.m_sample == kSampleMax) ? kSampleMax / kSelThreads : 1, kSelThreads, 0, stream>>>(
@@ -1377,17 +1709,23 @@ static int psis_stage_local(const double* lw, int64_t n, int64_t idx_off, int ex
       mask |= (unsigned long long)((1u << bits) - 1) << shift;
     }
   }
-  psis_pass_a_kernel<<<p.grid, 256, 0, stream>>>(lw, n, idx_off, q.sc, q.candx, q.candi, p.cap, q.blk);
+  if (onepass)
+    psis_pass_a_lean_kernel<true><<<p.grid, 256, 0, stream>>>(lw, n, idx_off, q.sc, q.candx, q.candi, p.cap, q.blk, q.mom, q.ghist);
+  else if (pass_a_v1())
+    psis_pass_a_kernel<<<p.grid, 256, 0, stream>>>(lw, n, idx_off, q.sc, q.candx, q.candi, p.cap, q.blk);
+  else
+    psis_pass_a_lean_kernel<false><<<p.grid, 256, 0, stream>>>(lw, n, idx_off, q.sc, q.candx, q.candi, p.cap, q.blk, q.mom, q.ghist);
   VB_CHECK_LAUNCH();
   return VB_OK;
 }
 
 // stage 2 (replicated): cutoff, tail ranking, GPD fit, smoothed values, log-sum-exp from the candidate list
-static int psis_stage_select(const PsisPlan& p, PsisPtrs& q, int nblk, int raw, cudaStream_t stream) {
+static int psis_stage_select(const PsisPlan& p, PsisPtrs& q, int nblk, int raw, cudaStream_t stream, bool need_hist) {
   const int cgrid = sm_count() * 2;
-  VB_CUDA(launch_pdl(psis_cand_hist_kernel, dim3(cgrid), dim3(256), stream, q.sc, q.candx, p.cap, q.ghist));
+  if (need_hist)      // the lean pass A has filled the histogram already
+    VB_CUDA(launch_pdl(psis_cand_hist_kernel, dim3(cgrid), dim3(256), stream, q.sc, q.candx, p.cap, q.ghist));
   VB_CUDA(launch_pdl(psis_cand_gather_kernel, dim3(cgrid / 4 > 0 ? cgrid / 4 : 1), dim3(kSelThreads), stream, q.sc, q.candx, p.cap, q.ghist, q.gbuf,
-                     q.blk, nblk));
+                     q.blk, q.mom, nblk));
   VB_CUDA(launch_pdl(psis_tail_count_kernel, dim3(cgrid / 4 > 0 ? cgrid / 4 : 1), dim3(kSelThreads), stream, q.sc, q.candx, q.vhist, q.voff));
   VB_CUDA(launch_pdl(psis_tail_place_kernel, dim3(cgrid), dim3(256), stream, q.sc, q.candx, q.candi, q.voff, q.vcur, q.tmpv, q.tmpi, q.tmpb,
                                                     (unsigned)p.tail_cap, raw));
@@ -1395,8 +1733,8 @@ static int psis_stage_select(const PsisPlan& p, PsisPtrs& q, int nblk, int raw, 
 }
 
 static int psis_stage_global(const PsisPlan& p, PsisPtrs& q, int nblk, double* result, int64_t* tail_idx,
-                             int32_t* tail_rank, cudaStream_t stream) {
-  int rc = psis_stage_select(p, q, nblk, 0, stream);
+                             int32_t* tail_rank, cudaStream_t stream, bool need_hist) {
+  int rc = psis_stage_select(p, q, nblk, 0, stream, need_hist);
   if (rc) return rc;
   int blocks = (p.tail_cap + 255) / 256;
   if (blocks > sm_count() * 4) blocks = sm_count() * 4;
@@ -1404,7 +1742,7 @@ static int psis_stage_global(const PsisPlan& p, PsisPtrs& q, int nblk, double* r
   if (tail_idx && tail_rank) {
     VB_CUDA(launch_pdl(psis_tail_index_order_kernel, dim3(blocks), dim3(256), stream, q.sc, q.taili, tail_idx, tail_rank));
   }
-  VB_CUDA(launch_pdl(psis_gpd_grid_kernel, dim3(p.mgrid, kGpdSplit), dim3(256), stream, q.sc, q.sorted, q.bs, q.part, q.Ls));
+  VB_CUDA(launch_pdl(psis_gpd_grid_kernel, dim3((p.mgrid + kGpdJ - 1) / kGpdJ, p.gchunks), dim3(256), stream, q.sc, q.sorted, q.bs, q.part, q.Ls));
   VB_CUDA(launch_pdl(psis_gpd_k_kernel, dim3(p.kparts), dim3(256), stream, q.sc, q.sorted, q.kpart));
   VB_CUDA(launch_pdl(psis_tail_values_kernel, dim3(p.vparts), dim3(256), stream, q.sc, q.kpart, p.kparts, q.tailv, q.tailout, q.part3, result));
   return VB_OK;
@@ -1462,7 +1800,7 @@ __global__ void __launch_bounds__(256) psis_export_kernel(const PsisScalars* sc,
     idx[j] = j < nt ? tmp_i[j] : -1;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const double below = sc->body_below > 0.0 ? sc->body_below * exp(sc->t0 - maxv) : 0.0;
+    const double below = sc->body_below > 0.0 ? sc->body_below * exp(sc->tbase - maxv) : 0.0;
     double body = below + sc->body_cand - (double)(K - nt) * exp(c - maxv);     // the copies of c_r travel in the record
     if (!(body > 0.0)) body = 0.0;
     rec[0] = maxv; rec[1] = c; rec[2] = log(body); rec[3] = (double)K;
@@ -1491,6 +1829,8 @@ __global__ void __launch_bounds__(256) psis_import_kernel(PsisScalars* sc, const
     }
     sc->maxkey = dkey(mx);
     sc->t0 = t0;
+    sc->hist_hi = mx;
+    sc->tbase = t0;
     sc->t0key = dkey(t0);
     sc->ncand = bad ? 0u : total;
     sc->strict = 0;
@@ -1529,8 +1869,12 @@ extern "C" int vb_psislw_f64(const double* lw, double* out, int64_t n, double re
   PsisPtrs q;
   psis_ptrs(static_cast<char*>(workspace), p, q);
   VB_CUDA(cudaMemsetAsync(result, 0, sizeof(double) * R_COUNT, stream));
-  if ((rc = psis_stage_local(lw, n, 0, exact, p, q, stream))) return rc;
-  if ((rc = psis_stage_global(p, q, p.grid, result, tail_idx, tail_rank, stream))) return rc;
+  // no output array: k-hat and the bound moments from ONE pass over the draws (VB_PSIS_ONEPASS=0: the two-pass form)
+  static const bool allow_onepass = [] { const char* e = getenv("VB_PSIS_ONEPASS"); return !(e && e[0] == '0'); }();
+  const int onepass = (!out && allow_onepass) ? 1 : 0;
+  if ((rc = psis_stage_local(lw, n, 0, exact, p, q, stream, onepass))) return rc;
+  if ((rc = psis_stage_global(p, q, p.grid, result, tail_idx, tail_rank, stream, pass_a_v1() && !onepass))) return rc;
+  if (onepass) return VB_OK;
   return psis_stage_apply(lw, out, n, 0, 1, p, q, result, stream);
 }
 
@@ -1564,7 +1908,7 @@ extern "C" int vb_psis_dist_local(const double* lw, int64_t n_local, int64_t idx
   psis_ptrs(static_cast<char*>(workspace), p, q);
   const bool small = n_local < (int64_t)p.M + 1;         // the sample is the whole shard and everything is a candidate
   if ((rc = psis_stage_local(lw, n_local, idx_off, small ? 0 : exact, p, q, stream))) return rc;
-  if (!small && (rc = psis_stage_select(p, q, p.grid, 1, stream))) return rc;
+  if (!small && (rc = psis_stage_select(p, q, p.grid, 1, stream, pass_a_v1()))) return rc;
   int blocks = (p.M + 1 + 255) / 256;
   if (blocks > sm_count()) blocks = sm_count();
   psis_export_kernel<<<blocks, 256, 0, stream>>>(q.sc, q.tmpv, q.tmpi, q.candx, q.candi, small ? 1 : 0, record);
@@ -1581,7 +1925,7 @@ extern "C" int vb_psis_dist_global(const double* records, int64_t n_local, int64
   PsisPtrs q;
   psis_ptrs(static_cast<char*>(workspace), p, q);
   VB_CUDA(cudaMemsetAsync(result, 0, sizeof(double) * R_COUNT, stream));
-  psis_init_kernel<<<8, 1024, 0, stream>>>(q.sc, p.M, q.ghist, q.vhist);
+  psis_init_kernel<<<8, 1024, 0, stream>>>(q.sc, p.M, q.ghist, q.vhist, 0, (long long)n_local);
   VB_CHECK_LAUNCH();
   const int reclen = 4 + 2 * (p.M + 1);
   int bx = (p.M + 1 + 255) / 256;
@@ -1589,7 +1933,7 @@ extern "C" int vb_psis_dist_global(const double* records, int64_t n_local, int64
   psis_import_kernel<<<dim3(bx, world > 64 ? 64 : world), 256, 0, stream>>>(q.sc, records, world, reclen, q.candx, q.candi,
                                                                           q.blk, p.grid);
   VB_CHECK_LAUNCH();
-  return psis_stage_global(p, q, p.grid, result, nullptr, nullptr, stream);
+  return psis_stage_global(p, q, p.grid, result, nullptr, nullptr, stream, true);
 }
 
 extern "C" int vb_psis_dist_apply(const double* lw, double* out, int64_t n_local, int64_t idx_off, int64_t n_global,
