@@ -100,6 +100,42 @@ def test_psislw_modes(vb, golden):
         vb.psislw(np.zeros((2, 2, 2)))
 
 
+@pytest.mark.parametrize('name', ['t5_t7_1e5', 't3_t30_2e5', 't50_t5_1e5', 'tiny_20', 'small_100', 'ties_3e4',
+                                  'underflow_5000', 'all_equal_50', 'big_1e6'])
+@pytest.mark.parametrize('variant', ['plain', 'exact', 'unaligned'])
+def test_psislw_moments_only_one_pass(vb, vo, name, variant):
+    """k-hat / bounds only (no output array) takes ONE pass over the draws: its k-hat, cutoff, log-sum-exp and the
+    CUBO / ELBO sums must equal the two-pass results and the oracle's (moments of v = out + lse) to 1e-10."""
+    lw = psis_case(name)
+    if variant == 'unaligned':
+        buf = torch.zeros(lw.size + 1, device='cuda', dtype=torch.float64)
+        buf[1:] = torch.as_tensor(lw, device='cuda')
+        t = buf[1:]                                        # 8-byte aligned only: the scalar loop
+    else:
+        t = torch.as_tensor(lw, device='cuda')
+    exact = variant == 'exact'
+    out = torch.empty(lw.size, device='cuda', dtype=torch.float64)
+    _, res2, _, _ = vb.psislw_device(t, out, exact=exact)
+    _, res1, _, _ = vb.psislw_device(t, None, exact=exact)
+    r1, r2 = res1.cpu().numpy(), res2.cpu().numpy()
+    assert r1[6] == r2[6]
+    if r2[6] != 0:                                         # sampled threshold missed (tiny / tied inputs): rerun exact
+        _, res2, _, _ = vb.psislw_device(t, out, exact=True)
+        _, res1, _, _ = vb.psislw_device(t, None, exact=True)
+        r1, r2 = res1.cpu().numpy(), res2.cpu().numpy()
+    assert r1[6] == 0 and r2[6] == 0
+    for slot in (0, 1, 2, 3, 4, 5, 9, 11):                 # khat, sigma, n2, cutoff, lse, max, M, smoothed
+        assert (r1[slot] == r2[slot]) or relerr(r1[slot], r2[slot]) < 1e-12, (slot, r1[slot], r2[slot])
+    with np.errstate(all='ignore'):
+        o_ref, k_ref = vo.psislw_1d(lw)[:2]
+    v = o_ref + r2[4]
+    sumv, sume = v.sum(), np.exp(2.0 * v).sum()
+    for got in (r1, r2):
+        assert relerr(got[7], sumv) < TOL and relerr(got[8], sume) < TOL, (got[7], sumv, got[8], sume)
+    if np.isfinite(k_ref):
+        assert relerr(r1[0], k_ref) < TOL
+
+
 @pytest.mark.parametrize('n,dfp,dfq', [(3000000, 4, 9), (10000000, 3, 30)])
 def test_psislw_large_vs_oracle(vb, vo, n, dfp, dfq):
     g = torch.Generator(device='cuda')

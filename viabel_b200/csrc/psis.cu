@@ -540,8 +540,13 @@ __global__ void __launch_bounds__(256, 4) psis_pass_a_lean_kernel(const double* 
   if (blockIdx.x == 0 && threadIdx.x == 0) sc->tbase = tb;
   // the candidate histogram (linear bins over [t0, sample maximum]) is filled here, from the slow path: one global
   // atomic per candidate spread over 2048 bins and the whole pass (the separate histogram kernel cost 7 us)
-  double hlo;
-  const double hscale = cand_scale(sc, hlo);
+  __shared__ double hpar[2];                // read on the slow path only: keeps two doubles out of the hot loop's registers
+  if (threadIdx.x == 0) {
+    double lo;
+    hpar[1] = cand_scale(sc, lo);
+    hpar[0] = lo;
+  }
+  __syncthreads();
   double mx = -INFINITY, acc0 = 0.0, acc1 = 0.0, s1 = 0.0, s3 = 0.0;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -565,7 +570,8 @@ __global__ void __launch_bounds__(256, 4) psis_pass_a_lean_kernel(const double* 
       if (staged + 32 > kStage) flush_warp();
       if (is_cand) {
         mx = fmax(mx, x);
-        if (hscale > 0.0) atomicAdd(&ghist[cbin(x, hlo, hscale)], 1u);
+        const double hscale = hpar[1];
+        if (hscale > 0.0) atomicAdd(&ghist[cbin(x, hpar[0], hscale)], 1u);
         else if (lane == __ffs(ball) - 1) atomicAdd(&ghist[0], (unsigned int)__popc(ball));    // degenerate range: one bin
         const unsigned int slot = staged + __popc(ball & ((1u << lane) - 1));
         sx[w][slot] = x;
@@ -1050,7 +1056,13 @@ __device__ __forceinline__ void gpd_weights(PsisScalars* sc, const double* bs, c
                                             int N, int m, double* red) {
   for (int j = threadIdx.x; j < m; j += blockDim.x) {
     double ksum = 0.0;
-    for (int u = 0; u < nparts; ++u) ksum += __ldcg(part + j * nparts + u);     // written by other blocks
+    for (int u0 = 0; u0 < nparts; u0 += 8) {                   // loads of a batch are independent: one L2 latency per 8
+      double pv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) pv[u] = u0 + u < nparts ? __ldcg(part + j * nparts + u0 + u) : 0.0;     // written by other blocks
+#pragma unroll
+      for (int u = 0; u < 8; ++u) ksum += pv[u];
+    }
     const double kj = ksum / (double)N;
     double L = __ldcg(bs + j) / kj;
     L = log(-L);
@@ -1245,8 +1257,10 @@ __global__ void __launch_bounds__(256) psis_tail_values_kernel(PsisScalars* sc, 
   const int N = (int)sc->ntail;
   double k = INFINITY, sigma = 0.0;
   if (N > 4) {
+    // same reduction tree in every CTA (a serial loop of dependent loads cost ~300 cycles per entry)
     double s = 0.0;
-    for (int i = 0; i < nkpart; ++i) s += kpart[i];            // same order in every CTA
+    for (int i = threadIdx.x & 31; i < nkpart; i += 32) s += kpart[i];
+    s = warp_sum(s);
     k = s / (double)N;
     sigma = -k / sc->bhat;
     k = k * (double)N / ((double)N + 10.0) + 5.0 / ((double)N + 10.0);
