@@ -16,8 +16,6 @@
 
 namespace vb {
 
-constexpr int kSweepThreads = 256;
-constexpr int kSweepWarps = 8;
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile(
@@ -83,7 +81,7 @@ struct SweepArgs {
   const double2* baseP;
   const double* wP;
   const double* auxP;
-  int WC;   // number of 32-sample warp-chunks (S padded to 32)
+  int WC;   // number of warp-chunks of 8 * JN samples (S padded to that)
   int KG;   // ceil(d/8)
   int P;    // shared-memory row pitch of the X tile, in doubles
   int want_grad;
@@ -110,9 +108,16 @@ __device__ __forceinline__ void link_eval(double z, double yv, double auxv, doub
   }
 }
 
-template <int BM, int LINK>
-__global__ void __launch_bounds__(kSweepThreads, 1) glm_sweep_f64_kernel(SweepArgs a) {
+// JN = 8-sample blocks per warp.  JN = 4: 8 warps of 32 samples (the first version); JN = 2: 16 warps of 16 samples --
+// the same operand traffic from L2 (every warp still loads only its own slice of theta / E), twice the shared-memory
+// reads of the X tile (far from a bound), and FOUR warps per scheduler instead of two: with two, a warp's link
+// epilogue, its shuffles and the fixed issue distance between dependent DMMAs left the FP64 tensor pipe idle 39 % of
+// the time (profiles/f64_ncu_full_r02.csv: `wait` was the top stall reason).
+template <int BM, int LINK, int JN>
+__global__ void __launch_bounds__(32 * (32 / JN), 1) glm_sweep_f64_kernel(SweepArgs a) {
   constexpr int MT = BM / 8;
+  constexpr int kSweepWarps = 32 / JN;
+  constexpr int kSweepThreads = 32 * kSweepWarps;
   extern __shared__ __align__(16) double smem[];
   const int Dp = a.KG * 8;
   double* Xs = smem;                        // [BM][P]
@@ -132,14 +137,14 @@ __global__ void __launch_bounds__(kSweepThreads, 1) glm_sweep_f64_kernel(SweepAr
   for (int sc = 0; sc < numSuper; ++sc) {
     const int wc = sc * kSweepWarps + warp;
     const bool active = wc < a.WC;
-    double llacc[4][2];
-    double wv[4][2], av[4][2];
+    double llacc[JN][2];
+    double wv[JN][2], av[JN][2];
 #pragma unroll
-    for (int jn = 0; jn < 4; ++jn)
+    for (int jn = 0; jn < JN; ++jn)
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         llacc[jn][c] = 0.0;
-        const int s = wc * 32 + jn * 8 + 2 * t + c;
+        const int s = wc * (8 * JN) + jn * 8 + 2 * t + c;
         wv[jn][c] = active ? a.wP[s] : 0.0;
         av[jn][c] = active ? a.auxP[s] : 1.0;
       }
@@ -177,23 +182,23 @@ __global__ void __launch_bounds__(kSweepThreads, 1) glm_sweep_f64_kernel(SweepAr
       }
       __syncthreads();
 
-      double acc[MT][4][2];
+      double acc[MT][JN][2];
       if (active) {
         // ---- phase A: z = X_tile . theta^T for this warp's 32 samples ------------------
 #pragma unroll
         for (int i = 0; i < MT; ++i)
 #pragma unroll
-          for (int jn = 0; jn < 4; ++jn) acc[i][jn][0] = acc[i][jn][1] = 0.0;
+          for (int jn = 0; jn < JN; ++jn) acc[i][jn][0] = acc[i][jn][1] = 0.0;
 
-        const double2* tp = a.thetaP + ((size_t)wc * 4 * a.KG) * 32 + lane;
+        const double2* tp = a.thetaP + ((size_t)wc * JN * a.KG) * 32 + lane;
         const size_t sbStride = (size_t)a.KG * 32;
-        double2 bcur[4], bnxt[4];
+        double2 bcur[JN], bnxt[JN];
 #pragma unroll
-        for (int jn = 0; jn < 4; ++jn) bcur[jn] = tp[jn * sbStride];
+        for (int jn = 0; jn < JN; ++jn) bcur[jn] = tp[jn * sbStride];
         for (int kg = 0; kg < a.KG; ++kg) {
           if (kg + 1 < a.KG) {
 #pragma unroll
-            for (int jn = 0; jn < 4; ++jn) bnxt[jn] = tp[jn * sbStride + (size_t)(kg + 1) * 32];
+            for (int jn = 0; jn < JN; ++jn) bnxt[jn] = tp[jn * sbStride + (size_t)(kg + 1) * 32];
           }
           double2 af[MT];
 #pragma unroll
@@ -204,13 +209,13 @@ __global__ void __launch_bounds__(kSweepThreads, 1) glm_sweep_f64_kernel(SweepAr
 #pragma unroll
           for (int i = 0; i < MT; ++i)
 #pragma unroll
-            for (int jn = 0; jn < 4; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], af[i].x, bcur[jn].x);
+            for (int jn = 0; jn < JN; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], af[i].x, bcur[jn].x);
 #pragma unroll
           for (int i = 0; i < MT; ++i)
 #pragma unroll
-            for (int jn = 0; jn < 4; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], af[i].y, bcur[jn].y);
+            for (int jn = 0; jn < JN; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], af[i].y, bcur[jn].y);
 #pragma unroll
-          for (int jn = 0; jn < 4; ++jn) bcur[jn] = bnxt[jn];
+          for (int jn = 0; jn < JN; ++jn) bcur[jn] = bnxt[jn];
         }
 
         // ---- phase B: link epilogue in registers -----------------------------------------
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) glm_sweep_f64_kernel(SweepAr
           const double rv = (n0 + r < a.N) ? 1.0 : 0.0;
           double rs = 0.0;
 #pragma unroll
-          for (int jn = 0; jn < 4; ++jn)
+          for (int jn = 0; jn < JN; ++jn)
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
               double ll, rr;
@@ -255,15 +260,15 @@ __global__ void __launch_bounds__(kSweepThreads, 1) glm_sweep_f64_kernel(SweepAr
         }
         if (active) {
           // ---- phase C: T = (r.w) E for this warp's samples; ge += colsum(X .* T) -------
-          const double2* bp = a.baseP + ((size_t)wc * 4 * a.KG) * 32 + lane;
+          const double2* bp = a.baseP + ((size_t)wc * JN * a.KG) * 32 + lane;
           const size_t sbStride = (size_t)a.KG * 32;
-          double2 ecur[4], enxt[4];
+          double2 ecur[JN], enxt[JN];
 #pragma unroll
-          for (int jn = 0; jn < 4; ++jn) ecur[jn] = bp[jn * sbStride];
+          for (int jn = 0; jn < JN; ++jn) ecur[jn] = bp[jn * sbStride];
           for (int jb = 0; jb < a.KG; ++jb) {
             if (jb + 1 < a.KG) {
 #pragma unroll
-              for (int jn = 0; jn < 4; ++jn) enxt[jn] = bp[jn * sbStride + (size_t)(jb + 1) * 32];
+              for (int jn = 0; jn < JN; ++jn) enxt[jn] = bp[jn * sbStride + (size_t)(jb + 1) * 32];
             }
             double p0 = 0.0, p1 = 0.0;
             double t0[MT], t1[MT];
@@ -271,7 +276,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) glm_sweep_f64_kernel(SweepAr
             for (int i = 0; i < MT; ++i) t0[i] = t1[i] = 0.0;
             // MT independent accumulation chains, interleaved (a chain's next DMMA is MT instructions away)
 #pragma unroll
-            for (int jn = 0; jn < 4; ++jn) {
+            for (int jn = 0; jn < JN; ++jn) {
 #pragma unroll
               for (int i = 0; i < MT; ++i) dmma884(t0[i], t1[i], acc[i][jn][0], ecur[jn].x);
 #pragma unroll
@@ -294,7 +299,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) glm_sweep_f64_kernel(SweepAr
               atomicAdd(&ge_s[8 * jb + 2 * t + 1], p1);
             }
 #pragma unroll
-            for (int jn = 0; jn < 4; ++jn) ecur[jn] = enxt[jn];
+            for (int jn = 0; jn < JN; ++jn) ecur[jn] = enxt[jn];
           }
         }
       }
@@ -303,13 +308,13 @@ __global__ void __launch_bounds__(kSweepThreads, 1) glm_sweep_f64_kernel(SweepAr
     // ---- per-CTA log-likelihood partials for this super-chunk ------------------------------
     if (active) {
 #pragma unroll
-      for (int jn = 0; jn < 4; ++jn)
+      for (int jn = 0; jn < JN; ++jn)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           double v = llacc[jn][c];
 #pragma unroll
           for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (g == 0) a.ll_part[(size_t)blockIdx.x * a.WC * 32 + wc * 32 + jn * 8 + 2 * t + c] = v;
+          if (g == 0) a.ll_part[(size_t)blockIdx.x * a.WC * (8 * JN) + wc * (8 * JN) + jn * 8 + 2 * t + c] = v;
         }
     }
   }  // super-chunks
@@ -334,7 +339,7 @@ __global__ void reduce_partials_f64_kernel(const double* __restrict__ part, int 
 }
 
 struct SweepPlan {
-  int BM, KG, P, WC, SB, grid;
+  int BM, KG, P, WC, SB, JN, grid;
   int64_t numTiles;
   size_t smem;
   size_t off_thetaP, off_baseP, off_wP, off_auxP, off_ll, off_gmu, off_ge, total;
@@ -344,8 +349,11 @@ static bool make_plan(int64_t N, int d, int64_t S, SweepPlan& p) {
   p.KG = (int)ceil_div(d, 8);
   const int Dp = p.KG * 8;
   p.P = (Dp % 16 == 0) ? Dp + 8 : Dp + 16;
-  p.WC = (int)ceil_div(S, 32);
-  p.SB = p.WC * 4;
+  // VB_F64_JN=4 selects the first version's 8 warps x 32 samples (A/B timing)
+  static const int jn = [] { const char* e = getenv("VB_F64_JN"); return (e && e[0] == '4') ? 4 : 2; }();
+  p.JN = jn;
+  p.WC = (int)ceil_div(S, 8 * p.JN);
+  p.SB = p.WC * p.JN;
   p.BM = 0;
   for (int bm : {32, 16, 8}) {
     size_t bytes = sizeof(double) * ((size_t)bm * p.P + 2 * bm + 2 * (size_t)Dp);
@@ -370,20 +378,25 @@ static bool make_plan(int64_t N, int d, int64_t S, SweepPlan& p) {
   p.off_baseP = take(packed);
   p.off_wP = take((size_t)p.SB * 8 * sizeof(double));
   p.off_auxP = take((size_t)p.SB * 8 * sizeof(double));
-  p.off_ll = take((size_t)p.grid * p.WC * 32 * sizeof(double));
+  p.off_ll = take((size_t)p.grid * p.SB * 8 * sizeof(double));
   p.off_gmu = take((size_t)p.grid * Dp * sizeof(double));
   p.off_ge = take((size_t)p.grid * Dp * sizeof(double));
   p.total = off;
   return true;
 }
 
-template <int BM, int LINK>
-static int launch_sweep(const SweepArgs& a, const SweepPlan& p, cudaStream_t stream) {
-  auto kern = glm_sweep_f64_kernel<BM, LINK>;
+template <int BM, int LINK, int JN>
+static int launch_sweep_jn(const SweepArgs& a, const SweepPlan& p, cudaStream_t stream) {
+  auto kern = glm_sweep_f64_kernel<BM, LINK, JN>;
   VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  kern<<<p.grid, kSweepThreads, p.smem, stream>>>(a);
+  kern<<<p.grid, 32 * (32 / JN), p.smem, stream>>>(a);
   VB_CHECK_LAUNCH();
   return VB_OK;
+}
+
+template <int BM, int LINK>
+static int launch_sweep(const SweepArgs& a, const SweepPlan& p, cudaStream_t stream) {
+  return p.JN == 4 ? launch_sweep_jn<BM, LINK, 4>(a, p, stream) : launch_sweep_jn<BM, LINK, 2>(a, p, stream);
 }
 
 template <int LINK>
@@ -459,7 +472,7 @@ extern "C" int vb_glm_sweep_f64(const double* X, int64_t ldx, const double* y, i
     default: rc = launch_sweep_bm<VB_LINK_GAUSSIAN>(a, p, stream); break;
   }
   if (rc != VB_OK) return rc;
-  reduce_partials_f64_kernel<<<(int)ceil_div(S, 256), 256, 0, stream>>>(a.ll_part, p.grid, (int64_t)p.WC * 32, S, out_ll);
+  reduce_partials_f64_kernel<<<(int)ceil_div(S, 256), 256, 0, stream>>>(a.ll_part, p.grid, (int64_t)p.SB * 8, S, out_ll);
   VB_CHECK_LAUNCH();
   if (want_grad) {
     reduce_partials_f64_kernel<<<(int)ceil_div(d, 256), 256, 0, stream>>>(a.gmu_part, p.grid, Dp, d, out_gmu);

@@ -1143,14 +1143,19 @@ __global__ void __launch_bounds__(256) psis_gpd_grid_kernel(PsisScalars* sc, con
     x[u] = i < N ? sorted_x[i] : 0.0;                    // a term 1 + nb * 0 = 1 leaves the product alone
   }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-  for (int jj = 0; jj < kGpdJ; ++jj) {
-    const int j = j0 + jj;
+  __shared__ double nbs[kGpdJ];
+  if (threadIdx.x < kGpdJ) {          // the grid point's sqrt and two divisions once per CTA, not once per thread
+    const int j = j0 + (int)threadIdx.x;
     double b = 1.0 - sqrt((double)m / ((double)(j + 1) - 0.5));
     b /= 3.0 * xq;
     b += 1.0 / xmax;
-    if (blockIdx.y == 0 && threadIdx.x == 0 && j < m) bs[j] = b;
-    const double nb = j < m ? -b : 0.0;
+    if (blockIdx.y == 0 && j < m) bs[j] = b;
+    nbs[threadIdx.x] = j < m ? -b : 0.0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int jj = 0; jj < kGpdJ; ++jj) {
+    const double nb = nbs[jj];
     double prod = fma(nb, x[0], 1.0);
 #pragma unroll
     for (int u = 1; u < 8; ++u) prod *= fma(nb, x[u], 1.0);
