@@ -1,10 +1,8 @@
 #!/bin/bash
-# A/B of the exact sweep: 16 warps x 16 samples (default) against 8 warps x 32 samples (VB_F64_JN=4)
 mkdir -p gpurun_out
 {
-echo "=== pytest elbo/engine/cv"; python -m pytest tests/test_gpu_elbo.py tests/test_gpu_engine.py tests/test_gpu_cv.py -x -q -m gpu 2>&1 | tail -3
-echo "=== JN=2"; python bench.py --path f64 --steps 5 --warmup 3 --no-psis --no-cpu-baseline
-echo "=== JN=4"; VB_F64_JN=4 python bench.py --path f64 --steps 5 --warmup 3 --no-psis --no-cpu-baseline
+echo "=== default"; python bench.py --path f64 --steps 5 --warmup 3 --no-psis --no-cpu-baseline
+echo "=== pytest elbo/engine/cv"; python -m pytest tests/test_gpu_elbo.py tests/test_gpu_engine.py tests/test_gpu_cv.py -x -q -m gpu 2>&1 | tail -2
 } > gpurun_out/ab_f64.log 2>&1
 grep -v "^{" gpurun_out/ab_f64.log | tail -20
 python - <<'PY'

@@ -113,7 +113,10 @@ __device__ __forceinline__ void link_eval(double z, double yv, double auxv, doub
 // reads of the X tile (far from a bound), and FOUR warps per scheduler instead of two: with two, a warp's link
 // epilogue, its shuffles and the fixed issue distance between dependent DMMAs left the FP64 tensor pipe idle 39 % of
 // the time (profiles/f64_ncu_full_r02.csv: `wait` was the top stall reason).
-template <int BM, int LINK, int JN>
+// PRIV: every warp accumulates ge into its own shared-memory row (plain read-modify-write) instead of atomicAdd on
+// one shared row -- a double-precision shared atomic is a compare-and-swap loop, and 16 warps spinning on the same
+// 8 addresses per step were ~10 % of the sweep's samples.  Used whenever the rows fit beside the X tile.
+template <int BM, int LINK, int JN, bool PRIV>
 __global__ void __launch_bounds__(32 * (32 / JN), 1) glm_sweep_f64_kernel(SweepArgs a) {
   constexpr int MT = BM / 8;
   constexpr int kSweepWarps = 32 / JN;
@@ -124,12 +127,12 @@ __global__ void __launch_bounds__(32 * (32 / JN), 1) glm_sweep_f64_kernel(SweepA
   double* ys = Xs + (size_t)BM * a.P;       // [BM]
   double* rbar = ys + BM;                   // [BM]
   double* gmu_s = rbar + BM;                // [Dp]
-  double* ge_s = gmu_s + Dp;                // [Dp]
+  double* ge_s = gmu_s + Dp;                // [Dp], or [warps][Dp] with PRIV
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
 
-  for (int j = tid; j < 2 * Dp; j += kSweepThreads) gmu_s[j] = 0.0;   // gmu_s and ge_s are adjacent
+  for (int j = tid; j < (PRIV ? 1 + kSweepWarps : 2) * Dp; j += kSweepThreads) gmu_s[j] = 0.0;   // gmu_s and ge_s are adjacent
 
   const int numSuper = (a.WC + kSweepWarps - 1) / kSweepWarps;
   const bool vec_ok = ((a.ldx & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.X) & 15) == 0);
@@ -260,34 +263,47 @@ __global__ void __launch_bounds__(32 * (32 / JN), 1) glm_sweep_f64_kernel(SweepA
         }
         if (active) {
           // ---- phase C: T = (r.w) E for this warp's samples; ge += colsum(X .* T) -------
+          // Software pipelined: the DMMAs of column block jb + 1 are issued BEFORE the reduction of block jb (its
+          // dependent X products, three shuffle levels and the shared-memory update), so that chain of latencies
+          // runs under tensor work of the same warp instead of in front of it.
           const double2* bp = a.baseP + ((size_t)wc * JN * a.KG) * 32 + lane;
           const size_t sbStride = (size_t)a.KG * 32;
-          double2 ecur[JN], enxt[JN];
+          double* ge_w = PRIV ? ge_s + (size_t)warp * Dp : ge_s;
+          double2 e1[JN], e2[JN];
+          double tc0[MT], tc1[MT], tn0[MT], tn1[MT];
+          auto issue = [&](double (&u0)[MT], double (&u1)[MT], const double2 (&e)[JN]) {
 #pragma unroll
-          for (int jn = 0; jn < JN; ++jn) ecur[jn] = bp[jn * sbStride];
-          for (int jb = 0; jb < a.KG; ++jb) {
-            if (jb + 1 < a.KG) {
-#pragma unroll
-              for (int jn = 0; jn < JN; ++jn) enxt[jn] = bp[jn * sbStride + (size_t)(jb + 1) * 32];
-            }
-            double p0 = 0.0, p1 = 0.0;
-            double t0[MT], t1[MT];
-#pragma unroll
-            for (int i = 0; i < MT; ++i) t0[i] = t1[i] = 0.0;
+            for (int i = 0; i < MT; ++i) u0[i] = u1[i] = 0.0;
             // MT independent accumulation chains, interleaved (a chain's next DMMA is MT instructions away)
 #pragma unroll
             for (int jn = 0; jn < JN; ++jn) {
 #pragma unroll
-              for (int i = 0; i < MT; ++i) dmma884(t0[i], t1[i], acc[i][jn][0], ecur[jn].x);
+              for (int i = 0; i < MT; ++i) dmma884(u0[i], u1[i], acc[i][jn][0], e[jn].x);
 #pragma unroll
-              for (int i = 0; i < MT; ++i) dmma884(t0[i], t1[i], acc[i][jn][1], ecur[jn].y);
+              for (int i = 0; i < MT; ++i) dmma884(u0[i], u1[i], acc[i][jn][1], e[jn].y);
             }
+          };
+#pragma unroll
+          for (int jn = 0; jn < JN; ++jn) e1[jn] = bp[jn * sbStride];
+          issue(tc0, tc1, e1);
+          if (a.KG > 1) {
+#pragma unroll
+            for (int jn = 0; jn < JN; ++jn) e1[jn] = bp[jn * sbStride + 32];
+          }
+#pragma unroll 2
+          for (int jb = 0; jb < a.KG; ++jb) {
+            if (jb + 2 < a.KG) {
+#pragma unroll
+              for (int jn = 0; jn < JN; ++jn) e2[jn] = bp[jn * sbStride + (size_t)(jb + 2) * 32];
+            }
+            if (jb + 1 < a.KG) issue(tn0, tn1, e1);
+            double p0 = 0.0, p1 = 0.0;
 #pragma unroll
             for (int i = 0; i < MT; ++i) {
               const double2 xv =
                   *reinterpret_cast<const double2*>(Xs + (size_t)(8 * i + g) * a.P + 8 * jb + 2 * t);
-              p0 += xv.x * t0[i];
-              p1 += xv.y * t1[i];
+              p0 += xv.x * tc0[i];
+              p1 += xv.y * tc1[i];
             }
 #pragma unroll
             for (int o = 4; o < 32; o <<= 1) {
@@ -295,11 +311,24 @@ __global__ void __launch_bounds__(32 * (32 / JN), 1) glm_sweep_f64_kernel(SweepA
               p1 += __shfl_xor_sync(0xffffffffu, p1, o);
             }
             if (g == 0) {
-              atomicAdd(&ge_s[8 * jb + 2 * t], p0);
-              atomicAdd(&ge_s[8 * jb + 2 * t + 1], p1);
+              if (PRIV) {
+                double2* q = reinterpret_cast<double2*>(ge_w + 8 * jb) + t;
+                double2 v = *q;
+                v.x += p0;
+                v.y += p1;
+                *q = v;
+              } else {
+                atomicAdd(&ge_s[8 * jb + 2 * t], p0);
+                atomicAdd(&ge_s[8 * jb + 2 * t + 1], p1);
+              }
             }
 #pragma unroll
-            for (int jn = 0; jn < JN; ++jn) ecur[jn] = enxt[jn];
+            for (int i = 0; i < MT; ++i) {
+              tc0[i] = tn0[i];
+              tc1[i] = tn1[i];
+            }
+#pragma unroll
+            for (int jn = 0; jn < JN; ++jn) e1[jn] = e2[jn];
           }
         }
       }
@@ -322,7 +351,11 @@ __global__ void __launch_bounds__(32 * (32 / JN), 1) glm_sweep_f64_kernel(SweepA
   if (a.want_grad) {
     for (int j = tid; j < Dp; j += kSweepThreads) {
       a.gmu_part[(size_t)blockIdx.x * Dp + j] = gmu_s[j];
-      a.ge_part[(size_t)blockIdx.x * Dp + j] = ge_s[j];
+      double v = ge_s[j];
+      if (PRIV) {
+        for (int w2 = 1; w2 < kSweepWarps; ++w2) v += ge_s[(size_t)w2 * Dp + j];      // fixed order: deterministic
+      }
+      a.ge_part[(size_t)blockIdx.x * Dp + j] = v;
     }
   }
 }
@@ -339,7 +372,7 @@ __global__ void reduce_partials_f64_kernel(const double* __restrict__ part, int 
 }
 
 struct SweepPlan {
-  int BM, KG, P, WC, SB, JN, grid;
+  int BM, KG, P, WC, SB, JN, priv, grid;
   int64_t numTiles;
   size_t smem;
   size_t off_thetaP, off_baseP, off_wP, off_auxP, off_ll, off_gmu, off_ge, total;
@@ -364,6 +397,11 @@ static bool make_plan(int64_t N, int d, int64_t S, SweepPlan& p) {
     }
   }
   if (p.BM == 0) return false;
+  {   // per-warp ge rows when they fit beside the tile
+    const size_t extra = sizeof(double) * (size_t)(32 / p.JN - 1) * Dp;
+    p.priv = (p.smem + extra <= 227 * 1024) ? 1 : 0;
+    if (p.priv) p.smem += extra;
+  }
   p.numTiles = ceil_div(N, p.BM);
   int sms = sm_count();
   p.grid = (int)((p.numTiles < sms) ? (p.numTiles > 0 ? p.numTiles : 1) : sms);
@@ -385,13 +423,18 @@ static bool make_plan(int64_t N, int d, int64_t S, SweepPlan& p) {
   return true;
 }
 
-template <int BM, int LINK, int JN>
-static int launch_sweep_jn(const SweepArgs& a, const SweepPlan& p, cudaStream_t stream) {
-  auto kern = glm_sweep_f64_kernel<BM, LINK, JN>;
+template <int BM, int LINK, int JN, bool PRIV>
+static int launch_sweep_priv(const SweepArgs& a, const SweepPlan& p, cudaStream_t stream) {
+  auto kern = glm_sweep_f64_kernel<BM, LINK, JN, PRIV>;
   VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   kern<<<p.grid, 32 * (32 / JN), p.smem, stream>>>(a);
   VB_CHECK_LAUNCH();
   return VB_OK;
+}
+
+template <int BM, int LINK, int JN>
+static int launch_sweep_jn(const SweepArgs& a, const SweepPlan& p, cudaStream_t stream) {
+  return p.priv ? launch_sweep_priv<BM, LINK, JN, true>(a, p, stream) : launch_sweep_priv<BM, LINK, JN, false>(a, p, stream);
 }
 
 template <int BM, int LINK>
