@@ -349,7 +349,11 @@ def bench_psis(torch, vb, args):
                          'peak_source': how, 'algorithmic_bytes_per_draw': 24},
             'diagnostics_only': {'value': n / sec_diag, 'unit': 'draws/s', 'ms': sec_diag * 1e3,
                                  'algorithmic_bytes_per_draw': 16, 'achieved_gbs': 16.0 * n / sec_diag / 1e9,
-                                 'frac': 16.0 * n / sec_diag / 1e9 / hbm},
+                                 'frac': 16.0 * n / sec_diag / 1e9 / hbm,
+                                 'traffic_bytes_per_draw': 8,
+                                 'note': 'k-hat + CUBO / ELBO sums in ONE pass over the draws (the sums of the second '
+                                         'pass are carried by the first): the kernel moves 8 B/draw, the fraction is '
+                                         'quoted on SURVEY 8(d)\'s 16 B/draw definition of the work'},
             'e2e': {'value': e2e, 'unit': 'draws/s', 'n_draws': m2, 'h2d_bytes': m2 * 8,
                     'd2h_bytes': m2 * 8 + 8, 'khat': k2, 'note': 'PCIe-bound'},
             'cpu_baseline': cpu}
