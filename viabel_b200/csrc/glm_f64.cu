@@ -141,15 +141,11 @@ __global__ void __launch_bounds__(32 * (32 / JN), 1) glm_sweep_f64_kernel(SweepA
     const int wc = sc * kSweepWarps + warp;
     const bool active = wc < a.WC;
     double llacc[JN][2];
-    double wv[JN][2], av[JN][2];
 #pragma unroll
     for (int jn = 0; jn < JN; ++jn)
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         llacc[jn][c] = 0.0;
-        const int s = wc * (8 * JN) + jn * 8 + 2 * t + c;
-        wv[jn][c] = active ? a.wP[s] : 0.0;
-        av[jn][c] = active ? a.auxP[s] : 1.0;
       }
 
     for (int64_t tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
@@ -222,6 +218,17 @@ __global__ void __launch_bounds__(32 * (32 / JN), 1) glm_sweep_f64_kernel(SweepA
         }
 
         // ---- phase B: link epilogue in registers -----------------------------------------
+        // (the per-sample weights are re-read here, L1 hits, rather than held in registers across the tile: phase C
+        // needs those registers to keep its DMMA chains interleaved)
+        double wv[JN][2], av[JN][2];
+#pragma unroll
+        for (int jn = 0; jn < JN; ++jn)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int s = wc * (8 * JN) + jn * 8 + 2 * t + c;
+            wv[jn][c] = __ldg(a.wP + s);
+            av[jn][c] = (LINK == VB_LINK_GAUSSIAN) ? __ldg(a.auxP + s) : 1.0;
+          }
         double rsum[MT];
 #pragma unroll
         for (int i = 0; i < MT; ++i) {
@@ -269,7 +276,7 @@ __global__ void __launch_bounds__(32 * (32 / JN), 1) glm_sweep_f64_kernel(SweepA
           const double2* bp = a.baseP + ((size_t)wc * JN * a.KG) * 32 + lane;
           const size_t sbStride = (size_t)a.KG * 32;
           double* ge_w = PRIV ? ge_s + (size_t)warp * Dp : ge_s;
-          double2 e1[JN], e2[JN];
+          double2 e1[JN];
           double tc0[MT], tc1[MT], tn0[MT], tn1[MT];
           auto issue = [&](double (&u0)[MT], double (&u1)[MT], const double2 (&e)[JN]) {
 #pragma unroll
@@ -292,11 +299,11 @@ __global__ void __launch_bounds__(32 * (32 / JN), 1) glm_sweep_f64_kernel(SweepA
           }
 #pragma unroll 2
           for (int jb = 0; jb < a.KG; ++jb) {
-            if (jb + 2 < a.KG) {
-#pragma unroll
-              for (int jn = 0; jn < JN; ++jn) e2[jn] = bp[jn * sbStride + (size_t)(jb + 2) * 32];
-            }
             if (jb + 1 < a.KG) issue(tn0, tn1, e1);
+            if (jb + 2 < a.KG) {      // the E fragments of block jb + 2 arrive under this block's reduction
+#pragma unroll
+              for (int jn = 0; jn < JN; ++jn) e1[jn] = bp[jn * sbStride + (size_t)(jb + 2) * 32];
+            }
             double p0 = 0.0, p1 = 0.0;
 #pragma unroll
             for (int i = 0; i < MT; ++i) {
@@ -327,8 +334,6 @@ __global__ void __launch_bounds__(32 * (32 / JN), 1) glm_sweep_f64_kernel(SweepA
               tc0[i] = tn0[i];
               tc1[i] = tn1[i];
             }
-#pragma unroll
-            for (int jn = 0; jn < JN; ++jn) e1[jn] = e2[jn];
           }
         }
       }
