@@ -145,3 +145,30 @@ def test_c2_full_size_properties(vb):
     # the summed-likelihood shortcut used by plain ExclusiveKL returns the mean in every slot
     tot = parts[0].sweep(theta, base, None, True, ll_total_only=True)[0] + parts[1].sweep(theta, base, None, True, ll_total_only=True)[0]
     assert abs(float(tot[0]) * S - float(ref[:S].sum())) < TOL_FAST * abs(float(ref[:S].sum()))
+
+
+def test_c2_full_size_vs_oracle(vb, vo):
+    """BASELINE configs[1] at FULL size (N=1e6, d=512, S=256) against the float64 numpy oracle itself (the oracle
+    walks the rows in chunks: a few seconds on the box's host cores): ExclusiveKL value and gradient of the exact
+    path to 1e-10, of the tensor-core fast path to 1e-4, at a near-converged point (the gradient is a small
+    difference of large sums there -- the hard case for the fast path's operand scheme)."""
+    N, d, S = 1000000, 512, 256
+    g = torch.Generator(device='cuda')
+    g.manual_seed(20260117)
+    beta = torch.randn(d, generator=g, device='cuda', dtype=torch.float64) / np.sqrt(d)
+    X = torch.randn(N, d, generator=g, device='cuda', dtype=torch.float64)
+    y = torch.where(torch.rand(N, generator=g, device='cuda', dtype=torch.float64) < torch.sigmoid(X @ beta), 1.0, -1.0)
+    rs = np.random.RandomState(512)
+    base = _f16_exact(rs.randn(S, d))
+    vp = np.concatenate([beta.cpu().numpy(), -3.5 * np.ones(d)])
+    Xh, yh = X.cpu().numpy(), y.cpu().numpy()
+    v0, g0, _ = vo.exclusive_kl_meanfield(vp, base, lambda th: vo.logistic_logp_grad(th, Xh, yh, 10.0))
+    del Xh, yh
+    model = vb.LogisticRegression(X, y, prior_scale=10.0)
+    approx = vb.MFGaussian(d)
+    obj = vb.ExclusiveKL(approx, model, S)
+    v, gr = obj(vp, base=base)
+    assert relerr(v, v0) < 1e-10 and relerr(gr, g0) < 1e-10, (relerr(v, v0), relerr(gr, g0))
+    model.enable_fast_path()
+    v, gr = obj(vp, base=base)
+    assert relerr(v, v0) < TOL_FAST and relerr(gr, g0) < TOL_FAST, (relerr(v, v0), relerr(gr, g0))
