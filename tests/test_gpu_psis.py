@@ -136,6 +136,40 @@ def test_psislw_moments_only_one_pass(vb, vo, name, variant):
         assert relerr(r1[0], k_ref) < TOL
 
 
+@pytest.mark.parametrize('n', [5000, 300001])
+def test_psislw_nan_and_minus_inf(vb, vo, n):
+    """Non-finite log-weights, as the reference treats them (_psis.py run unmodified: a NaN makes every output NaN
+    and k-hat +inf -- the tail {x > cutoff} is empty; -inf weights are ordinary draws of weight zero)."""
+    rs = np.random.RandomState(n)
+    base = rs.standard_t(4, size=n)
+    for pos in (1234, n - 1):                              # vectorised main loop / scalar remainder of pass A
+        for nan in (np.nan, -np.nan, np.inf - np.inf):
+            lw = base.copy()
+            lw[pos] = nan
+            for out_wanted in (True, False):
+                t = torch.as_tensor(lw, device='cuda')
+                out = torch.empty_like(t) if out_wanted else None
+                for exact in (False, True):                # status 1 = sampled threshold missed: the API reruns exact
+                    _, res, _, _ = vb.psislw_device(t, out, exact=exact)
+                    r = res.cpu().numpy()
+                    if r[6] != 1:
+                        break
+                assert r[6] == 0 and np.isposinf(r[0]), (pos, r[0], r[6])
+                if out_wanted:
+                    assert bool(torch.isnan(out).all())
+            out, k = vb.psislw(lw)
+            assert np.isposinf(k) and np.isnan(out).all()
+    lw = base.copy()
+    lw[[7, 1234, n - 1]] = -np.inf
+    out, k = vb.psislw(lw)
+    with np.errstate(all='ignore'):
+        o_ref, k_ref = vo.psislw_1d(lw)[:2]
+    assert relerr(k, k_ref) < TOL
+    fin = np.isfinite(o_ref)
+    assert np.array_equal(np.isneginf(out), np.isneginf(o_ref)) and fin.sum() == n - 3
+    np.testing.assert_allclose(out[fin], o_ref[fin], rtol=1e-10, atol=1e-10)
+
+
 @pytest.mark.parametrize('n,dfp,dfq', [(3000000, 4, 9), (10000000, 3, 30)])
 def test_psislw_large_vs_oracle(vb, vo, n, dfp, dfq):
     g = torch.Generator(device='cuda')

@@ -588,10 +588,11 @@ __global__ void __launch_bounds__(256, 4) psis_pass_a_lean_kernel(const double* 
     const bool special = (h0 >= kHiSpecial) | (h1 >= kHiSpecial) | (h2 >= kHiSpecial) | (h3 >= kHiSpecial);
     if (__any_sync(0xffffffffu, special)) {
       const bool c0 = a.x >= tb, c1 = a.y >= tb, c2 = b.x >= tb, c3 = b.y >= tb;
-      e0 = h0 >= kHiSpecial ? 0.0 : e0;
-      e1 = h1 >= kHiSpecial ? 0.0 : e1;
-      e2 = h2 >= kHiSpecial ? 0.0 : e2;
-      e3 = h3 >= kHiSpecial ? 0.0 : e3;
+      // (a NaN draw is no candidate and must poison the sums, as it poisons the reference's max and logsumexp)
+      e0 = h0 >= kHiSpecial ? (d0 != d0 ? d0 : 0.0) : e0;
+      e1 = h1 >= kHiSpecial ? (d1 != d1 ? d1 : 0.0) : e1;
+      e2 = h2 >= kHiSpecial ? (d2 != d2 ? d2 : 0.0) : e2;
+      e3 = h3 >= kHiSpecial ? (d3 != d3 ? d3 : 0.0) : e3;
       if (kMom) {
         d0 = c0 ? 0.0 : d0;
         d1 = c1 ? 0.0 : d1;
@@ -646,7 +647,7 @@ __global__ void __launch_bounds__(256, 4) psis_pass_a_lean_kernel(const double* 
       const bool c = v && (all || x >= tb);
       if (v && !c) {
         const double d = x - tb;
-        const double e = (unsigned int)__double2hiint(d) >= 0xC0861E00u ? 0.0 : exp_core(d, etab);
+        const double e = d != d ? d : ((unsigned int)__double2hiint(d) >= 0xC0861E00u ? 0.0 : exp_core(d, etab));
         acc0 += e;
         if (kMom) {
           s1 += d;
@@ -1223,20 +1224,22 @@ __device__ __forceinline__ void lse_warp(PsisScalars* sc, const double* part3, i
   sv = warp_sum(sv);
   se = warp_sum(se);
   if (threadIdx.x != 0) return;
-  const double below = sc->body_below > 0.0 ? sc->body_below * exp(sc->tbase - sc->maxv) : 0.0;
+  const double below = sc->body_below == 0.0 ? 0.0 : sc->body_below * exp(sc->tbase - sc->maxv)   /* NaN passes */;
   const double total = below + sc->body_cand + ts;
   if (sc->onepass) {
     // moments of v = x - max over ALL draws from pass A's sums (relative to tbase), the candidate list and the tail
     const double nbelow = (double)(sc->n_local - (long long)sc->ncand);
     const double shift = sc->tbase - sc->maxv;
     result[R_SUMV] = (nbelow > 0.0 ? sc->below_sv + nbelow * shift : 0.0) + sc->cand_sv + sv;
-    result[R_SUMEXP2V] = (sc->below_se2 > 0.0 ? sc->below_se2 * exp(2.0 * shift) : 0.0) + sc->cand_se2 + se;
+    result[R_SUMEXP2V] = (sc->below_se2 == 0.0 ? 0.0 : sc->below_se2 * exp(2.0 * shift)) + sc->cand_se2 + se;
   }
   sc->tail_sum = ts;
   sc->sumv = sv;
   sc->sumexp2v = se;
   sc->lse = log(total);
-  result[R_KHAT] = sc->k;
+  // a NaN among the draws: the reference's max is NaN, every output is NaN, the tail {x > cutoff} is empty and
+  // k-hat is therefore +inf (_psis.py:154-180)
+  result[R_KHAT] = total != total ? INFINITY : sc->k;
   result[R_SIGMA] = sc->sigma;
   result[R_N2] = (double)sc->ntail;
   result[R_CUTOFF] = sc->cutoff;
@@ -1819,9 +1822,9 @@ __global__ void __launch_bounds__(256) psis_export_kernel(const PsisScalars* sc,
     idx[j] = j < nt ? tmp_i[j] : -1;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const double below = sc->body_below > 0.0 ? sc->body_below * exp(sc->tbase - maxv) : 0.0;
+    const double below = sc->body_below == 0.0 ? 0.0 : sc->body_below * exp(sc->tbase - maxv);
     double body = below + sc->body_cand - (double)(K - nt) * exp(c - maxv);     // the copies of c_r travel in the record
-    if (!(body > 0.0)) body = 0.0;
+    if (!(body > 0.0) && body == body) body = 0.0;          // (a NaN stays: it must reach every rank's log-sum-exp)
     rec[0] = maxv; rec[1] = c; rec[2] = log(body); rec[3] = (double)K;
   }
 }
@@ -1844,7 +1847,7 @@ __global__ void __launch_bounds__(256) psis_import_kernel(PsisScalars* sc, const
     }
     for (int r = 0; r < world; ++r) {
       const double* h = recs + (size_t)r * reclen;
-      if (h[2] > -INFINITY) below += exp(h[2] + h[0] - t0);          // every term is <= exp(c_r - t0) * count <= count
+      if (h[2] > -INFINITY || h[2] != h[2]) below += exp(h[2] + h[0] - t0);          // every term is <= exp(c_r - t0) * count <= count
     }
     sc->maxkey = dkey(mx);
     sc->t0 = t0;
