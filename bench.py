@@ -315,19 +315,20 @@ def bench_psis(torch, vb, args):
     achieved = 24.0 * n / sec / 1e9
     # end to end from HOST memory through the public API call: H2D of the weights, PSIS, D2H of k-hat and the
     # smoothed weights (pinned buffers; a PCIe-bound number, reported for completeness)
-    m2 = min(n, 20000000)
+    m2 = min(n, 100000000)            # configs[4]'s own size: 0.8 GB each way
     host = torch.empty(m2, dtype=torch.float64).pin_memory()
     host.copy_(lw[:m2])
     hout = torch.empty_like(host).pin_memory()
     dev_in = torch.empty(m2, device='cuda', dtype=torch.float64)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    dev_in.copy_(host, non_blocking=True)
-    _, res2, _, _ = vb.psislw_device(dev_in, dev_in)
-    hout.copy_(dev_in, non_blocking=True)
-    k2 = float(res2[0].item())
-    torch.cuda.synchronize()
-    e2e = m2 / (time.perf_counter() - t0)
+    for rep in range(2):                  # the second repetition is the timed one (pages touched, workspace cached)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dev_in.copy_(host, non_blocking=True)
+        _, res2, _, _ = vb.psislw_device(dev_in, dev_in)
+        hout.copy_(dev_in, non_blocking=True)
+        k2 = float(res2[0].item())
+        torch.cuda.synchronize()
+        e2e = m2 / (time.perf_counter() - t0)
     cpu = None
     if not args.no_cpu_baseline:
         from oracle import viabel_oracle as vo
