@@ -260,6 +260,18 @@ __global__ void __launch_bounds__(256) mf_pre_kernel(StepCfg c, StepPtrs p, fast
     const size_t o = ((size_t)(sg >> 6) * c.d_pad + (j0 + jj)) * 64 + (sg & 63);
     *reinterpret_cast<uint2*>(ops.Th + o) = *reinterpret_cast<const uint2*>(hi);
     *reinterpret_cast<uint2*>(ops.Tl + o) = *reinterpret_cast<const uint2*>(lo);
+    if (ops.T8) {      // e5m2 copies for the fp8 correction passes: Theta_h * 2^-ax and Theta_l * 2^bx, 128-sample groups
+      const float sh = exp2f((float)-ops.ax), sl = exp2f((float)ops.bx);
+      uint32_t h8 = 0, l8 = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        h8 |= (uint32_t)fast::to_e5m2(__half2float(hi[u]) * sh) << (8 * u);
+        l8 |= (uint32_t)fast::to_e5m2(__half2float(lo[u]) * sl) << (8 * u);
+      }
+      const size_t o8 = ((size_t)(sg >> 7) * c.d_pad + (j0 + jj)) * 128 + (sg & 127);
+      *reinterpret_cast<uint32_t*>(ops.T8 + o8) = h8;
+      *reinterpret_cast<uint32_t*>(ops.T8 + (size_t)2 * c.d_pad * 128 + o8) = l8;
+    }
   }
   if (blockIdx.x == 0 && blockIdx.y == 0) ops.wf[threadIdx.x] = (int)threadIdx.x < c.S ? 1.0f : 0.0f;
 }
@@ -660,7 +672,7 @@ extern "C" int vb_mf_step_glm(const vb_step_config* cfg, const vb_step_buffers* 
   p.aux = reinterpret_cast<double*>(ws + L.off_aux);
   p.ticket = reinterpret_cast<unsigned int*>(ws + L.off_ticket);
 
-  fast::FastOperands ops;
+  fast::FastOperands ops = {};
   memset(&ops, 0, sizeof(ops));
   if (fast) {
     int md = 0, mdp = 0;

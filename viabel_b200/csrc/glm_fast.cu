@@ -201,6 +201,17 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, u
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// 8-bit float operands (e4m3 / e5m2 per the instruction descriptor), K = 32 per instruction, fp32 accumulate
+__device__ __forceinline__ void umma_f8_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrives on the barrier at the same shared-memory offset in both CTAs of the pair
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
   const uint16_t mask = 3;
@@ -244,6 +255,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// instruction descriptor: e5m2 x e5m2 -> f32 (kind::f8f6f4; a_format / b_format: 0 = e4m3, 1 = e5m2)
+__host__ __device__ constexpr uint32_t make_idesc8(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) /*c=f32*/ | (1u << 7) /*a=e5m2*/ | (1u << 10) /*b=e5m2*/ | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 struct Params {
   int64_t N;
   int d_pad;       // multiple of 128
@@ -260,6 +277,8 @@ struct Params {
   int uniform_w;     // 1: every valid sample has weight 1 (w == NULL on the host side)
   const __half* Xh;  // pair kernel: E2 reads its X rows from global memory
   const __half* Xl;
+  const uint8_t* Xl8;  // fp8 scheme: e5m2 of X_l * 2^ax, [tile][d_pad][128 n]
+  float xl_scale;      // 2^-ax
 };
 
 struct Misc {
@@ -804,10 +823,19 @@ __device__ __forceinline__ void link_chunk_total(float (&v)[32], uint32_t (&pack
 //       after the stages with (kc & 7) == 1 (and i > 0): the 4 E slots of GEMM2 group jbp = kc >> 3 of super-tile i-1,
 //       consumed after stage (kc & 7) == 3
 //   a last iteration i = nIter only carries the GEMM2 groups of the final super-tile.
+// FP8 (VB_FAST_FP8, tools/emulate_fp8_scheme.py): the two CORRECTION passes of GEMM1 run on e5m2 copies with reciprocal
+// power-of-two scales, (X_l 2^ax)(Theta_h 2^-ax) and (X_h 2^-bx)(Theta_l 2^bx), as kind::f8f6f4 (K = 32 per instruction,
+// twice the fp16 rate): their terms are 2^-11 of the product, so 3 significant bits per operand leave 2^-13 overall --
+// GEMM1 costs 1 + 1/2 + 1/2 pass units instead of 3.  A stage keeps its 2 x 16 KB: slot A = X_h (2 halves, 8 KB) | X_l8 |
+// X_h8 (4 KB each: 32 j-rows x 128 n bytes), slot B = Theta_h (2 groups, 8 KB) | Theta_h8 | Theta_l8 (this CTA's 128
+// samples).  E2 takes its X as X_h + X_l8 2^-ax (3 bytes per element from L2 instead of 4).
+template <bool FP8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsP, 1)
-glm_fast_pair_kernel(const __grid_constant__ CUtensorMap tmX,      // 5-D: [hi|lo][tile][half][j][64 n]
-                     const __grid_constant__ CUtensorMap tmT,      // 4-D: [hi|lo][group][j][64 s]
+glm_fast_pair_kernel(const __grid_constant__ CUtensorMap tmX,      // 5-D: [hi|lo][tile][half][j][64 n]; FP8: 4-D [tile][half][j][64 n] (X_h)
+                     const __grid_constant__ CUtensorMap tmT,      // 4-D: [hi|lo][group][j][64 s];      FP8: 3-D [group][j][64 s] (Theta_h)
                      const __grid_constant__ CUtensorMap tmE,      // 3-D: [j group][s][64 j]
+                     const __grid_constant__ CUtensorMap tmX8,     // FP8: 4-D [X_l8|X_h8][tile][j][128 n] bytes
+                     const __grid_constant__ CUtensorMap tmT8,     // FP8: 4-D [Theta_h8|Theta_l8][group][j][128 s] bytes
                      Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem;
@@ -856,6 +884,7 @@ glm_fast_pair_kernel(const __grid_constant__ CUtensorMap tmX,      // 5-D: [hi|l
     // ================================ TMA producer (both CTAs) ================================
     if (lane == 0) {
       prefetch_tmap(&tmX); prefetch_tmap(&tmT); prefetch_tmap(&tmE);
+      if (FP8) { prefetch_tmap(&tmX8); prefetch_tmap(&tmT8); }
       uint32_t fill = 0, sc = 0, ec = 0;
       auto acquire = [&]() -> uint32_t {
         const uint32_t slot = fill % kNumSlots, par = (fill / kNumSlots) & 1;
@@ -883,9 +912,17 @@ glm_fast_pair_kernel(const __grid_constant__ CUtensorMap tmX,      // 5-D: [hi|l
             if (leader) mbar_expect_tx(bar_l, 4 * kSlotBytes);
             const uint32_t bar = mapa_u32(bar_l, 0);
             uint32_t dst = acquire();
-            tma_load_5d_pair(dst, &tmX, 0, j0, 0, tile, 0, bar);         // hi n0 | hi n1 | lo n0 | lo n1: 16 KB
-            dst = acquire();
-            tma_load_4d_pair(dst, &tmT, 0, j0, 2 * (int)rank, 0, bar);   // Theta_hi g0 | g1 | Theta_lo g0 | g1 (this CTA's half)
+            if (FP8) {
+              tma_load_4d_pair(dst, &tmX, 0, j0, 0, tile, bar);            // X_h n0 | n1: 8 KB
+              tma_load_4d_pair(dst + 8192, &tmX8, 0, j0, tile, 0, bar);    // X_l8 | X_h8: 2 x 4 KB
+              dst = acquire();
+              tma_load_3d_pair(dst, &tmT, 0, j0, 2 * (int)rank, bar);      // Theta_h g0 | g1 (this CTA's half): 8 KB
+              tma_load_4d_pair(dst + 8192, &tmT8, 0, j0, (int)rank, 0, bar);   // Theta_h8 | Theta_l8 of its 128 samples
+            } else {
+              tma_load_5d_pair(dst, &tmX, 0, j0, 0, tile, 0, bar);         // hi n0 | hi n1 | lo n0 | lo n1: 16 KB
+              dst = acquire();
+              tma_load_4d_pair(dst, &tmT, 0, j0, 2 * (int)rank, 0, bar);   // Theta_hi g0 | g1 | Theta_lo g0 | g1 (this CTA's half)
+            }
             if (grad && it > 0 && (kc & 7) == 1) g2_fills(kc >> 3);     // two stages ahead of the group that consumes them
           }
         } else if (grad && it > 0) {
@@ -944,7 +981,21 @@ glm_fast_pair_kernel(const __grid_constant__ CUtensorMap tmX,      // 5-D: [hi|l
             mbar_wait_cl(smem_u32(&misc->g1_full[sc % kFullRing]), (sc / kFullRing) & 1);
             if (timing) w_g1 += clock64() - c0;
             tc_fence_after();
-            if (elect_one()) {
+            if (FP8) {
+              if (elect_one()) {
+                constexpr uint32_t idesc8 = make_idesc8(256, 256, 1, 1);
+#pragma unroll
+                for (int k = 0; k < 2; ++k)                 // X_h . Theta_h, fp16, K = 16 each
+                  umma_f16_pair(tmem, make_desc(ax + k * 2048, 4096, 1024), make_desc(bh + k * 2048, 4096, 1024), idesc1,
+                                (kc | k) ? 1u : 0u);
+                // corrections, e5m2, K = 32: one 128-byte row holds all 128 rows / samples of this CTA (a single MN group)
+                umma_f8_pair(tmem, make_desc(ax + 8192, 4096, 1024), make_desc(bh + 8192, 4096, 1024), idesc8, 1u);     // X_l8 . Theta_h8
+                umma_f8_pair(tmem, make_desc(ax + 12288, 4096, 1024), make_desc(bh + 12288, 4096, 1024), idesc8, 1u);   // X_h8 . Theta_l8
+                umma_commit_pair(smem_u32(&misc->empty[sa]));
+                umma_commit_pair(smem_u32(&misc->empty[sb]));
+                if (kc == KC - 1) umma_commit_pair(smem_u32(&misc->z_full));
+              }
+            } else if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 2; ++k)
                 umma_f16_pair(tmem, make_desc(ax + k * 2048, 4096, 1024), make_desc(bl + k * 2048, 4096, 1024), idesc1,
@@ -1006,15 +1057,21 @@ glm_fast_pair_kernel(const __grid_constant__ CUtensorMap tmX,      // 5-D: [hi|l
       // this thread's X values: column j, the 64 rows of half nh2 of tile t2 (128 contiguous bytes), hi and lo
       const __half* xhp = p.Xh + ((size_t)((2 * sup + t2) * 2 + nh2) * p.d_pad + j) * 64;
       const __half* xlp = p.Xl + ((size_t)((2 * sup + t2) * 2 + nh2) * p.d_pad + j) * 64;
-      uint32_t xa[32], xb[32];                   // [0,16): hi, [16,32): lo of a 32-row step
+      uint32_t xa[32], xb[32];                   // [0,16): hi, [16,32): lo of a 32-row step (FP8: [16,24) = 32 e5m2 bytes)
       ldg256(xhp, xa);                           // X does not depend on the MMA: in flight while waiting
       ldg256(xhp + 16, xa + 8);
-      ldg256(xlp, xa + 16);
-      ldg256(xlp + 16, xa + 24);
       ldg256(xhp + 32, xb);
       ldg256(xhp + 48, xb + 8);
-      ldg256(xlp + 32, xb + 16);
-      ldg256(xlp + 48, xb + 24);
+      if (FP8) {
+        const uint8_t* xl8 = p.Xl8 + ((size_t)(2 * sup + t2) * p.d_pad + j) * 128 + 64 * nh2;
+        ldg256(xl8, xa + 16);
+        ldg256(xl8 + 32, xb + 16);
+      } else {
+        ldg256(xlp, xa + 16);
+        ldg256(xlp + 16, xa + 24);
+        ldg256(xlp + 32, xb + 16);
+        ldg256(xlp + 48, xb + 24);
+      }
       float ge = 0.0f, gm = 0.0f;
       auto compute = [&](const uint32_t* x, int part) {
         const float* rbp = &misc->rb[itp & 1][128 * t2 + 64 * nh2 + 32 * part];
@@ -1023,8 +1080,18 @@ glm_fast_pair_kernel(const __grid_constant__ CUtensorMap tmX,      // 5-D: [hi|l
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const float2 fh2 = __half22float2(*reinterpret_cast<const __half2*>(&x[e]));
-          const float2 fl2 = __half22float2(*reinterpret_cast<const __half2*>(&x[16 + e]));
-          const float x0 = fh2.x + fl2.x, x1 = fh2.y + fl2.y;
+          float x0, x1;
+          if (FP8) {
+            // an e5m2 byte is the high byte of the fp16 with the same value: spread two bytes into an fp16 pair
+            const uint32_t h2 = __byte_perm(x[16 + (e >> 1)], 0u, (e & 1) ? 0x3424u : 0x1404u);
+            const float2 fl2 = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+            x0 = fmaf(fl2.x, p.xl_scale, fh2.x);
+            x1 = fmaf(fl2.y, p.xl_scale, fh2.y);
+          } else {
+            const float2 fl2 = __half22float2(*reinterpret_cast<const __half2*>(&x[16 + e]));
+            x0 = fh2.x + fl2.x;
+            x1 = fh2.y + fl2.y;
+          }
           const float2 rb2 = *reinterpret_cast<const float2*>(rbp + 2 * e);
           ge = fmaf(x0, tv[2 * e], ge);
           ge = fmaf(x1, tv[2 * e + 1], ge);
@@ -1236,11 +1303,27 @@ __global__ void fast_prepare_x_kernel(const double* __restrict__ X, int64_t ldx,
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(absmax), __float_as_int(mx));
 }
 
+// e5m2 copies of the split X for the fp8 correction passes, [X_l * 2^ax | X_h * 2^-bx][tile][d_pad][128 n] (one 128-byte row =
+// the 128 rows of a tile for one column j: a single MN group of the 8-bit MN-major operand)
+__global__ void fast_prepare_x8_kernel(const __half* __restrict__ Xh, const __half* __restrict__ Xl, int64_t numTiles, int d_pad,
+                                       float sl, float sh, uint8_t* __restrict__ X8) {
+  const int64_t total = numTiles * (int64_t)d_pad * 128;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i & 127);
+    const int64_t tj = i >> 7;                       // tile * d_pad + j
+    const int64_t t = tj / d_pad;
+    const int j = (int)(tj - t * d_pad);
+    const size_t o = (((size_t)t * 2 + (n >> 6)) * d_pad + j) * 64 + (n & 63);
+    X8[i] = to_e5m2(__half2float(Xl[o]) * sl);
+    X8[total + i] = to_e5m2(__half2float(Xh[o]) * sh);
+  }
+}
+
 // Theta^T hi/lo [4][d_pad][64], E [d_pad/64][256][64] (fp16) and weights, zero padded
 __global__ void fast_prepare_theta_kernel(const double* __restrict__ theta, const double* __restrict__ base,
                                           const double* __restrict__ w, int64_t S, int d, int d_pad,
                                           __half* __restrict__ Th, __half* __restrict__ Tl, __half* __restrict__ E,
-                                          float* __restrict__ wf) {
+                                          float* __restrict__ wf, uint8_t* __restrict__ T8, int ax, int bx) {
   PDL_SYNC();
   const int64_t total = (int64_t)kSP * d_pad;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1259,7 +1342,13 @@ __global__ void fast_prepare_theta_kernel(const double* __restrict__ theta, cons
       const __half hi = __float2half_rn(t);
       const size_t o = ((size_t)(s >> 6) * d_pad + j) * 64 + (s & 63);
       Th[o] = hi;
-      Tl[o] = __float2half_rn(t - __half2float(hi));
+      const __half lo = __float2half_rn(t - __half2float(hi));
+      Tl[o] = lo;
+      if (T8) {
+        const size_t o8 = ((size_t)(s >> 7) * d_pad + j) * 128 + (s & 127);
+        T8[o8] = to_e5m2(__half2float(hi) * exp2f((float)-ax));
+        T8[(size_t)2 * d_pad * 128 + o8] = to_e5m2(__half2float(lo) * exp2f((float)bx));
+      }
     }
   }
   for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < kSP; s += (int64_t)gridDim.x * blockDim.x)
@@ -1319,7 +1408,7 @@ static EncodeTiledFn get_encode() {
 // fp16 tensor of 128-byte rows (innermost dimension 64), 128-byte swizzle.  dims/box are innermost first;
 // strides (bytes) are those of dims[1..rank-1].
 static bool encode_nd(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                      const uint32_t* box) {
+                      const uint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t gd[5], gs[4];
@@ -1330,7 +1419,7 @@ static bool encode_nd(CUtensorMap* map, const void* base, int rank, const uint64
     es[i] = 1;
     if (i + 1 < rank) gs[i] = strides[i];
   }
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = enc(map, dtype, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
@@ -1349,10 +1438,13 @@ struct FastModel {
   const __half* Xl;
   CUtensorMap tmXh, tmXl, tmXh2, tmXl2;      // one-CTA kernel: 2-D views
   CUtensorMap tmXP;                          // pair kernel: 5-D [hi|lo][tile][half][j][64]
+  const uint8_t* X8;                         // fp8 scheme: e5m2 [X_l 2^ax | X_h 2^-bx][tile][d_pad][128]
+  int ax, bx;
+  CUtensorMap tmXP16, tmXP8;                 // fp8 scheme: 4-D [tile][half][j][64] over X_h; 4-D [which][tile][j][128] bytes
 };
 
 struct FastLayout {
-  size_t off_Th, off_Tl, off_E, off_w, off_ll, off_gmu, off_ge, total;
+  size_t off_Th, off_Tl, off_E, off_w, off_ll, off_gmu, off_ge, off_T8, total;
   int grid;
 };
 
@@ -1370,6 +1462,7 @@ static void fast_layout(int64_t N, int d_pad, FastLayout& L) {
   L.off_ll = take((size_t)L.grid * kSP * sizeof(double));
   L.off_gmu = take((size_t)L.grid * d_pad * sizeof(double));
   L.off_ge = take((size_t)L.grid * d_pad * sizeof(double));
+  L.off_T8 = take((size_t)2 * kSP * d_pad);                    // e5m2 Theta_h8 | Theta_l8
   L.total = off;
 }
 
@@ -1383,7 +1476,7 @@ extern "C" size_t vb_glm_fast_model_bytes(int64_t N, int d) {
   if (N <= 0 || d <= 0) return 0;
   const int64_t N_pad = ceil_div(N, 2 * kBM) * 2 * kBM;        // whole 256-row super-tiles (CTA pairs)
   const int64_t d_pad = ceil_div(d, 256) * 256;
-  return (size_t)(2 * N_pad * d_pad * 2) + 1024;
+  return (size_t)(2 * N_pad * d_pad * 2) + 1024 + (size_t)(2 * N_pad * d_pad);       // fp16 hi | lo, absmax, e5m2 X_l8 | X_h8
 }
 
 extern "C" size_t vb_glm_fast_workspace_bytes(int64_t N, int d, int64_t S) {
@@ -1419,14 +1512,30 @@ extern "C" int vb_glm_fast_create(void** handle, const double* X, int64_t ldx, c
   fast_prepare_x_kernel<<<sm_count() * 8, 256, 0, stream>>>(X, ldx, y, N, d, m->numTiles, m->d_pad, Xh, Xl, absmax);
   e = cudaGetLastError();
   if (e != cudaSuccess) { delete m; return set_cuda_error(e); }
-  if (absmax_host) {
-    e = cudaMemcpyAsync(absmax_host, absmax, sizeof(float), cudaMemcpyDeviceToHost, stream);
+  float amax = 0.0f;
+  {
+    e = cudaMemcpyAsync(&amax, absmax, sizeof(float), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) { delete m; return set_cuda_error(e); }
-    if (!(*absmax_host < 3.0e4f)) {
+    if (absmax_host) *absmax_host = amax;
+    if (absmax_host && !(amax < 3.0e4f)) {
       delete m;
       return set_error(VB_ERR_UNSUPPORTED, "glm_fast: |y*X| exceeds the fp16 operand range; use the float64 path");
     }
+  }
+  {
+    // fp8 correction operands: static power-of-two scales from the magnitude of the data (s = floor(log2 max|y X|)):
+    // X_l 2^ax sits ~2^-10 and X_h 2^-bx ~2^-8 for typical entries, leaving e5m2's 30 binades to Theta on the other side
+    int sexp = 0;
+    if (amax > 0.0f) frexpf(amax, &sexp), sexp -= 1;
+    m->ax = 4 - sexp;
+    m->bx = 6 + sexp;
+    uint8_t* X8 = reinterpret_cast<uint8_t*>(model_mem) + (size_t)elems * 4 + 1024;
+    m->X8 = X8;
+    fast_prepare_x8_kernel<<<sm_count() * 8, 256, 0, stream>>>(Xh, Xl, m->numTiles, m->d_pad, exp2f((float)m->ax),
+                                                               exp2f((float)-m->bx), X8);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { delete m; return set_cuda_error(e); }
   }
   const uint64_t rows = (uint64_t)m->numTiles * 2 * m->d_pad;
   const uint64_t xd[5] = {64, (uint64_t)m->d_pad, 2, (uint64_t)m->numTiles, 2};
@@ -1434,6 +1543,17 @@ extern "C" int vb_glm_fast_create(void** handle, const double* X, int64_t ldx, c
   const uint32_t xb[5] = {64, 32, 2, 1, 2};
   if (!encode_2d(&m->tmXh, Xh, rows, 32) || !encode_2d(&m->tmXl, Xl, rows, 32) || !encode_2d(&m->tmXh2, Xh, rows, 64) ||
       !encode_2d(&m->tmXl2, Xl, rows, 64) || !encode_nd(&m->tmXP, Xh, 5, xd, xs, xb)) {
+    delete m;
+    return set_error(VB_ERR_CUDA, "glm_fast_create: cuTensorMapEncodeTiled failed");
+  }
+  const uint64_t x16d[4] = {64, (uint64_t)m->d_pad, 2, (uint64_t)m->numTiles};
+  const uint64_t x16s[3] = {128, (uint64_t)m->d_pad * 128, (uint64_t)m->d_pad * 256};
+  const uint32_t x16b[4] = {64, 32, 2, 1};
+  const uint64_t x8d[4] = {128, (uint64_t)m->d_pad, (uint64_t)m->numTiles, 2};
+  const uint64_t x8s[3] = {128, (uint64_t)m->d_pad * 128, (uint64_t)elems};
+  const uint32_t x8b[4] = {128, 32, 1, 2};
+  if (!encode_nd(&m->tmXP16, Xh, 4, x16d, x16s, x16b) ||
+      !encode_nd(&m->tmXP8, m->X8, 4, x8d, x8s, x8b, CU_TENSOR_MAP_DATA_TYPE_UINT8)) {
     delete m;
     return set_error(VB_ERR_CUDA, "glm_fast_create: cuTensorMapEncodeTiled failed");
   }
@@ -1472,6 +1592,9 @@ int fast_operands(void* handle, void* workspace, size_t workspace_bytes, FastOpe
   ops->Tl = reinterpret_cast<__half*>(ws + L.off_Tl);
   ops->E = reinterpret_cast<__half*>(ws + L.off_E);
   ops->wf = reinterpret_cast<float*>(ws + L.off_w);
+  ops->T8 = reinterpret_cast<uint8_t*>(ws + L.off_T8);
+  ops->ax = m->ax;
+  ops->bx = m->bx;
   return VB_OK;
 }
 
@@ -1490,7 +1613,9 @@ int fast_launch(void* handle, void* workspace, size_t workspace_bytes, int S, in
 
   static thread_local const void* cached_ws = nullptr;
   static thread_local int cached_dpad = 0;
-  static thread_local CUtensorMap tmTh, tmTl, tmE, tmTP, tmEP;
+  static thread_local CUtensorMap tmTh, tmTl, tmE, tmTP, tmEP, tmTP16, tmTP8;
+  // VB_FAST_FP8=0 selects the three-fp16-pass GEMM1 (A/B measurements)
+  static const bool use_fp8 = [] { const char* e = getenv("VB_FAST_FP8"); return !(e && e[0] == '0'); }();
   if (cached_ws != workspace || cached_dpad != m->d_pad) {
     const uint64_t dp = (uint64_t)m->d_pad;
     const uint64_t td[4] = {64, dp, 4, 2}, ts[3] = {128, dp * 128, dp * 512};      // Tl follows Th
@@ -1503,6 +1628,13 @@ int fast_launch(void* handle, void* workspace, size_t workspace_bytes, int S, in
         !encode_2d(&tmE, ops.E, (dp / 64) * kSP, 64) || !encode_nd(&tmTP, ops.Th, 4, td, ts, tb) ||
         !encode_nd(&tmEP, ops.E, 3, ed, es, eb))
       return set_error(VB_ERR_CUDA, "glm_fast_sweep: cuTensorMapEncodeTiled failed");
+    const uint64_t t16d[3] = {64, dp, 4}, t16s[2] = {128, dp * 128};
+    const uint32_t t16b[3] = {64, 32, 2};
+    const uint64_t t8d[4] = {128, dp, 2, 2}, t8s[3] = {128, dp * 128, dp * 256};
+    const uint32_t t8b[4] = {128, 32, 1, 2};
+    if (!encode_nd(&tmTP16, ops.Th, 3, t16d, t16s, t16b) ||
+        !encode_nd(&tmTP8, ops.T8, 4, t8d, t8s, t8b, CU_TENSOR_MAP_DATA_TYPE_UINT8))
+      return set_error(VB_ERR_CUDA, "glm_fast_sweep: cuTensorMapEncodeTiled failed (fp8 operands)");
     cached_ws = workspace;
     cached_dpad = m->d_pad;
   }
@@ -1522,6 +1654,8 @@ int fast_launch(void* handle, void* workspace, size_t workspace_bytes, int S, in
   p.tim = debug ? reinterpret_cast<long long*>(debug + (size_t)49152 * L.grid) : nullptr;
   p.Xh = m->Xh;
   p.Xl = m->Xl;
+  p.Xl8 = m->X8;
+  p.xl_scale = exp2f((float)-m->ax);
   p.uniform_w = uniform_w;
   // kernel choice: the CTA-pair kernel unless the device cannot co-schedule clusters of two such CTAs
   // (VB_FAST_KERNEL=single forces the one-CTA kernel, for A/B measurements)
@@ -1537,7 +1671,8 @@ int fast_launch(void* handle, void* workspace, size_t workspace_bytes, int S, in
     std::lock_guard<std::mutex> lock(mu);
     if (!ready[dev]) {
       VB_CUDA(cudaFuncSetAttribute(glm_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      VB_CUDA(cudaFuncSetAttribute(glm_fast_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      VB_CUDA(cudaFuncSetAttribute(glm_fast_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      VB_CUDA(cudaFuncSetAttribute(glm_fast_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
       const char* env = getenv("VB_FAST_KERNEL");
       int nc = 0;
       if (!(env && strcmp(env, "single") == 0)) {
@@ -1552,7 +1687,7 @@ int fast_launch(void* handle, void* workspace, size_t workspace_bytes, int S, in
         qa[0].val.clusterDim.z = 1;
         qc.attrs = qa;
         qc.numAttrs = 1;
-        if (cudaOccupancyMaxActiveClusters(&nc, glm_fast_pair_kernel, &qc) != cudaSuccess) {
+        if (cudaOccupancyMaxActiveClusters(&nc, glm_fast_pair_kernel<true>, &qc) != cudaSuccess) {
           cudaGetLastError();
           nc = 0;
         }
@@ -1582,7 +1717,10 @@ int fast_launch(void* handle, void* workspace, size_t workspace_bytes, int S, in
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = 2;
-    VB_CUDA(cudaLaunchKernelEx(&cfg, glm_fast_pair_kernel, m->tmXP, tmTP, tmEP, p));
+    if (use_fp8)
+      VB_CUDA(cudaLaunchKernelEx(&cfg, glm_fast_pair_kernel<true>, m->tmXP16, tmTP16, tmEP, m->tmXP8, tmTP8, p));
+    else
+      VB_CUDA(cudaLaunchKernelEx(&cfg, glm_fast_pair_kernel<false>, m->tmXP, tmTP, tmEP, m->tmXP8, tmTP8, p));
     nblk_ll = 2 * clusters;
     nblk_g = clusters;              // one row of gradient partials per pair (a CTA owns half of the columns)
   } else {
@@ -1619,7 +1757,7 @@ extern "C" int vb_glm_fast_sweep(void* handle, const double* theta, const double
   int rc = fast_operands(handle, workspace, workspace_bytes, &ops);
   if (rc) return rc;
   VB_CUDA(launch_pdl(fast_prepare_theta_kernel, dim3(128), dim3(256), stream, theta, want_grad ? base : nullptr, w, S, m->d, m->d_pad,
-                     ops.Th, ops.Tl, ops.E, ops.wf));
+                     ops.Th, ops.Tl, ops.E, ops.wf, ops.T8, ops.ax, ops.bx));
   FastPartials parts;
   rc = fast_launch(handle, workspace, workspace_bytes, (int)S, want_grad, ll_total_only, w ? 0 : 1, debug, stream, &parts);
   if (rc) return rc;
