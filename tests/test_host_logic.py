@@ -191,6 +191,29 @@ def test_fast_path_numerics_scheme_emulated():
     e3, e1 = err(z3), err(z1)
     assert e3 < 3e-5, e3
     assert e1 > 1e-4, e1
+    # the shipped form of GEMM1: the two correction products on e5m2 operands with reciprocal power-of-two scales
+    # (X_l 2^ax)(Theta_h 2^-ax) + (X_h 2^-bx)(Theta_l 2^bx), accumulated in the same fp32 sum; E2 takes X as
+    # X_h + e5m2(X_l 2^ax) 2^-ax.  Must stay well inside 1e-4, while dropping a correction product does not.
+    import torch
+
+    def e5m2(v, scale):
+        t = torch.from_numpy(np.ascontiguousarray(v * np.float32(scale), dtype=np.float32))
+        return (t.to(torch.float8_e5m2).to(torch.float32).numpy() / np.float32(scale)).astype(np.float32)
+
+    ax, bx = 2, 8                                   # what vb_glm_fast_create derives for max|y X| in [4, 8)
+    Xl8 = e5m2(Xl, 2.0 ** ax)
+    z8 = Xh @ Th.T + Xl8 @ e5m2(Th, 2.0 ** -ax).T + e5m2(Xh, 2.0 ** -bx) @ e5m2(Tl, 2.0 ** bx).T
+    Xe2 = Xh.astype(np.float64) + Xl8.astype(np.float64)
+    z = z8.astype(np.float32)
+    t = np.exp2(-np.abs(z) * np.float32(1.4426950408889634))
+    r = (np.where(z >= 0, t, np.float32(1.0)) / (1 + t)).astype(np.float32)
+    sp = np.maximum(-z, 0) + np.log2(1 + t) * np.float32(0.6931471805599453)
+    T = r.astype(np.float16).astype(np.float32) @ base.astype(np.float32)
+    e8 = max(relerr(-sp.astype(np.float64).sum(axis=0), ll0), relerr(Xe2.T @ r.astype(np.float64).sum(axis=1), gmu0),
+             relerr((Xe2 * T.astype(np.float64)).sum(axis=0), ge0))
+    e2 = err(Xh @ Th.T + Xh @ Tl.T)                 # without X_l . Theta_h
+    assert e8 < 4e-5, e8
+    assert e2 > 2 * e8, (e2, e8)
 
 
 def test_product_never_touches_the_oracle_and_needs_its_library(tmp_path):
