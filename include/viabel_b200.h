@@ -101,7 +101,8 @@ int vb_glm_sweep_f64(const double* X, int64_t ldx, const double* y, int64_t N, i
 /* ---------------------------------------------------------------------------------------
  * GLM model plugin, tensor-core fast path (logistic link; tolerance 1e-4 relative).
  * Same contract and outputs (float64 sums) as vb_glm_sweep_f64, but the two contractions run
- * as tcgen05.mma on fp16 hi+lo operand splits fed by TMA, with fp32 accumulators in TMEM.
+ * as tcgen05.mma on fp16 hi+lo operand splits fed by TMA (the two correction products of the first contraction on
+ * e5m2 copies, kind::f8f6f4), with fp32 accumulators in TMEM.
  *
  * vb_glm_fast_create: one-off preprocessing of the model data into `model_mem` (1024-byte
  *   aligned device memory of vb_glm_fast_model_bytes(N,d) bytes, owned by the caller and kept

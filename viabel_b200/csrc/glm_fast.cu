@@ -4,6 +4,8 @@
 // Per 128-observation tile, one persistent CTA per SM:
 //   GEMM1  Z[n,s]  = sum_j Xy[n,j] Theta[s,j]        M=128 (n), N=256 (s), K=d
 //          three fp16 passes  Xh.Th + Xl.Th + Xh.Tl  (Xy = y*X and Theta split hi+lo: 22-bit operands)
+//          (the CTA-pair kernel, the default, runs the two correction products Xl.Th and Xh.Tl on e5m2 copies with
+//          reciprocal power-of-two scales as kind::f8f6f4 MMAs: see glm_fast_pair_kernel)
 //   E1     link epilogue out of TMEM: ll[s] += -softplus(-z), R[n,s] = w_s*sigmoid(-z) -> fp16 tile in
 //          shared memory (the N x S logits / residuals never touch HBM), rbar[n] = sum_s R[n,s]
 //   GEMM2  Tt[j,n] = sum_s E[s,j] R[n,s]             M=128 (j), N=128 (n), K=256 (s); A = E (MN-major)
