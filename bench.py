@@ -605,8 +605,10 @@ def run_b200(args):
                 'bf16_peak_tflops': bf16_peak, 'bf16_peak_source': how,
                 'bf16_peak_sustained_tflops': bf16_sus,
                 'frac_bf16_algorithmic': achieved / bf16_sus,
-                'frac_bf16_executed': (2.0 * achieved / bf16_sus) if path == 'fast' else None,
-                'executed_note': 'fp16 hi/lo operand splits: 3 + 1 tensor passes = 2x the algorithmic flops',
+                'frac_bf16_executed': ((1.5 if os.environ.get('VB_FAST_FP8', '1') != '0' else 2.0) * achieved / bf16_sus)
+                                      if path == 'fast' else None,
+                'executed_note': ('GEMM1 = one fp16 pass + two e5m2 correction passes at twice the fp16 rate, GEMM2 = one fp16 '
+                                  'pass: 1.5x the algorithmic flops in fp16-pass units (VB_FAST_FP8=0: three fp16 passes, 2x)'),
                 'algorithmic_flops_per_launch': flops, 'algorithmic_bytes_per_launch': (hi - lo) * d * 4.0 if path == 'fast'
                 else (hi - lo) * d * 8.0}
 
