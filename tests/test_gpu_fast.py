@@ -174,3 +174,30 @@ def test_c2_full_size_vs_oracle(vb, vo):
     model.enable_fast_path()
     v, gr = obj(vp, base=base)
     assert relerr(v, v0) < TOL_FAST and relerr(gr, g0) < TOL_FAST, (relerr(v, v0), relerr(gr, g0))
+
+
+@pytest.mark.parametrize('kind', ['x1000', 'x0.001', 'outliers'])
+def test_fast_path_operand_scales(vb, vo, kind):
+    """The fp8 correction passes take static power-of-two operand scales from the typical magnitude of y*X: data far
+    from unit scale (with theta scaled inversely, so the logits are the same) and data with a few huge entries must
+    meet the same 1e-4 against the oracle."""
+    N, d, S = 20000, 128, 64
+    X, y, beta = logistic_problem(N, d, seed=77)
+    rs = np.random.RandomState(5)
+    base = _f16_exact(rs.randn(S, d))
+    scale = {'x1000': 1000.0, 'x0.001': 0.001, 'outliers': 1.0}[kind]
+    X = X * scale
+    beta = beta / scale
+    if kind == 'outliers':
+        for n, j in ((3, 5), (777, 100), (12345, 0), (19999, 127), (5000, 64)):
+            X[n, j] = 2.0e4
+    prior = 10.0 / scale
+    model = vb.LogisticRegression(X, y, prior_scale=prior).enable_fast_path()
+    oracle_model = lambda th: vo.logistic_logp_grad(th, X, y, prior)
+    approx = vb.MFGaussian(d)
+    for name, vp in (('conv', np.concatenate([beta * (1 + 0.01 * rs.randn(d)), np.log(np.exp(-3.5) / scale) + 0.1 * rs.randn(d)])),
+                     ('wide', np.concatenate([0.5 * beta, np.log(np.exp(-1.0) / scale) * np.ones(d)]))):
+        v, gr = vb.ExclusiveKL(approx, model, S)(vp, base=base)
+        v0, g0, _ = vo.exclusive_kl_meanfield(vp, base, oracle_model)
+        assert relerr(v, v0) < TOL_FAST, (kind, name, 'value', relerr(v, v0))
+        assert relerr(gr[:d], g0[:d]) < TOL_FAST and relerr(gr[d:], g0[d:]) < TOL_FAST, (kind, name, relerr(gr[:d], g0[:d]), relerr(gr[d:], g0[d:]))

@@ -250,11 +250,13 @@ __global__ void __launch_bounds__(256) mf_pre_kernel(StepCfg c, StepPtrs p, fast
     const int jj = threadIdx.x >> 2, q4 = (threadIdx.x & 3) * 4;
     __align__(8) __half hi[4];
     __align__(8) __half lo[4];
+    float lof[4];                      // residual in fp32: the e5m2 copy must not inherit an fp16 underflow of lo
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float t = tt[jj][q4 + u];
       hi[u] = __float2half_rn(t);
-      lo[u] = __float2half_rn(t - __half2float(hi[u]));
+      lof[u] = t - __half2float(hi[u]);
+      lo[u] = __float2half_rn(lof[u]);
     }
     const int sg = s0 + q4;                                     // 16 | 64: the 4 samples stay inside one 64-group
     const size_t o = ((size_t)(sg >> 6) * c.d_pad + (j0 + jj)) * 64 + (sg & 63);
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(256) mf_pre_kernel(StepCfg c, StepPtrs p, fast
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         h8 |= (uint32_t)fast::to_e5m2(__half2float(hi[u]) * sh) << (8 * u);
-        l8 |= (uint32_t)fast::to_e5m2(__half2float(lo[u]) * sl) << (8 * u);
+        l8 |= (uint32_t)fast::to_e5m2(lof[u] * sl) << (8 * u);
       }
       const size_t o8 = ((size_t)(sg >> 7) * c.d_pad + (j0 + jj)) * 128 + (sg & 127);
       *reinterpret_cast<uint32_t*>(ops.T8 + o8) = h8;

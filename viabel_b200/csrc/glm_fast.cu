@@ -1273,6 +1273,7 @@ __global__ void fast_prepare_x_kernel(const double* __restrict__ X, int64_t ldx,
                                       float* __restrict__ absmax) {
   __shared__ float tile[32][33];
   float mx = 0.0f;
+  double sq = 0.0;                         // sum of squares: the typical magnitude sets the fp8 operand scales
   // 32 x 32 transposes: coalesced reads along j, coalesced writes along n
   const int64_t blocksPerTile = (int64_t)(d_pad / 32) * 4;
   const int64_t total = numTiles * blocksPerTile;
@@ -1289,6 +1290,7 @@ __global__ void fast_prepare_x_kernel(const double* __restrict__ X, int64_t ldx,
       if (n < N && j < d) v = (float)(X[n * ldx + j] * y[n]);
       tile[r][tx] = v;
       mx = fmaxf(mx, fabsf(v));
+      sq += (double)v * (double)v;
     }
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
@@ -1303,6 +1305,9 @@ __global__ void fast_prepare_x_kernel(const double* __restrict__ X, int64_t ldx,
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(absmax), __float_as_int(mx));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(reinterpret_cast<double*>(absmax + 2), sq);
 }
 
 // e5m2 copies of the split X for the fp8 correction passes, [X_l * 2^ax | X_h * 2^-bx][tile][d_pad][128 n] (one 128-byte row =
@@ -1344,12 +1349,13 @@ __global__ void fast_prepare_theta_kernel(const double* __restrict__ theta, cons
       const __half hi = __float2half_rn(t);
       const size_t o = ((size_t)(s >> 6) * d_pad + j) * 64 + (s & 63);
       Th[o] = hi;
-      const __half lo = __float2half_rn(t - __half2float(hi));
+      const float lof = t - __half2float(hi);       // fp32 residual: the e5m2 copy must not inherit an fp16 underflow
+      const __half lo = __float2half_rn(lof);
       Tl[o] = lo;
       if (T8) {
         const size_t o8 = ((size_t)(s >> 7) * d_pad + j) * 128 + (s & 127);
         T8[o8] = to_e5m2(__half2float(hi) * exp2f((float)-ax));
-        T8[(size_t)2 * d_pad * 128 + o8] = to_e5m2(__half2float(lo) * exp2f((float)bx));
+        T8[(size_t)2 * d_pad * 128 + o8] = to_e5m2(lof * exp2f((float)bx));
       }
     }
   }
@@ -1509,16 +1515,18 @@ extern "C" int vb_glm_fast_create(void** handle, const double* X, int64_t ldx, c
   float* absmax = reinterpret_cast<float*>(Xl + elems);
   m->Xh = Xh;
   m->Xl = Xl;
-  cudaError_t e = cudaMemsetAsync(absmax, 0, sizeof(float), stream);
+  cudaError_t e = cudaMemsetAsync(absmax, 0, 16, stream);          // [0]: max |y X| (float), [2..3]: sum of squares (double)
   if (e != cudaSuccess) { delete m; return set_cuda_error(e); }
   fast_prepare_x_kernel<<<sm_count() * 8, 256, 0, stream>>>(X, ldx, y, N, d, m->numTiles, m->d_pad, Xh, Xl, absmax);
   e = cudaGetLastError();
   if (e != cudaSuccess) { delete m; return set_cuda_error(e); }
   float amax = 0.0f;
+  float stats[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   {
-    e = cudaMemcpyAsync(&amax, absmax, sizeof(float), cudaMemcpyDeviceToHost, stream);
+    e = cudaMemcpyAsync(stats, absmax, 16, cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) { delete m; return set_cuda_error(e); }
+    amax = stats[0];
     if (absmax_host) *absmax_host = amax;
     if (absmax_host && !(amax < 3.0e4f)) {
       delete m;
@@ -1526,12 +1534,20 @@ extern "C" int vb_glm_fast_create(void** handle, const double* X, int64_t ldx, c
     }
   }
   {
-    // fp8 correction operands: static power-of-two scales from the magnitude of the data (s = floor(log2 max|y X|)):
-    // X_l 2^ax sits ~2^-10 and X_h 2^-bx ~2^-8 for typical entries, leaving e5m2's 30 binades to Theta on the other side
-    int sexp = 0;
-    if (amax > 0.0f) frexpf(amax, &sexp), sexp -= 1;
-    m->ax = 4 - sexp;
-    m->bx = 6 + sexp;
+    // fp8 correction operands: static power-of-two scales from the TYPICAL magnitude of the data (r = round(log2 rms),
+    // not the maximum: one outlier must not push the other entries' residuals below e5m2's range): X_l 2^ax sits near
+    // 2^-10 and X_h 2^-bx near 2^-8 for typical entries, which leaves e5m2's 30 binades to Theta on the other side
+    // (|theta| ~ 1 / (rms sqrt(d)) for logits of order one); clamped so that the largest entry cannot overflow e5m2.
+    double sumsq;
+    memcpy(&sumsq, stats + 2, sizeof(double));
+    const double rms = sqrt(sumsq / ((double)N * (double)d));
+    int r = 0, sexp = 0;
+    if (rms > 0.0) r = (int)lrint(log2(rms));
+    if (amax > 0.0f) frexpf(amax, &sexp);                       // amax < 2^sexp
+    m->ax = 2 - r;
+    m->bx = 8 + r;
+    if (m->ax > 26 - sexp) m->ax = 26 - sexp;                    // |X_l| <= 2^-11 max|X|:  X_l 2^ax < 2^15
+    if (m->bx < sexp - 15) m->bx = sexp - 15;                    // X_h 2^-bx < 2^15
     uint8_t* X8 = reinterpret_cast<uint8_t*>(model_mem) + (size_t)elems * 4 + 1024;
     m->X8 = X8;
     fast_prepare_x8_kernel<<<sm_count() * 8, 256, 0, stream>>>(Xh, Xl, m->numTiles, m->d_pad, exp2f((float)m->ax),
