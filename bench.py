@@ -647,7 +647,8 @@ def run_b200(args):
         'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
         'settle_steps': 16 + args.steps + n_sus,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-        'dtype': 'f64' if path == 'f64' else 'f16x2-split/f32',
+        'dtype': 'f64' if path == 'f64' else ('f16+e5m2-corrections/f32' if os.environ.get('VB_FAST_FP8', '1') != '0'
+                                             else 'f16x2-split/f32'),
         'data': 'synthetic',
         'config': {'workload': workload_name(N, d, S),
                    'path': path, 'rows_per_rank': hi - lo, 'l2': 'inputs larger than L2 (X = %.2f GB per rank)'
