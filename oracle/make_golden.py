@@ -375,6 +375,16 @@ def gen_psis():
     print('psis: %d arrays' % len(out))
 
 
+def gen_psisloo():
+    rs = np.random.RandomState(4711)
+    n, m = 4000, 5
+    # Gaussian log-likelihood terms of different widths: raw weights exp(c z^2 / 2) with tail index k ~ c
+    log_lik = -0.5 * np.linspace(0.1, 0.9, m)[None, :] * rs.randn(n, m) ** 2 - rs.gamma(2.0, 0.3, size=(1, m))
+    loo, loos, ks = ref_psis.psisloo(log_lik.copy())
+    np.savez_compressed(os.path.join(OUT, 'psisloo.npz'), log_lik=log_lik, loo=loo, loos=loos, ks=ks)
+    print('psisloo: 4 arrays')
+
+
 def gen_diagnostics():
     out = {}
     samples, lw = diag_problem()
@@ -598,6 +608,7 @@ if __name__ == '__main__':
     gen_lr_gaussian()
     gen_optimizers()
     gen_psis()
+    gen_psisloo()
     gen_diagnostics()
     gen_mc_diagnostics()
     gen_dis()

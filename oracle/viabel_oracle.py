@@ -914,6 +914,15 @@ def psislw(lw, Reff=1.0):
     return out, ks
 
 
+def psisloo(log_lik, Reff=1.0):
+    """_psis.py:69-110: PSIS leave-one-out from n x m log-likelihood draws.  Returns (loo, loos[m], ks[m])."""
+    ll = np.asarray(log_lik, dtype=np.float64)
+    lw, ks = psislw(-ll, Reff)
+    lw = lw + ll
+    loos = np.array([sumlogs(lw[:, i]) for i in range(lw.shape[1])])
+    return loos.sum(), loos, ks
+
+
 # --------------------------------------------------------------------------
 # Divergence / Wasserstein / error bounds (diagnostics.py:13-219)
 # --------------------------------------------------------------------------

@@ -460,3 +460,36 @@ def test_gemm_f64_epilogues(vb, ta, tb, M, N, K):
     vb._lib.check(lib.vb_gemm_f64(ta, tb, M, N, K, 1.0, ptr(Ad), Ad.shape[1], ptr(Bd), Bd.shape[1], ptr(C), N, None, None, None,
                                   None, None, vb._lib.stream()))
     assert relerr(C.cpu().numpy(), Aop @ Bop) < 1e-13
+
+
+def test_stan_model_adapter(vb, vo):
+    """StanModel around a fit-like object (host log_prob / grad_log_prob, one row at a time): values, per-sample
+    gradients and an ExclusiveKL evaluation against the oracle on the same Gaussian target."""
+    d, S = 6, 40
+    rs = np.random.RandomState(12)
+    mean, sd = rs.randn(d), 0.5 + rs.rand(d)
+
+    class Fit:
+        def log_prob(self, x):
+            return float(np.sum(-0.5 * ((np.asarray(x) - mean) / sd) ** 2 - np.log(sd) - 0.5 * np.log(2 * np.pi)))
+
+        def grad_log_prob(self, x):
+            return -(np.asarray(x) - mean) / sd ** 2
+
+        def constrain_pars(self, x):
+            return x
+
+    model = vb.StanModel(Fit())
+    theta = rs.randn(S, d)
+    ref = np.array([Fit().log_prob(t) for t in theta])
+    assert relerr(model(theta), ref) < TOL64
+    assert abs(model(theta[0]) - ref[0]) < 1e-12
+    lp, g = model.logp_and_grad(torch.as_tensor(theta, device='cuda'))
+    assert relerr(lp.cpu().numpy(), ref) < TOL64
+    assert relerr(g.cpu().numpy(), -(theta - mean) / sd ** 2) < TOL64
+    approx = vb.MFGaussian(d)
+    base = rs.randn(S, d)
+    vp = np.concatenate([0.3 * rs.randn(d), -0.5 + 0.1 * rs.randn(d)])
+    v, gr = vb.ExclusiveKL(approx, model, S)(vp, base=base)
+    v0, g0, _ = vo.exclusive_kl_meanfield(vp, base, lambda th: vo.gauss_target_logp_grad(th, mean, sd))
+    assert relerr(v, v0) < TOL64 and relerr(gr, g0) < TOL64

@@ -136,6 +136,19 @@ def test_psislw_moments_only_one_pass(vb, vo, name, variant):
         assert relerr(r1[0], k_ref) < TOL
 
 
+def test_psisloo_golden(vb, golden):
+    """PSIS leave-one-out (_psis.py:69-110) against the unmodified reference: every column of -log_lik is one
+    PSIS problem; loo, the per-term loos and the tail indices to 1e-10."""
+    g = golden('psisloo')
+    ll = g['log_lik']
+    keep = ll.copy()
+    loo, loos, ks = vb.psisloo(ll)
+    assert np.array_equal(ll, keep)                        # the caller's array is not touched
+    assert relerr(loo, g['loo']) < TOL and relerr(loos, g['loos']) < TOL and relerr(ks, g['ks']) < TOL
+    with pytest.raises(ValueError):
+        vb.psisloo(np.zeros(5))
+
+
 @pytest.mark.parametrize('n', [5000, 300001])
 def test_psislw_nan_and_minus_inf(vb, vo, n):
     """Non-finite log-weights, as the reference treats them (_psis.py run unmodified: a NaN makes every output NaN

@@ -235,3 +235,25 @@ def test_product_never_touches_the_oracle_and_needs_its_library(tmp_path):
     out = subprocess.run([sys.executable, '-c', 'import viabel_b200'], cwd=str(tmp_path), capture_output=True, text=True,
                          timeout=120)
     assert out.returncode != 0 and 'ImportError' in out.stderr and 'libviabel_b200' in out.stderr
+
+
+def test_stan_model_adapter_host_side():
+    """StanModel (models.py:80-100) wraps a PyStan fit object: construction and `constrain` are host-only (the
+    log density itself needs CUDA tensors: tests/test_gpu_elbo.py::test_stan_model_adapter)."""
+    import viabel_b200 as vb
+
+    class Fit:                                   # the three methods of StanFit4model the reference uses
+        def log_prob(self, x):
+            return -0.5 * float(np.sum(np.asarray(x) ** 2))
+
+        def grad_log_prob(self, x):
+            return -np.asarray(x)
+
+        def constrain_pars(self, x):
+            return {'theta': np.asarray(x)}
+
+    m = vb.StanModel(Fit())
+    assert isinstance(m, vb.Model) and not m.supports_tempering
+    assert np.array_equal(m.constrain(np.arange(3.0))['theta'], np.arange(3.0))
+    with pytest.raises(NotImplementedError):
+        m.set_inverse_temperature(0.5)

@@ -188,6 +188,13 @@ def test_gpd_helpers(golden):
         vo.psislw(np.zeros((2, 2, 2)))
 
 
+def test_psisloo(golden):
+    g = golden('psisloo')
+    with np.errstate(all='ignore'):
+        loo, loos, ks = vo.psisloo(g['log_lik'])
+    assert relerr(loo, g['loo']) < TOL and relerr(loos, g['loos']) < TOL and relerr(ks, g['ks']) < TOL
+
+
 def test_diagnostics(golden):
     g = golden('diagnostics')
     samples, lw = diag_problem()

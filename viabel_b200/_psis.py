@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from ._tensor import F64, device, is_host, to_dev
 
-__all__ = ['psislw', 'psislw_device', 'psislw_sharded', 'PsisShard', 'gpdfitnew', 'gpinv', 'sumlogs']
+__all__ = ['psislw', 'psislw_device', 'psislw_sharded', 'PsisShard', 'psisloo', 'gpdfitnew', 'gpinv', 'sumlogs']
 
 R_KHAT, R_SIGMA, R_N2, R_CUTOFF, R_LSE, R_MAX, R_STATUS, R_SUMV, R_SUMEXP2V, R_M, R_NCAND, R_SMOOTHED = range(12)
 
@@ -266,6 +266,19 @@ def gpdfitnew(x, sort=True, sort_in_place=False, return_quadrature=False):
         kq = np.mean(np.log1p(-bsk[:, None] * xs), axis=1) * n / (n + 10) + 5 / (n + 10)
         return k, sigma, kq, w
     return k, sigma
+
+
+def psisloo(log_lik, **kwargs):
+    """PSIS leave-one-out log predictive densities (_psis.py:69-110): log_lik is n x m (n posterior draws of the m
+    log-likelihood terms); every column is one PSIS problem on the raw log-weights -log_lik.  Returns (loo, loos[m],
+    ks[m]); further keyword arguments go to psislw (Reff)."""
+    ll = np.asarray(log_lik, dtype=np.float64)
+    if ll.ndim != 2:
+        raise ValueError('log_lik must be an n x m array')
+    kwargs['overwrite_lw'] = True
+    lw, ks = psislw(np.asfortranarray(-ll), **kwargs)
+    loos = sumlogs(lw + ll, axis=0)
+    return loos.sum(), loos, ks
 
 
 def sumlogs(x, axis=None, out=None):

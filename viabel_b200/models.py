@@ -14,7 +14,7 @@ from . import _lib
 from ._tensor import F64, device, is_host, like_input, to_dev
 from .parallel import allreduce_sum_
 
-__all__ = ['Model', 'GLMModel', 'LogisticRegression', 'ProbitRegression', 'HierarchicalLinearRegression',
+__all__ = ['Model', 'StanModel', 'GLMModel', 'LogisticRegression', 'ProbitRegression', 'HierarchicalLinearRegression',
            'GaussianTarget', 'StudentTTarget']
 
 
@@ -78,6 +78,26 @@ class Model(object):
 
     def set_inverse_temperature(self, inverse_temp):
         raise NotImplementedError()
+
+
+class StanModel(Model):
+    """Adapter for a PyStan fit object (models.py:80-100).  The log density and its gradient are the fit's own
+    `log_prob` / `grad_log_prob`, evaluated on the host one row at a time as the reference does
+    (`_utils.vectorize_if_needed`): Stan is CPU code and outside the B200 path, so the samples round-trip through host
+    memory, while families, objectives, optimisers and diagnostics run on the device as for any `Model(log_density, grad)`."""
+
+    def __init__(self, fit):
+        self._fit = fit
+
+        def rows(f, x):
+            a = x.detach().cpu().numpy()
+            return np.stack([np.asarray(f(r), dtype=np.float64) for r in a])
+
+        super().__init__(lambda x: to_dev(rows(fit.log_prob, x).reshape(-1)),
+                         lambda x: to_dev(rows(fit.grad_log_prob, x).reshape(x.shape)))
+
+    def constrain(self, model_param):
+        return self._fit.constrain_pars(model_param)
 
 
 class GLMModel(Model):
